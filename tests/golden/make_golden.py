@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""Generate the committed golden vectors by running the UNMODIFIED reference in this container.
+
+    python tests/golden/make_golden.py            # writes tests/golden/*.npz, *.json
+
+Needs /root/reference (read-only).  The outputs are small fixtures that travel to the GPU
+box; the tests never read /root/reference themselves.  Inputs that are too large to commit
+(>= 1025^2) are regenerated from the seeds recorded in the fixture (numpy MT19937 is
+platform independent) and only the residual histories are stored.
+"""
+import contextlib
+import io
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_harness as H  # noqa: E402
+
+torch.set_num_threads(os.cpu_count())
+OUT = HERE
+
+
+def t2n(t):
+    return t.detach().cpu().numpy().copy()
+
+
+def keys_of(mesh):
+    n = mesh.nnode_edge
+    k = np.zeros(n * n, np.int64)
+    tot = np.zeros(n * n, np.int64)
+    for key, m in mesh.global_pattern_center.items():
+        k += key * np.asarray(m)
+        tot += np.asarray(m)
+    assert (tot == 1).all()
+    return k.reshape(n, n).astype(np.uint8)
+
+
+def gen_mesh():
+    H.load_reference()
+    from FEANet.mesh import MeshCenterInterface, MeshSquare
+
+    out = {}
+    for n in (4, 8, 16, 32, 64):
+        for shape in (0, 1):
+            m = MeshCenterInterface(2, [1, 20], n + 1, shape=shape)
+            out[f"keys_n{n}_s{shape}"] = keys_of(m)
+    for prop in ([1, 20], [1, 100], [3, 0.5]):
+        m = MeshCenterInterface(2, prop, 9)
+        out[f"ktab_{prop[0]}_{prop[1]}"] = np.stack([m.kernel_dict[k] for k in range(16)])
+    out["ktab_iso"] = MeshSquare(2, 9).kernel_dict[0]
+    np.savez_compressed(os.path.join(OUT, "mesh.npz"), **out)
+    print("mesh.npz", len(out))
+
+
+def gen_ops():
+    H.load_reference()
+    from FEANet.geo import Geometry
+    from FEANet.jacobi import JacobiBlock
+    from FEANet.mesh import MeshCenterInterface, MeshSquare
+    from FEANet.model import FNet, KNet
+
+    ns = H.notebook_namespace("M-FEANet-mg_test.ipynb", [1, 2, 3, 4, 5])
+    HNet = ns["HNet"]
+    hnet = HNet(3)
+    hnet.load_state_dict(torch.load(os.path.join(H.REF, "Model/learn_iterator/iso_poisson/iso_poisson_33x33.pth"),
+                                    weights_only=True))
+    hw = np.stack([t2n(l.weight).reshape(9) for l in hnet.convLayers])
+    M = H.load_reference_multigrid_module()
+    nsA = H.notebook_namespace("MM_Model_convergence.ipynb", [1, 2, 3, 4])
+
+    g = torch.Generator().manual_seed(20260)
+    out = {"hnet_w": hw}
+    for N in (9, 17, 33):
+        B = 2
+        u = torch.randn(B, 1, N, N, generator=g)
+        f = torch.randn(B, 1, N, N, generator=g)
+        out[f"u_{N}"], out[f"f_{N}"] = t2n(u), t2n(f)
+        # general (data) Dirichlet BC: ring values random, mask = interior ones (per-sample)
+        geo = Geometry(N)
+        bidx = geo.geometry_idx.repeat(B, 1, 1, 1).clone()
+        bval = torch.randn(B, 1, N, N, generator=g) * (1 - bidx)
+        out[f"bidx_{N}"], out[f"bval_{N}"] = t2n(bidx), t2n(bval)
+        for tag, mesh in (("iso", MeshSquare(2, N)), ("c20", MeshCenterInterface(2, [1, 20], N, shape=0)),
+                          ("s100", MeshCenterInterface(2, [1, 100], N, shape=1))):
+            knet = KNet(mesh)
+            fnet = FNet(2.0 / (N - 1))
+            jac = JacobiBlock(knet, mesh, 2 / 3., geo.geometry_idx, geo.boundary_value)
+            with torch.no_grad():
+                out[f"{tag}_Ku_{N}"] = t2n(knet(u))
+                out[f"{tag}_split_{N}"] = t2n(knet.split_x(u))
+                out[f"{tag}_dmat_{N}"] = t2n(jac.d_mat)
+                out[f"{tag}_jac1_{N}"] = t2n(jac.jacobi_convolution(u, f))
+                v = u
+                for _ in range(3):
+                    v = jac.jacobi_convolution(v, f)
+                out[f"{tag}_jac3_{N}"] = t2n(v)
+                jac2 = JacobiBlock(knet, mesh, 2 / 3., bidx, bval)
+                out[f"{tag}_dmatB_{N}"] = t2n(jac2.d_mat)
+                out[f"{tag}_jacbc1_{N}"] = t2n(jac2.jacobi_convolution(u, f))
+                v = u
+                for _ in range(2):
+                    v = jac2.jacobi_convolution(v, f)
+                out[f"{tag}_jacbc2_{N}"] = t2n(v)
+                if tag == "iso":
+                    out[f"fnet_{N}"] = t2n(fnet(u))
+                    out[f"fnet_w_{N}"] = t2n(fnet.net.weight).reshape(9)
+
+                # learned smoother HRelax (mg_test cell 5) on top of each jac (default and data BC)
+                class _G:  # duck-typed grid holder for HJacIterator
+                    pass
+
+                for bt, jj in (("", jac), ("bc", jac2)):
+                    gh = _G()
+                    gh.jac = jj
+                    it = ns["HJacIterator"](n=N - 1, hnet=hnet, grid=gh)
+                    out[f"{tag}_hjac{bt}1_{N}"] = t2n(it.HRelax(u, f, 1))
+                    out[f"{tag}_hjac{bt}2_{N}"] = t2n(it.HRelax(u, f, 2))
+                # residual
+                r = f - knet(u)
+                out[f"{tag}_res_{N}"] = t2n(r)
+                # 16-channel / 1-channel R and P of FEANet/multigrid.py with per-channel perturbed weights
+                C = knet.n_channel
+                if C == 16:
+                    P4 = torch.tensor([[1, 2, 1], [2, 4, 2], [1, 2, 1]], dtype=torch.float32) / 4.0
+                    R16 = torch.tensor([[1, 2, 1], [2, 4, 2], [1, 2, 1]], dtype=torch.float32) / 16.0
+                    conv = M.RestrictionNet(R16)
+                    deconv = M.ProlongationNet(P4)
+                    gp = torch.Generator().manual_seed(7 + N)
+                    conv.net.weight.data += 0.05 * torch.randn(conv.net.weight.shape, generator=gp)
+                    deconv.net.weight.data += 0.05 * torch.randn(deconv.net.weight.shape, generator=gp)
+                    out[f"{tag}_Rw_{N}"] = t2n(conv.net.weight).reshape(16, 9)
+                    out[f"{tag}_Pw_{N}"] = t2n(deconv.net.weight).reshape(16, 9)
+                    rF = knet.split_x(r)
+                    rFC = conv(rF[:, :, 1:-1, 1:-1].clone())
+                    rFC = torch.nn.functional.pad(rFC, (1, 1, 1, 1), "constant", 0)
+                    out[f"{tag}_restrictB_{N}"] = t2n(1.7 * rFC)
+                    # prolongation uses the COARSE level's knet for the split
+                    Nc = (N - 1) // 2 + 1
+                    shape = 0 if tag == "c20" else 1
+                    prop = [1, 20] if tag == "c20" else [1, 100]
+                    mesh_c = MeshCenterInterface(2, prop, Nc, shape=shape)
+                    knet_c = KNet(mesh_c)
+                    vc = torch.randn(B, 1, Nc, Nc, generator=g)
+                    out[f"{tag}_vc_{N}"] = t2n(vc)
+                    eF = deconv(knet_c.split_x(vc).clone())
+                    out[f"{tag}_prolongB_{N}"] = t2n(u + 0.9 * eF)
+        # variant A restrict / interpolate (iso notebook driver); needs a Multigrid instance of size N-1
+        np.random.seed(1)
+        with contextlib.redirect_stdout(io.StringIO()):
+            mgA = nsA["Multigrid"](N - 1)
+        with torch.no_grad():
+            out[f"restrictA_{N}"] = t2n(4 * mgA.Restrict(f))
+            Nc = (N - 1) // 2 + 1
+            vc = torch.randn(B, 1, Nc, Nc, generator=g)
+            out[f"vcA_{N}"] = t2n(vc)
+            out[f"prolongA_{N}"] = t2n(u + mgA.Interpolate(vc))
+    np.savez_compressed(os.path.join(OUT, "ops.npz"), **out)
+    print("ops.npz", len(out))
+
+
+def model_problem_u0(n, seed=123):
+    """MM_Model_convergence.ipynb cell 3 `random_data` with the (commented-out) seed enabled, cast to fp32."""
+    np.random.seed(seed)
+    coef = 100000 + 50000 * np.random.rand(2)
+    return (coef[0] * np.random.random((n + 1, n + 1)).astype("f") + coef[1]).astype(np.float32)
+
+
+def gen_solve():
+    nsA = H.notebook_namespace("MM_Model_convergence.ipynb", [1, 2, 3, 4])
+    MG = nsA["Multigrid"]
+    hist = {}
+    arrays = {}
+
+    def run(tag, n, L, v1v2, rec=True, n_iter=None, EPS=None, rhs_seed=None, keep_u=False):
+        t0 = time.time()
+        np.random.seed(123)
+        with contextlib.redirect_stdout(io.StringIO()):
+            p = MG(n, L)
+        p.initial_v = torch.from_numpy(model_problem_u0(n))
+        if rhs_seed is not None:
+            rs = np.random.RandomState(rhs_seed)
+            F = torch.from_numpy(rs.standard_normal((1, 1, n + 1, n + 1)).astype(np.float32))
+            with torch.no_grad():
+                p.grids[0].f = p.grids[0].fnet(F)
+            p.initial_v = torch.zeros(n + 1, n + 1)
+        with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+            res = p.Solve(list(v1v2), rec=rec, n_iter=n_iter, EPS=EPS)
+        hist[tag] = dict(n=n, L=L, v1v2=list(v1v2), rec=rec, n_iter=n_iter, EPS=EPS, rhs_seed=rhs_seed,
+                         res=[float(r) for r in res])
+        if keep_u:
+            arrays[tag + "_u"] = t2n(p.grids[0].v)
+        print(tag, len(res), "cycles", "%.1fs" % (time.time() - t0), res[:2], res[-1])
+
+    for n in (2, 4, 8, 16, 32):
+        run(f"modelA_n{n}_v11", n, None, (1, 1), n_iter=12, keep_u=(n <= 16))
+    run("modelA_n64_v11", 64, None, (1, 1), n_iter=20, keep_u=True)
+    run("modelA_n64_v11_iter", 64, None, (1, 1), rec=False, n_iter=8, keep_u=True)
+    for v in ((0, 1), (1, 0), (0, 2), (2, 0), (1, 2), (2, 1), (2, 2), (3, 3)):
+        run(f"modelA_n64_v{v[0]}{v[1]}", 64, None, v, n_iter=10)
+    run("modelA_n64_L4_v11", 64, 4, (1, 1), n_iter=20, keep_u=True)
+    run("modelA_n64_eps1e-6", 64, None, (1, 1), EPS=1e-6)
+    run("modelA_n64_rhs", 64, None, (1, 1), n_iter=12, rhs_seed=5, keep_u=True)
+    run("modelA_n256_v11", 256, None, (1, 1), n_iter=15)
+    run("modelA_n1024_L10", 1024, 10, (1, 1), n_iter=15)
+    run("modelA_n1024_L8", 1024, 8, (1, 1), n_iter=10)
+    run("modelA_n1024_rhs", 1024, 10, (1, 1), n_iter=8, rhs_seed=5)
+    if os.environ.get("MGFEA_GOLDEN_BIG", "1") == "1":
+        run("modelA_n4096_L12", 4096, 12, (1, 1), n_iter=13)
+
+    # fp64 reference histories (noise band for the per-cycle tolerance, SURVEY section 7 "hard parts")
+    def run64(tag, n, L, n_iter, rhs_seed=None):
+        np.random.seed(123)
+        with contextlib.redirect_stdout(io.StringIO()):
+            p = MG(n, L)
+        for lv in p.grids.values():
+            lv.Knet.double()
+            lv.Knet.global_pattern = lv.Knet.global_pattern.double()
+            lv.jac.geometry_idx = lv.jac.geometry_idx.double()
+            lv.jac.boundary_value = lv.jac.boundary_value.double()
+            lv.jac.d_mat = lv.jac.d_mat.double()
+            lv.v = lv.v.double()
+            lv.f = lv.f.double()
+            lv.fnet.double()
+        p.initial_v = torch.from_numpy(model_problem_u0(n)).double()
+        if rhs_seed is not None:
+            rs = np.random.RandomState(rhs_seed)
+            F = torch.from_numpy(rs.standard_normal((1, 1, n + 1, n + 1)).astype(np.float32)).double()
+            with torch.no_grad():
+                p.grids[0].f = p.grids[0].fnet.float()(F.float()).double()
+            p.initial_v = torch.zeros(n + 1, n + 1).double()
+        # Restrict builds an fp32 kernel: patch through a double-capable copy of the same code path
+        import torch.nn.functional as F_
+
+        def Restrict(f):
+            k = torch.asarray([[1, 2, 1], [2, 4, 2], [1, 2, 1]], dtype=torch.float64) / 16.0
+            return F_.pad(F_.conv2d(f[:, :, 1:-1, 1:-1], k.view(1, 1, 3, 3), stride=2), (1, 1, 1, 1), "constant", 0)
+
+        p.Restrict = Restrict
+        with torch.no_grad():
+            res = p.Solve([1, 1], n_iter=n_iter)
+        hist[tag]["res64"] = [float(r) for r in res]
+
+    run64("modelA_n64_v11", 64, None, 20)
+    run64("modelA_n64_rhs", 64, None, 12, rhs_seed=5)
+    run64("modelA_n1024_L10", 1024, 10, 15)
+
+    # ---- MM_Interface_error.ipynb: two-phase circle a=[1,20], n=64, f=fnet(ones), u0=0, EPS=5e-5 (quirk variant)
+    nsI = H.notebook_namespace("MM_Interface_error.ipynb", [0, 1, 2])
+    t0 = time.time()
+    prob = nsI["Multigrid"](64)
+    prob.grids[0].v = torch.zeros((1, 1, 65, 65), dtype=torch.float32)
+    res_list = []
+    res = 1
+    with torch.no_grad():
+        while abs(res) > 5e-5 and len(res_list) < 40:
+            prob.rec_V_cycle(0, prob.grids[0].v, prob.grids[0].f)
+            r = prob.grids[0].f - prob.grids[0].Knet(prob.grids[0].v)
+            res = torch.sqrt(torch.sum(r[:, :, 1:-1, 1:-1] ** 2)).item()
+            res_list.append(res)
+    hist["interface_quirk_n64"] = dict(n=64, prop=[1, 20], res=res_list,
+                                       notebook_recorded=[0.04344373568892479, 0.025038596242666245,
+                                                          0.016153400763869286, 0.0099326865747571,
+                                                          0.005999982822686434, 0.0035448919516056776,
+                                                          0.002057234989479184, 0.0011781713692471385,
+                                                          0.000666382780764252, 0.0003720286185853183,
+                                                          0.00020798530022148043, 0.00011407280544517562,
+                                                          6.423080776585266e-05, 3.4823522582883015e-05])
+    arrays["interface_quirk_n64_u"] = t2n(prob.grids[0].v)
+    print("interface_quirk", len(res_list), "%.1fs" % (time.time() - t0), res_list[:3])
+
+    # ---- M-FEANet-mg_test.ipynb MultiGrid (variant B, 1-channel R=P=[1 2 1;2 4 2;1 2 1]/4), jac and hjac,
+    #      on Data/IsoPoisson/poisson2d_33x33.h5 samples 0..2 (data Dirichlet BCs on level 0), EPS=5e-5
+    bi, bv, rhs, uex = H.read_h5_contiguous(os.path.join(H.REF, "Data/IsoPoisson/poisson2d_33x33.h5"), (100, 33, 33))
+    arrays["iso33_bidx"] = bi[:3].astype(np.float32)
+    arrays["iso33_bval"] = bv[:3].astype(np.float32)
+    arrays["iso33_rhs"] = rhs[:3].astype(np.float32)
+    arrays["iso33_u"] = uex[:3].astype(np.float32)
+    # known-answer: K u = fnet(rhs) in fp64
+    arrays["iso33_rhs64"] = rhs[:3].copy()
+    arrays["iso33_u64"] = uex[:3].copy()
+    nsT = H.notebook_namespace("M-FEANet-mg_test.ipynb", [1, 2, 3, 4, 5, 18, 19, 20])
+    hnet = nsT["HNet"](3)
+    hnet.load_state_dict(torch.load(os.path.join(H.REF, "Model/learn_iterator/iso_poisson/iso_poisson_33x33.pth"),
+                                    weights_only=True))
+    for mode in ("jac", "hjac"):
+        for k in range(3):
+            n = 32
+            mg = nsT["MultiGrid"](n=n, hnet=hnet, P=nsT["linear_tensor_P"], mode=mode)
+            f_mg = torch.from_numpy(arrays["iso33_rhs"][k]).reshape(1, 1, n + 1, n + 1)
+            bidx = torch.from_numpy(arrays["iso33_bidx"][k]).reshape(1, 1, n + 1, n + 1)
+            bval = torch.from_numpy(arrays["iso33_bval"][k]).reshape(1, 1, n + 1, n + 1)
+            u_mg = torch.zeros((1, 1, n + 1, n + 1), dtype=torch.float32)
+            with torch.no_grad():
+                mg(u_mg, f_mg, bidx, bval, 1)
+                r = mg.f - mg.iterators[0].grid.Knet(mg.u0)
+                res = torch.norm(r[:, :, 1:-1, 1:-1].clone(), dim=(2, 3)).item()
+                rl = [res]
+                while abs(res) > 5e-5 and len(rl) < 60:
+                    u_mg = mg.Step(u_mg, mg.f)
+                    r = mg.f - mg.iterators[0].grid.Knet(u_mg)
+                    res = torch.norm(r[:, :, 1:-1, 1:-1].clone(), dim=(2, 3)).item()
+                    rl.append(res)
+            hist[f"mgtest_{mode}_s{k}"] = dict(n=n, mode=mode, sample=k, res=rl)
+            arrays[f"mgtest_{mode}_s{k}_u"] = t2n(u_mg)
+            print("mgtest", mode, k, len(rl) - 1, "cycles", rl[:3])
+
+    # ---- committed FEANet/multigrid.py MultiGrid.iterate (16-channel R/P, w) with the n_iter shim, n=32,
+    #      two-phase circle [1,20]; (a) linear R/P, w=[4,1]; (b) learned weights from Model/
+    M = H.load_reference_multigrid_module()
+    P4 = torch.tensor([[1, 2, 1], [2, 4, 2], [1, 2, 1]], dtype=torch.float32) / 4.0
+    R16 = torch.tensor([[1, 2, 1], [2, 4, 2], [1, 2, 1]], dtype=torch.float32) / 16.0
+    sd = torch.load(os.path.join(H.REF, "Model/learn_intergrid_operator/multigrid_rhs_qm/"
+                                 "model_multigrid_interface_ratio.pth"), weights_only=True)
+    arrays["learned_w"] = t2n(sd["w"])
+    arrays["learned_R"] = t2n(sd["conv.net.weight"]).reshape(16, 9)
+    arrays["learned_P"] = t2n(sd["deconv.net.weight"]).reshape(16, 9)
+    n = 32
+    rs = np.random.RandomState(11)
+    Fr = torch.from_numpy(rs.standard_normal((2, 1, n + 1, n + 1)).astype(np.float32))
+    x0 = torch.from_numpy(rs.standard_normal((2, 1, n + 1, n + 1)).astype(np.float32))
+    arrays["iterate_F"] = t2n(Fr)
+    arrays["iterate_x0"] = t2n(x0)
+    for tag, learned in (("linear", False), ("learned", True)):
+        mg = M.MultiGrid(n, R16, P4, torch.tensor([4.0, 1.0]))
+        if learned:
+            mg.load_state_dict(sd)
+        with torch.no_grad():
+            f = mg.grids[0].fnet(Fr)
+            x = x0
+            rl = []
+            for _ in range(6):
+                x = mg.iterate(x, f)
+                r = f - mg.grids[0].Knet(x)
+                rl.append(torch.norm(r[:, :, 1:-1, 1:-1], dim=(2, 3)).reshape(-1).tolist())
+        hist[f"iterate_{tag}"] = dict(n=n, res=rl)
+        arrays[f"iterate_{tag}_u"] = t2n(x)
+        print("iterate", tag, rl[0], rl[-1])
+
+    json.dump(hist, open(os.path.join(OUT, "solve_histories.json"), "w"), indent=1)
+    np.savez_compressed(os.path.join(OUT, "solve_arrays.npz"), **arrays)
+    print("solve fixtures written")
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["mesh", "ops", "solve"]
+    if "mesh" in which:
+        gen_mesh()
+    if "ops" in which:
+        gen_ops()
+    if "solve" in which:
+        gen_solve()
