@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py -- V-cycles/s and GDOF/s of the multigrid V-cycle hot path on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W          # our arm (sm_100a kernels through the C ABI)
+    python bench.py --impl reference --steps K --warmup W   # the reference's CPU torch path on the box's host cores
+
+A "step" is one V(1,1) cycle (smooth, residual+restrict, ..., prolong+correct, smooth, interior residual norm) over the
+headline workload: isotropic Poisson, 4097 x 4097 nodal quad grid, 12 levels, single right-hand side, fp32.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "multigrid-feanet_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "V-cycles/s (4097^2 Poisson, V(1,1), fp32)"
+
+
+def model_u0(n, seed=123):
+    """MM_Model_convergence.ipynb cell 3 random_data (seed enabled): the reference's own benchmark problem, f = 0"""
+    np.random.seed(seed)
+    coef = 100000 + 50000 * np.random.rand(2)
+    return (coef[0] * np.random.random((n + 1, n + 1)).astype("f") + coef[1]).astype(np.float32)
+
+
+def algorithmic_bytes_per_cycle(n, L, nu1=1, nu2=1, B=1, key_bytes=0):
+    """compulsory fp32 traffic of one V-cycle, no credit for temporal blocking"""
+    M = [(n // 2 ** l + 1) ** 2 for l in range(L)]
+    words = 3 * (nu1 + nu2) * sum(M) + 2 * sum(2 * M[l] + M[l + 1] for l in range(L - 1)) + 2 * M[0]
+    kb = key_bytes * ((nu1 + nu2 + 1) * sum(M) + M[0])
+    return (4 * words + kb) * B
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)"""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.strip().split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def hbm_peak():
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(pk["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's CPU torch path (ATen call-for-call restatement, oracle/feanet_torch.py) on the host cores."""
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import feanet_torch as FT
+
+    n, L = args.n, int(np.log2(args.n))
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    levels = FT.make_levels(n, L)
+    u = torch.from_numpy(model_u0(n)).reshape(1, 1, n + 1, n + 1)
+    f = torch.zeros(1, 1, n + 1, n + 1)
+    steps, warm = args.steps, args.warmup
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        u = FT.vcycle(levels, u, f)
+        t_first = time.perf_counter() - t0
+        budget = 150.0
+        steps_eff = max(1, min(steps, int(budget / max(t_first, 1e-3))))
+        for _ in range(max(0, min(warm, 2) - 1)):
+            u = FT.vcycle(levels, u, f)
+        t0 = time.perf_counter()
+        for _ in range(steps_eff):
+            u = FT.vcycle(levels, u, f)
+            r = f - levels[0].K(u)
+            _ = torch.sqrt(torch.sum(r[:, :, 1:-1, 1:-1] ** 2)).item()
+        dt = time.perf_counter() - t0
+    val = steps_eff / dt
+    dof = (n + 1) ** 2
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "V-cycles/s", "n_gpus": 0,
+            "steps": steps_eff, "warmup": min(warm, 2), "ms_per_step": 1e3 * dt / steps_eff,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "gdof_per_s": val * dof / 1e9,
+            "config": {"workload": f"iso Poisson {n + 1}x{n + 1}, V(1,1), {L} levels, single RHS, f=0 model problem",
+                       "n": n, "levels": L, "nu": [1, 1], "batch": 1},
+            "cpu_baseline": {"value": val, "unit": "V-cycles/s", "cores": cores, "kind": "port",
+                             "sample": f"{steps_eff} V-cycles (+ residual norm each) of the same {n + 1}^2 problem; "
+                                       "ATen call-for-call restatement of the reference CPU torch path "
+                                       "(oracle/feanet_torch.py), torch threads = all host cores"},
+            "e2e": {"value": val, "unit": "V-cycles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample(n, L, seconds=20.0):
+    import torch
+
+    from oracle import feanet_torch as FT
+
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    levels = FT.make_levels(n, L)
+    u = torch.from_numpy(model_u0(n)).reshape(1, 1, n + 1, n + 1)
+    f = torch.zeros(1, 1, n + 1, n + 1)
+    with torch.no_grad():
+        u = FT.vcycle(levels, u, f)  # warm-up
+        t0 = time.perf_counter()
+        k = 0
+        while k < 2 or (time.perf_counter() - t0 < seconds and k < 50):
+            u = FT.vcycle(levels, u, f)
+            r = f - levels[0].K(u)
+            _ = torch.sqrt(torch.sum(r[:, :, 1:-1, 1:-1] ** 2)).item()
+            k += 1
+        dt = time.perf_counter() - t0
+    return {"value": k / dt, "unit": "V-cycles/s", "cores": cores, "kind": "port",
+            "sample": f"{k} V-cycles (+ residual norm) at {n + 1}^2 after 1 warm-up, torch CPU threads={cores}; "
+                      "ATen call-for-call restatement of the reference (oracle/feanet_torch.py)"}
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import mgfea
+    from FEANet.drivers import Multigrid
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, L = args.n, int(np.log2(args.n))
+    N = n + 1
+    dof = N * N
+    steps, warm = args.steps, max(args.warmup, 3)
+
+    prob = Multigrid(n)  # every rank: one independent replica of the workload (see DESIGN.md "Multi-GPU")
+    u0_host = torch.from_numpy(model_u0(n, seed=123 + rank)).reshape(1, 1, N, N).pin_memory()
+    f_host = torch.zeros(1, 1, N, N).pin_memory()
+    prob.initial_v = u0_host
+    prob.grids[0].f = f_host
+    eng = prob._engine(1, 1, 0, B=1)
+    eng.set_u(u0_host)
+    eng.set_f(f_host)
+    eng.refresh()
+    eng._ctl_reset(0, -1.0, eng.max_cycles)  # eps2 < 0: never converge; the history ring is capped at max_cycles
+    eng._ensure_graph()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ctl.cycle would hit max_cycles and set done; re-arm it on the device without a host sync
+    zero_ctl = eng.ctl.clone()
+
+    def rearm():
+        eng.ctl.copy_(zero_ctl, non_blocking=True)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    # untimed load phase so that the clock samples are taken under this workload, doubles as warm-up
+    t_end = time.time() + 1.0
+    while time.time() < t_end:
+        rearm()
+        for _ in range(64):
+            eng._graph.replay()
+        torch.cuda.synchronize()
+    rearm()
+    for _ in range(warm):
+        eng._graph.replay()
+    barrier()
+    launches0 = mgfea.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rearm()
+    ev0.record()
+    done = 0
+    while done < steps:
+        k = min(steps - done, eng.max_cycles - 1)
+        for _ in range(k):
+            eng._graph.replay()
+        done += k
+        if done < steps:
+            rearm()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    # launches per cycle: count one eager cycle (graph replays do not pass through the host-side counter)
+    c0 = mgfea.launch_count()
+    rearm()
+    eng.cycle(use_ctl=True)
+    torch.cuda.synchronize()
+    per_cycle = mgfea.launch_count() - c0
+    # keep the GPU under the same load a little longer for the sampler
+    t_end = time.time() + 0.3
+    while time.time() < t_end:
+        rearm()
+        for _ in range(64):
+            eng._graph.replay()
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+
+    cycles_per_s = world * steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (level-0 fused kernels), CUDA events on the launching stream
+    import ctypes
+
+    peak, peak_src = hbm_peak()
+    g0 = eng._grids[0]
+    rt = eng._keep[0]
+    M0, M1 = dof, (n // 2 + 1) ** 2
+    reps = 30
+
+    def time_kernel(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    def down():
+        mgfea.check(mgfea.lib().mgfea_smooth_residual_restrict(
+            ctypes.byref(g0), eng.u[0].ptr, eng.u_alt[0].ptr, eng.f[0].ptr, 1, 0, None, 0, eng.f[1].ptr,
+            eng.f[1].pitch, eng.f[1].plane, rt.data_ptr(), 1, 1, 4.0, None, 1, mgfea.stream_ptr()))
+
+    def up():
+        g1 = eng._grids[1]
+        mgfea.check(mgfea.lib().mgfea_prolong_correct_smooth(
+            ctypes.byref(g0), ctypes.byref(g1), eng.u[1].ptr, eng.u_alt[0].ptr, eng.u[0].ptr, eng.f[0].ptr,
+            mgfea.PROLONG_BILINEAR, None, 0, 0, 0.0, None, 1, 0, None, 0, 1, mgfea.stream_ptr()))
+
+    ms_down, ms_up = time_kernel(down), time_kernel(up)
+    alg_down = 4 * (3 * M0 + 2 * M0 + M1)      # pre-smooth (u,f -> u) + residual->restrict (u,f -> f_c)
+    alg_up = 4 * (2 * M0 + M1 + 3 * M0)        # prolong->correct (v_c,u -> u) + post-smooth (u,f -> u)
+    if ms_down >= ms_up:
+        kname, kms, kalg = "mg_tile_kernel<iso> level-0 down leg (smooth+residual+restrict)", ms_down, alg_down
+    else:
+        kname, kms, kalg = "mg_tile_kernel<iso> level-0 up leg (prolong+correct+smooth)", ms_up, alg_up
+    ach = kalg / (kms * 1e-3) / 1e9
+    balg = algorithmic_bytes_per_cycle(n, L)
+    cyc_ms = ms / steps
+    cyc_ach = balg / (cyc_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "kernel": kname, "kernel_ms": kms, "algorithmic_bytes_per_launch": kalg, "peak_source": peak_src,
+                "other_kernel_ms": {"down_leg": ms_down, "up_leg": ms_up},
+                "cycle": {"algorithmic_bytes": balg, "ms": cyc_ms, "achieved": cyc_ach, "frac": cyc_ach / peak}}
+
+    # ---- end to end through the reference-facing API: Multigrid.Solve from HOST buffers to 1e-8 relative
+    def e2e_once():
+        prob.initial_v = u0_host
+        prob.grids[0].f = f_host
+        r0 = None
+        t0 = time.perf_counter()
+        res = prob.Solve([1, 1], n_iter=args.e2e_cycles, chunk=args.e2e_cycles)
+        u_host = prob.grids[0].v  # Solve returns the solution on the host for host inputs (D2H inside)
+        dt = time.perf_counter() - t0
+        return dt, res, u_host
+
+    e2e_once()
+    barrier()
+    reps_e = 3
+    t0 = time.perf_counter()
+    for _ in range(reps_e):
+        dt, res, _ = e2e_once()
+    torch.cuda.synchronize()
+    e2e_dt = (time.perf_counter() - t0) / reps_e
+    te = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_dt = float(te.item())
+    e2e_val = world * args.e2e_cycles / e2e_dt
+
+    # ---- time to 1e-8 relative residual (device resident, f = 0 model problem)
+    eng.set_u(u0_host)
+    eng.set_f(f_host)
+    torch.cuda.synchronize()
+    r0 = float(torch.sqrt(eng.residual_sumsq().sum()).item())
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    hist = eng.run(EPS=1e-8 * r0, chunk=4)
+    torch.cuda.synchronize()
+    t_tol = time.perf_counter() - t0
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = cpu_baseline_sample(n, L) if (world == 1 and not args.no_cpu_baseline) else None
+    line = {"metric": METRIC, "value": cycles_per_s, "unit": "V-cycles/s", "n_gpus": world, "steps": steps,
+            "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "gdof_per_s": cycles_per_s * dof / 1e9,
+            "time_to_1e-8_rel_ms": 1e3 * t_tol, "cycles_to_1e-8_rel": len(hist),
+            "config": {"workload": f"iso Poisson {N}x{N}, V(1,1), {L} levels, single RHS per GPU, f=0 model problem "
+                                   "(MM_Model_convergence.ipynb cell 3), residual norm fused in every cycle",
+                       "n": n, "levels": L, "nu": [1, 1], "batch": 1,
+                       "l2": "inputs larger than L2 (level-0 u, u', f = 201 MB > 126 MB); no explicit flush",
+                       "replicas": world, "loader": "tma" if args.loader == "tma" else "cp.async"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": "V-cycles/s", "h2d_bytes_per_step": int(2 * 4 * dof / args.e2e_cycles),
+                    "d2h_bytes_per_step": int((4 * dof + 8 * args.e2e_cycles) / args.e2e_cycles),
+                    "what": f"Multigrid.Solve(n_iter={args.e2e_cycles}) from pinned host u0,f: H2D of both fields, "
+                            f"{args.e2e_cycles} cycles, D2H of the residual history and of the solution; "
+                            "bytes are per V-cycle", "ms_per_solve": 1e3 * e2e_dt},
+            "gpu_launches": int(per_cycle * steps), "gpu_launches_per_step": int(per_cycle),
+            "roofline": roofline}
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=4096)
+    ap.add_argument("--e2e-cycles", type=int, default=13)
+    ap.add_argument("--loader", default="tma", choices=["tma", "cpasync"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps == 200:
+            args.steps = 10
+        run_reference(args)
+        return
+    import mgfea
+
+    mgfea.set_loader(args.loader == "tma")
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

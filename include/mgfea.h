@@ -1,0 +1,173 @@
+/*
+ * mgfea.h -- C ABI of libmgfea.so: the B200 (sm_100a) multigrid V-cycle kernels behind the FEANet module API.
+ *
+ * The reference (longfish/Multigrid-FEANet) has no FFI of its own: its hot path is Python calling CPU ATen ops.
+ * Each entry point below replaces the ATen call sequence of one reference method (file:line relative to the
+ * reference tree); the Python package multigrid-feanet_b200/FEANet binds them through ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative MGFEA_E* code for argument errors, or a positive
+ *     cudaError_t; nothing throws, allocates device memory for the caller, or synchronises the device
+ *     (two small internal scratch buffers per device are created lazily at first use);
+ *   - all pointers are DEVICE pointers owned by the caller; `stream` is a cudaStream_t passed as void*;
+ *   - fields are fp32, row-major, [B][N][pitch]: `pitch` = row pitch in floats, `plane` = sample stride in floats.
+ *     Kernels require pitch % 4 == 0 and 16-byte aligned base pointers ("padded-pitch" level buffers; N = 2^k+1 is
+ *     odd, so contiguous N*N tensors are packed/unpacked at the API edge with mgfea_pack / mgfea_unpack).
+ *     Columns [N, pitch) of every field are kept zero by all kernels;
+ *   - material pattern keys are uint8 [N][key_pitch] (key_pitch % 16 == 0), NULL for single-pattern (iso) meshes;
+ *   - 3x3 tables are [npat][9] fp32, tap t = 3*(di+1)+(dj+1), read from device memory at launch time so that live
+ *     nn.Parameter weights (KNet.net2.weight, FNet.net.weight, RestrictionNet/ProlongationNet.net.weight,
+ *     HNet.convLayers[i].weight, MultiGrid.w) behave as in the reference.
+ *   - arithmetic: IEEE fp32 in a fixed order (row-major FMA chain per stencil), identical to oracle/mgfea_oracle.c.
+ */
+#ifndef MGFEA_H
+#define MGFEA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGFEA_EINVAL (-1)     /* bad argument (NULL pointer, bad size) */
+#define MGFEA_EALIGN (-2)     /* pointer/pitch alignment requirement violated */
+#define MGFEA_EUNSUPPORTED (-3)
+#define MGFEA_EDRIVER (-4)    /* cuTensorMapEncodeTiled unavailable / failed */
+
+/* One multigrid level ("grid").  Mirrors the per-level state of the reference's SingleGrid
+ * (FEANet/multigrid.py:12-47): Knet weights + pattern map, Jacobi diagonal, Dirichlet masks. */
+typedef struct mgfea_grid {
+    int32_t N;          /* nodes per edge (n+1) */
+    int32_t pitch;      /* floats per row of every field of this level */
+    int64_t plane;      /* floats per sample */
+    int32_t npat;       /* number of material patterns C: 1 (MeshSquare) or 16 (MeshCenterInterface) */
+    int32_t key_pitch;  /* bytes per row of `keys` */
+    const uint8_t *keys;   /* [N][key_pitch] pattern key per node (FEANet/mesh.py:95-101), or NULL */
+    const float *ktab;     /* [npat][9]  KNet.net2.weight[0]            (FEANet/model.py:16,20) */
+    const float *invd;     /* [npat]     omega / d per pattern key      (FEANet/jacobi.py:31-37,46) */
+    const float *bc_idx;   /* optional general geometry_idx  [B or 1][N][pitch] (FEANet/jacobi.py:19,29); NULL = square ring */
+    const float *bc_val;   /* optional general boundary_value, same layout; NULL = 0 */
+    int64_t bc_plane;      /* sample stride of bc_idx/bc_val in floats; 0 = shared by all samples */
+} mgfea_grid;
+
+/* smoother selection */
+#define MGFEA_SMOOTH_JACOBI 0 /* JacobiBlock.jacobi_convolution       FEANet/jacobi.py:39-47 */
+#define MGFEA_SMOOTH_HJACOBI 1 /* HJacIterator.HRelax + HNet.forward   M-FEANet-mg_test.ipynb cells 4,5 */
+
+/* prolongation selection */
+#define MGFEA_PROLONG_BILINEAR 1 /* F.interpolate(bilinear, align_corners) + fine reset_boundary: MM_Model_convergence.ipynb cell 3 `Interpolate` */
+#define MGFEA_PROLONG_TABLE 3    /* ConvTranspose2d(C->1,3,stride 2,pad 1) [* w[1]]: FEANet/multigrid.py:62-73,124-130,177-179 */
+
+/* residual-norm convergence rule evaluated on the device */
+#define MGFEA_CONV_SUM 0 /* whole-batch sum of squares  (Multigrid.Solve, MM_Model_convergence.ipynb cell 3) */
+#define MGFEA_CONV_MAX 1 /* max over samples            (per-sample torch.norm, M-FEANet-mg_test.ipynb cell 21) */
+
+/* Device-resident solve control block (one per solve; zero it before the first cycle).  Every kernel of a cycle
+ * returns immediately when `done` is set, so cycles enqueued past convergence are no-ops and the host may check
+ * convergence every few cycles instead of every cycle (the reference syncs with .item() each cycle). */
+typedef struct mgfea_ctl {
+    int32_t cycle;      /* number of residual norms recorded so far */
+    int32_t done;       /* set by the device when converged / max_cycles reached */
+    int32_t min_cycles; /* Solve's n_iter */
+    int32_t max_cycles; /* capacity of hist (in cycles) */
+    int32_t conv_rule;  /* MGFEA_CONV_SUM | MGFEA_CONV_MAX */
+    int32_t pad_;
+    double eps2;        /* EPS^2 (absolute interior 2-norm threshold, squared); <0 disables */
+} mgfea_ctl;
+
+/* ---- library / device -------------------------------------------------------------------------------- */
+const char *mgfea_version(void);
+const char *mgfea_error_string(int code);
+/* 0 = cp.async tile loader, 1 = TMA (cp.async.bulk.tensor) tile loader [default]; returns previous value */
+int mgfea_set_loader(int use_tma);
+/* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
+uint64_t mgfea_launch_count(void);
+
+/* ---- layout ------------------------------------------------------------------------------------------ */
+/* contiguous [B][N][N] <-> padded [B][N][pitch]; pack zero-fills columns [N,pitch) */
+int mgfea_pack(const float *src, float *dst, int N, int pitch, int64_t plane, int B, void *stream);
+int mgfea_unpack(const float *src, float *dst, int N, int pitch, int64_t plane, int B, void *stream);
+
+/* ---- operators (one reference method each) ----------------------------------------------------------- */
+/* KNet.forward (FEANet/model.py:22-30): out = K u on ALL nodes, zero padding, weights indexed by SOURCE-node key */
+int mgfea_stiffness_apply(const mgfea_grid *g, const float *u, float *out, int B, void *stream);
+/* FNet.forward (FEANet/model.py:49-61) / any single 3x3 correlation: out = w9 (*) x, zero padding */
+int mgfea_load_vector(const float *w9, const float *x, float *out, int N, int pitch, int64_t plane, int B,
+                      void *stream);
+/* KNet.split_x (FEANet/model.py:37-47): out[b][c] = x[b] where key==c else 0; out contiguous [B][C][N][N] */
+int mgfea_split_x(const mgfea_grid *g, const float *x, float *out, int B, void *stream);
+/* JacobiBlock.reset_boundary (FEANet/jacobi.py:27-29) */
+int mgfea_reset_boundary(const mgfea_grid *g, const float *u, float *out, int B, void *stream);
+/* nsweeps of the smoother, temporally blocked inside one tile pass where the halo allows.
+ * hw = [nlayers][9] HNet weights (HJACOBI only).  u_in may NOT alias u_out. */
+int mgfea_smooth(const mgfea_grid *g, const float *u_in, float *u_out, const float *f, int nsweeps, int smoother,
+                 const float *hw, int nlayers, int B, void *stream);
+/* r = f - K u on all nodes (the `f - Knet(v)` expression of every driver) */
+int mgfea_residual(const mgfea_grid *g, const float *u, const float *f, float *r, int B, void *stream);
+/* Restrict (MM_Model_convergence.ipynb cell 3; FEANet/multigrid.py:115-122): fc = scale * R (*) r[1:-1,1:-1] stride 2,
+ * zero ring.  rtab = [rtab_n][9], rtab_n = 1 or g->npat (table of the FINE source node's key).
+ * scale: *scale_dev if non-NULL, else scale_host; has_scale = 0 skips the multiply. */
+int mgfea_restrict(const mgfea_grid *g, const float *r, float *fc, int pitch_c, int64_t plane_c, const float *rtab,
+                   int rtab_n, int has_scale, float scale_host, const float *scale_dev, int B, void *stream);
+/* API-compat forms taking an already split (B,C,.,.) CONTIGUOUS tensor, as MultiGrid.Restrict / .Interpolate of
+ * FEANet/multigrid.py:115-130 receive it: fc (B,1,Nc,Nc) = pad(conv(C->1,3x3,stride 2)(rF[:, :, 1:-1, 1:-1])),
+ * out (B,1,2Nc-1,2Nc-1) = convT(C->1,3x3,stride 2,pad 1)(eFC).  No scale is applied. */
+int mgfea_restrict_channels(const float *rF, float *fc, const float *rtab, int C, int N, int B, void *stream);
+int mgfea_prolong_channels(const float *eFC, float *out, const float *ptab, int C, int Nc, int B, void *stream);
+/* fused: nsweeps pre-smoothing (u_in==NULL means u_in = 0), write u_out, then fc = scale*R(f - K u_out) */
+int mgfea_smooth_residual_restrict(const mgfea_grid *g, const float *u_in, float *u_out, const float *f, int nsweeps,
+                                   int smoother, const float *hw, int nlayers, float *fc, int pitch_c,
+                                   int64_t plane_c, const float *rtab, int rtab_n, int has_scale, float scale_host,
+                                   const float *scale_dev, int B, void *stream);
+/* Interpolate + correct (+ post-smooth): u_out = smooth^nsweeps(u_in + scale * P(vc)).
+ * mode BILINEAR: P = bilinear x2 followed by the fine level's reset_boundary (variant A);
+ * mode TABLE: transposed conv with ptab[ptab_n][9] indexed by the COARSE node's key (gc->keys), times scale. */
+int mgfea_prolong_correct_smooth(const mgfea_grid *g, const mgfea_grid *gc, const float *vc, const float *u_in,
+                                 float *u_out, const float *f, int mode, const float *ptab, int ptab_n,
+                                 int has_scale, float scale_host, const float *scale_dev, int nsweeps, int smoother,
+                                 const float *hw, int nlayers, int B, void *stream);
+/* sumsq[b] = sum over interior nodes of (f - K u)^2, accumulated in fp64, deterministic order.
+ * If ctl != NULL the value is also appended to hist[ctl->cycle*B + b] and the convergence rule is evaluated. */
+int mgfea_residual_norm(const mgfea_grid *g, const float *u, const float *f, double *sumsq, mgfea_ctl *ctl,
+                        double *hist, int B, void *stream);
+
+/* ---- whole V-cycle ----------------------------------------------------------------------------------- */
+typedef struct mgfea_cycle_cfg {
+    int32_t nu1, nu2;      /* pre / post sweeps (coarsest level gets nu1 + nu2) */
+    int32_t smoother;      /* MGFEA_SMOOTH_* */
+    int32_t nlayers;       /* HNet layers */
+    const float *hw;       /* [nlayers][9] */
+    int32_t prolong_mode;  /* MGFEA_PROLONG_* */
+    int32_t rtab_n;        /* 1 or 16 */
+    const float *rtab;     /* [rtab_n][9] */
+    int32_t ptab_n;
+    int32_t r_has_scale;
+    const float *ptab;     /* [ptab_n][9] (TABLE mode) */
+    float r_scale_host;
+    float p_scale_host;
+    const float *r_scale_dev; /* MultiGrid.w[0] */
+    const float *p_scale_dev; /* MultiGrid.w[1] */
+    int32_t p_has_scale;
+    int32_t quirk_level0;  /* MM_Interface_error.ipynb cell 2: pre-smooth is always applied to level 0 */
+    int32_t tail_max_n;    /* levels with N <= tail_max_n run inside the single coarse-tail kernel (0: default) */
+    int32_t compute_norm;  /* 1: fuse the interior residual norm of level 0 into the last kernel */
+} mgfea_cycle_cfg;
+
+/* Per-level buffers of one V-cycle: u ping-pong pair and f.  After the call the result is in u[0] again. */
+typedef struct mgfea_level_bufs {
+    float *u;      /* solution (level 0: in/out; coarser: scratch) */
+    float *u_alt;  /* ping-pong partner */
+    float *f;      /* right-hand side (level 0: input; coarser: written by the restriction) */
+} mgfea_level_bufs;
+
+/* One V(nu1,nu2) cycle over `nlevels` grids (grids[0] finest).  Restates Multigrid.rec_V_cycle
+ * (MM_Model_convergence.ipynb cell 3), MultiGrid.Step (M-FEANet-mg_test.ipynb cell 19) and MultiGrid.iterate
+ * (FEANet/multigrid.py:159-185).  Graph-capturable: no host synchronisation, no allocation. */
+int mgfea_vcycle(const mgfea_grid *grids, const mgfea_level_bufs *bufs, int nlevels, const mgfea_cycle_cfg *cfg,
+                 double *sumsq, mgfea_ctl *ctl, double *hist, int B, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGFEA_H */

@@ -1,0 +1,116 @@
+"""Weighted-Jacobi smoother with Dirichlet reset on the GPU (reference: FEANet/jacobi.py)."""
+import numpy as np
+import torch
+
+import mgfea
+from mgfea import Field, as_field, check, lib, stream_ptr
+
+from .model import _like_input
+
+
+def _is_default_ring(geometry_idx, boundary_value):
+    """True when the masks are the square ring with zero boundary values (geo.py:13-30): the kernels then use index
+    arithmetic instead of reading mask fields.  Tagged tensors from FEANet.geo skip the O(N^2) comparison."""
+    if getattr(geometry_idx, "_mgfea_default_ring", False) and getattr(boundary_value, "_mgfea_zero", False):
+        return True
+    if geometry_idx.shape[0] != 1 or geometry_idx.shape != boundary_value.shape:
+        return False
+    g = geometry_idx.detach().cpu()
+    ring = torch.ones_like(g)
+    ring[..., 0, :] = 0
+    ring[..., -1, :] = 0
+    ring[..., :, 0] = 0
+    ring[..., :, -1] = 0
+    return bool(torch.equal(g, ring)) and not bool(boundary_value.detach().cpu().any())
+
+
+class JacobiBlock():
+    """ Define all the methods necessary for a CNN-based Jacobi iteration (Dirichlet boundary condition)
+
+        Knet: neural network model for stiffness terms
+        mesh: an object that define the mesh
+        geometry_idx : tensor-like, shape = [*, *, n, n]; 1.0 for inner points 0.0 elsewhere.
+        boundary_value: tensor-like, shape = [*, *, n, n]; desired values for boundary points 0.0 elsewhere.
+    """
+
+    def __init__(self, Knet, mesh, omega, geometry_idx, boundary_value):
+        self.nnode_edge = geometry_idx.shape[2]
+        self.geometry_idx = geometry_idx
+        self.boundary_value = boundary_value
+        self.omega = omega
+        self.mesh = mesh
+        self.Knet = Knet
+        self._d_mat = None
+        self._default_bc = _is_default_ring(geometry_idx, boundary_value)
+        self._bc_fields = None
+        # per-pattern omega/d exactly as torch evaluates `self.omega/self.d_mat` (jacobi.py:46): reciprocal, then
+        # multiply by fl32(omega)
+        diag = np.array([np.asarray(mesh.kernel_dict[k], dtype=np.float32)[1, 1] for k in sorted(mesh.kernel_dict)],
+                        dtype=np.float32)
+        self._diag = diag
+        self._invd_np = ((np.float32(1.0) / diag).astype(np.float32) * np.float32(omega)).astype(np.float32)
+        self._invd_dev = None
+
+    # -- reference attribute: (B or 1,1,N,N) Jacobi diagonal (jacobi.py:31-37); lazy, not used by the kernels
+    @property
+    def d_mat(self):
+        if self._d_mat is None:
+            d = torch.zeros_like(self.geometry_idx)
+            keys = getattr(self.Knet, "_keys_np", None)
+            if keys is None:
+                d += float(self._diag[0])
+            else:
+                d += torch.from_numpy(self._diag[keys.astype(np.int64)]).to(d.device)
+            self._d_mat = d
+        return self._d_mat
+
+    def compute_diagonal_matrix(self):
+        self._d_mat = None
+        return self.d_mat
+
+    def invd_dev(self):
+        if self._invd_dev is None:
+            self._invd_dev = torch.from_numpy(self._invd_np).to(mgfea.require_cuda())
+        return self._invd_dev
+
+    def bc_fields(self):
+        if self._default_bc:
+            return None
+        if self._bc_fields is None:
+            self._bc_fields = (as_field(self.geometry_idx), as_field(self.boundary_value))
+        return self._bc_fields
+
+    def grid_struct(self, fld):
+        return self.Knet.grid_struct(fld, self.invd_dev(), self.bc_fields())
+
+    def reset_boundary(self, u):
+        """ Reset values at the boundary of the domain """
+        uf = as_field(u)
+        out = Field(uf.B, uf.N, uf.store.device)
+        check(lib().mgfea_reset_boundary(self.grid_struct(uf), uf.ptr, out.ptr, uf.B, stream_ptr()))
+        return _like_input(u, out)
+
+    def smooth_fields(self, uf, ff, n_iter=1, smoother=mgfea.SMOOTH_JACOBI, hw=None, nlayers=0):
+        """n_iter sweeps on padded fields, temporally blocked inside one tile pass where the halo allows"""
+        g = self.grid_struct(uf)
+        dev = uf.store.device
+        depth = (1 + nlayers) if smoother == mgfea.SMOOTH_HJACOBI else 1
+        kmax = max(1, 8 // depth)
+        cur, remaining = uf, n_iter
+        while remaining > 0:
+            k = min(kmax, remaining)
+            out = Field(uf.B, uf.N, dev)
+            check(lib().mgfea_smooth(g, cur.ptr, out.ptr, ff.ptr, k, smoother, hw, nlayers, uf.B, stream_ptr()))
+            cur, remaining = out, remaining - k
+        return cur
+
+    def jacobi_convolution(self, initial_u, forcing_term, n_iter=1):
+        """ Jacobi method iteration step defined as a convolution:
+        u_new = omega/d_mat*residual + u, where residual = f - K*u (* is convolution operator here)
+        note that the forcing_term should be already convoluted, i.e., forcing_term = fnet(f), when source term is f.
+        `n_iter` accepts the older API that FEANet/multigrid.py:46 still calls."""
+        uf, ff = as_field(initial_u), as_field(forcing_term)
+        if ff.B != uf.B:
+            raise mgfea.MgfeaError("u and f batch sizes differ")
+        out = self.smooth_fields(uf, ff, n_iter)
+        return _like_input(initial_u, out)

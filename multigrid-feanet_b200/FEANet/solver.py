@@ -1,0 +1,215 @@
+"""V-cycle engine shared by the reference-facing drivers (FEANet.drivers, FEANet.multigrid).
+
+Holds the padded per-level buffers in HBM (u ping-pong pair + f per level), the level descriptors handed to the C ABI,
+and drives ``mgfea_vcycle``.  The steady-state loop replays a CUDA graph of one cycle (residual norm fused into the last
+kernel, convergence evaluated on the device in an ``mgfea_ctl`` block), so the host only synchronises every few cycles
+instead of calling ``.item()`` per cycle like the reference does (MM_Model_convergence.ipynb cell 3 ``Solve``).
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+import mgfea
+from mgfea import CycleCfg, Ctl, Field, Grid, LevelBufs, check, lib, stream_ptr
+
+FULL_WEIGHTING_16 = (np.array([[1, 2, 1], [2, 4, 2], [1, 2, 1]], dtype=np.float32) / np.float32(16.0))
+LINEAR_4 = (np.array([[1, 2, 1], [2, 4, 2], [1, 2, 1]], dtype=np.float32) / np.float32(4.0))
+
+
+class VCycleEngine:
+    """levels: list of FEANet.jacobi.JacobiBlock (finest first); each carries its KNet (weights, pattern keys), its
+    omega/d table and its Dirichlet masks."""
+
+    def __init__(self, jacs, B=1, nu1=1, nu2=1, smoother="jac", hnet=None, prolong="bilinear", rtab=None, r_scale=4.0,
+                 ptab=None, p_scale=None, w_param=None, quirk_level0=False, conv_rule=mgfea.CONV_SUM,
+                 max_cycles=256):
+        self.dev = mgfea.require_cuda()
+        self.jacs = list(jacs)
+        self.L = len(self.jacs)
+        self.B = B
+        self.nu1, self.nu2 = int(nu1), int(nu2)
+        self.smoother = smoother
+        self.hnet = hnet
+        self.prolong = prolong
+        self.quirk_level0 = quirk_level0
+        self.conv_rule = conv_rule
+        self.max_cycles = max_cycles
+        self._rtab_src = rtab  # numpy array, torch tensor / Parameter (live) or None (full weighting /16)
+        self._ptab_src = ptab
+        self.r_scale, self.p_scale = r_scale, p_scale
+        self.w_param = w_param  # live MultiGrid.w (2,) -> device scales
+        self._tabs = {k: mgfea.DeviceTable() for k in ("r", "p", "w", "h")}
+        self.u = [Field(B, j.nnode_edge, self.dev) for j in self.jacs]
+        self.u_alt = [Field(B, j.nnode_edge, self.dev) for j in self.jacs]
+        self.f = [Field(B, j.nnode_edge, self.dev) for j in self.jacs]
+        self.sumsq = torch.zeros(B, dtype=torch.float64, device=self.dev)
+        self.hist = torch.zeros((max_cycles, B), dtype=torch.float64, device=self.dev)
+        self.ctl = torch.zeros(8, dtype=torch.int32, device=self.dev)  # mgfea_ctl (32 bytes)
+        self._ctl_host = torch.zeros(8, dtype=torch.int32).pin_memory()
+        self._graph = None
+        self._graph_key = None
+        self._keep = []
+        self.refresh()
+        # first use allocates the library's per-device scratch (must not happen inside a graph capture)
+        check(lib().mgfea_residual_norm(ctypes.byref(self._grids[0]), self.u[0].ptr, self.f[0].ptr,
+                                        self.sumsq.data_ptr(), None, None, B, stream_ptr()))
+
+    # -- descriptors ---------------------------------------------------------------------------------------
+    def _table(self, which, src, default):
+        if src is None:
+            src = default
+        t = src if isinstance(src, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(src, dtype=np.float32))
+        t = t.detach().reshape(-1, 9)
+        return self._tabs[which].get(t.contiguous() if not t.is_contiguous() else t)
+
+    def refresh(self):
+        """(re)build the C descriptors; picks up live weight changes (KNet.net2, R/P kernels, w, HNet layers)"""
+        grids = (Grid * self.L)()
+        bufs = (LevelBufs * self.L)()
+        for l, j in enumerate(self.jacs):
+            grids[l] = j.grid_struct(self.u[l])
+            bufs[l].u, bufs[l].u_alt, bufs[l].f = self.u[l].ptr, self.u_alt[l].ptr, self.f[l].ptr
+        self._grids, self._bufs = grids, bufs
+        cfg = CycleCfg()
+        cfg.nu1, cfg.nu2 = self.nu1, self.nu2
+        cfg.smoother = mgfea.SMOOTH_HJACOBI if self.smoother == "hjac" else mgfea.SMOOTH_JACOBI
+        keep = []
+        if self.smoother == "hjac":
+            ws = [l.weight for l in self.hnet.convLayers]
+            sid = tuple((w.data_ptr(), w._version) for w in ws)
+            if getattr(self, "_hw_dev", None) is None or self._hw_dev.shape[0] != len(ws):
+                self._hw_dev, self._hw_sid = torch.zeros((len(ws), 9), dtype=torch.float32, device=self.dev), None
+            if sid != self._hw_sid:  # persistent device buffer: the pointer stays valid for captured graphs
+                self._hw_dev.copy_(torch.stack([w.detach().reshape(9).float().cpu() for w in ws]))
+                self._hw_sid = sid
+            cfg.hw, cfg.nlayers = self._hw_dev.data_ptr(), len(ws)
+        rt = self._table("r", self._rtab_src, FULL_WEIGHTING_16)
+        keep.append(rt)
+        cfg.rtab, cfg.rtab_n = rt.data_ptr(), rt.shape[0]
+        cfg.prolong_mode = mgfea.PROLONG_TABLE if self.prolong == "table" else mgfea.PROLONG_BILINEAR
+        if self.prolong == "table":
+            pt = self._table("p", self._ptab_src, LINEAR_4)
+            keep.append(pt)
+            cfg.ptab, cfg.ptab_n = pt.data_ptr(), pt.shape[0]
+        if self.w_param is not None:
+            w = self._tabs["w"].get(self.w_param)
+            keep.append(w)
+            cfg.r_has_scale = cfg.p_has_scale = 1
+            cfg.r_scale_dev, cfg.p_scale_dev = w.data_ptr(), w.data_ptr() + 4
+        else:
+            cfg.r_has_scale = int(self.r_scale is not None)
+            cfg.r_scale_host = float(self.r_scale or 0.0)
+            cfg.p_has_scale = int(self.p_scale is not None)
+            cfg.p_scale_host = float(self.p_scale or 0.0)
+        cfg.quirk_level0 = int(self.quirk_level0)
+        cfg.compute_norm = 1
+        self._cfg = cfg
+        self._keep = keep
+        sig = (cfg.hw, cfg.rtab, cfg.ptab, cfg.r_scale_dev, tuple(g.ktab for g in grids), tuple(g.bc_idx for g in grids),
+               self.nu1, self.nu2)
+        if sig != self._graph_key:
+            self._graph, self._graph_key = None, sig
+
+    # -- problem data --------------------------------------------------------------------------------------
+    def set_u(self, u):
+        self._load(self.u[0], u)
+
+    def set_f(self, f):
+        self._load(self.f[0], f)
+
+    def _load(self, dst: Field, x):
+        fld = getattr(x, "_mgfea_field", None)
+        if fld is dst:
+            return
+        x = torch.as_tensor(x)
+        if x.dim() == 2:
+            x = x[None, None]
+        elif x.dim() == 3:
+            x = x[:, None]
+        if x.shape[0] != dst.B and x.shape[0] == 1:
+            x = x.expand(dst.B, -1, -1, -1)
+        if tuple(x.shape) != (dst.B, 1, dst.N, dst.N):
+            raise mgfea.MgfeaError(f"field shape {tuple(x.shape)} does not match level ({dst.B},1,{dst.N},{dst.N})")
+        # strided copy straight into the padded layout (H2D when x lives on the host)
+        dst.view.copy_(x.to(dtype=torch.float32), non_blocking=True)
+
+    # -- cycles --------------------------------------------------------------------------------------------
+    def _ctl_reset(self, min_cycles, eps2, max_cycles):
+        c = Ctl()
+        c.cycle, c.done, c.min_cycles, c.max_cycles = 0, 0, int(min_cycles), int(max_cycles)
+        c.conv_rule, c.eps2 = self.conv_rule, eps2
+        raw = np.frombuffer(bytes(c), dtype=np.int32).copy()
+        self.ctl.copy_(torch.from_numpy(raw), non_blocking=False)
+
+    def cycle(self, use_ctl=False):
+        """one V-cycle, eager launch sequence (no graph); the interior residual sum of squares lands in self.sumsq"""
+        check(lib().mgfea_vcycle(self._grids, self._bufs, self.L, ctypes.byref(self._cfg), self.sumsq.data_ptr(),
+                                 self.ctl.data_ptr() if use_ctl else None, self.hist.data_ptr() if use_ctl else None,
+                                 self.B, stream_ptr()))
+
+    def residual_sumsq(self):
+        """per-sample interior sum of squares of f - K u on level 0 (device tensor, float64)"""
+        check(lib().mgfea_residual_norm(ctypes.byref(self._grids[0]), self.u[0].ptr, self.f[0].ptr,
+                                        self.sumsq.data_ptr(), None, None, self.B, stream_ptr()))
+        return self.sumsq
+
+    def _ensure_graph(self):
+        if self._graph is not None:
+            return
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        # warm the lazily initialised pieces (function attributes, tensor maps) on a side stream with the done flag set
+        # so that no field is modified: every kernel returns immediately when ctl->done != 0
+        saved = self.ctl.clone()
+        self.ctl[1] = 1
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self.cycle(use_ctl=True)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.ctl.copy_(saved)
+        with torch.cuda.graph(g):
+            self.cycle(use_ctl=True)
+        self._graph = g
+
+    def run(self, n_iter=None, EPS=None, max_cycles=None, chunk=4, use_graph=True):
+        """Multigrid.Solve loop: repeat cycles while (res > EPS or n < n_iter).  Returns the list of per-cycle interior
+        residual 2-norms (whole batch for CONV_SUM; per-sample array rows for CONV_MAX via self.last_hist)."""
+        if n_iter is None:
+            if EPS is None:
+                print("At least one of EPS and n_iter have to be assigned")
+                return None
+            n_iter = 0
+        elif EPS is None:
+            EPS = math.inf
+        cap = min(max_cycles or self.max_cycles, self.max_cycles)
+        if n_iter > cap:
+            raise mgfea.MgfeaError(f"n_iter={n_iter} exceeds the history capacity {cap}")
+        eps2 = float(EPS) * float(EPS) if math.isfinite(EPS) else 1.7e308
+        self.refresh()
+        self._ctl_reset(n_iter, eps2, cap)
+        if use_graph:
+            self._ensure_graph()
+        done = False
+        while not done:
+            for _ in range(chunk):
+                if use_graph:
+                    self._graph.replay()
+                else:
+                    self.cycle(use_ctl=True)
+            self._ctl_host.copy_(self.ctl, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            done = bool(self._ctl_host[1].item())
+        ncyc = int(self._ctl_host[0].item())
+        h = self.hist[:ncyc].cpu().numpy()
+        self.last_hist = h
+        if self.conv_rule == mgfea.CONV_SUM:
+            return [float(math.sqrt(v)) for v in h.sum(axis=1)]
+        return [np.sqrt(row) for row in h]
+
+    @property
+    def solution(self):
+        return self.u[0].view

@@ -1,0 +1,235 @@
+"""ctypes binding of libmgfea.so (C ABI in include/mgfea.h) for torch CUDA tensors.
+
+PyTorch is plumbing here: device memory, streams, H2D/D2H copies.  Every numerical operation on the V-cycle path is a
+call into the hand-written sm_100a kernels of ``csrc/``.  There is NO CPU / eager fallback: if the shared library is
+missing or no CUDA device is present, operations raise ``MgfeaError``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmgfea.so")
+CSRC = os.path.join(_HERE, "csrc")
+INCLUDE = os.path.abspath(os.path.join(_HERE, "..", "..", "include"))
+
+SMOOTH_JACOBI, SMOOTH_HJACOBI = 0, 1
+PROLONG_BILINEAR, PROLONG_TABLE = 1, 3
+CONV_SUM, CONV_MAX = 0, 1
+
+EXPORTS = [
+    "mgfea_version", "mgfea_error_string", "mgfea_set_loader", "mgfea_launch_count", "mgfea_pack", "mgfea_unpack",
+    "mgfea_stiffness_apply", "mgfea_load_vector", "mgfea_split_x", "mgfea_reset_boundary", "mgfea_smooth",
+    "mgfea_residual", "mgfea_restrict", "mgfea_smooth_residual_restrict", "mgfea_prolong_correct_smooth",
+    "mgfea_residual_norm", "mgfea_vcycle", "mgfea_restrict_channels", "mgfea_prolong_channels",
+]
+
+
+class MgfeaError(RuntimeError):
+    pass
+
+
+def build(verbose: bool = False) -> str:
+    """Compile csrc/mgfea.cu for sm_100a into libmgfea.so (in-tree).  nvcc cross-compiles without a GPU."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(INCLUDE, "mgfea.h")]
+    if os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+        return LIB_PATH
+    cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
+           "-Xcompiler", "-fPIC", os.path.join(CSRC, "mgfea.cu"), "-o", LIB_PATH]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+class Grid(ctypes.Structure):
+    _fields_ = [("N", ctypes.c_int32), ("pitch", ctypes.c_int32), ("plane", ctypes.c_int64), ("npat", ctypes.c_int32),
+                ("key_pitch", ctypes.c_int32), ("keys", ctypes.c_void_p), ("ktab", ctypes.c_void_p),
+                ("invd", ctypes.c_void_p), ("bc_idx", ctypes.c_void_p), ("bc_val", ctypes.c_void_p),
+                ("bc_plane", ctypes.c_int64)]
+
+
+class Ctl(ctypes.Structure):
+    _fields_ = [("cycle", ctypes.c_int32), ("done", ctypes.c_int32), ("min_cycles", ctypes.c_int32),
+                ("max_cycles", ctypes.c_int32), ("conv_rule", ctypes.c_int32), ("pad_", ctypes.c_int32),
+                ("eps2", ctypes.c_double)]
+
+
+class CycleCfg(ctypes.Structure):
+    _fields_ = [("nu1", ctypes.c_int32), ("nu2", ctypes.c_int32), ("smoother", ctypes.c_int32),
+                ("nlayers", ctypes.c_int32), ("hw", ctypes.c_void_p), ("prolong_mode", ctypes.c_int32),
+                ("rtab_n", ctypes.c_int32), ("rtab", ctypes.c_void_p), ("ptab_n", ctypes.c_int32),
+                ("r_has_scale", ctypes.c_int32), ("ptab", ctypes.c_void_p), ("r_scale_host", ctypes.c_float),
+                ("p_scale_host", ctypes.c_float), ("r_scale_dev", ctypes.c_void_p), ("p_scale_dev", ctypes.c_void_p),
+                ("p_has_scale", ctypes.c_int32), ("quirk_level0", ctypes.c_int32), ("tail_max_n", ctypes.c_int32),
+                ("compute_norm", ctypes.c_int32)]
+
+
+class LevelBufs(ctypes.Structure):
+    _fields_ = [("u", ctypes.c_void_p), ("u_alt", ctypes.c_void_p), ("f", ctypes.c_void_p)]
+
+
+_lib = None
+
+
+def lib():
+    """The loaded C-ABI library; fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MgfeaError(f"{LIB_PATH} not found: run __graft_entry__.build() (nvcc, sm_100a). "
+                             "There is no CPU fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        L.mgfea_version.restype = ctypes.c_char_p
+        L.mgfea_error_string.restype = ctypes.c_char_p
+        L.mgfea_error_string.argtypes = [ctypes.c_int]
+        L.mgfea_launch_count.restype = ctypes.c_uint64
+        vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+        G = ctypes.POINTER(Grid)
+        L.mgfea_set_loader.argtypes = [i32]
+        L.mgfea_pack.argtypes = [vp, vp, i32, i32, i64, i32, vp]
+        L.mgfea_unpack.argtypes = [vp, vp, i32, i32, i64, i32, vp]
+        L.mgfea_stiffness_apply.argtypes = [G, vp, vp, i32, vp]
+        L.mgfea_load_vector.argtypes = [vp, vp, vp, i32, i32, i64, i32, vp]
+        L.mgfea_split_x.argtypes = [G, vp, vp, i32, vp]
+        L.mgfea_reset_boundary.argtypes = [G, vp, vp, i32, vp]
+        L.mgfea_smooth.argtypes = [G, vp, vp, vp, i32, i32, vp, i32, i32, vp]
+        L.mgfea_residual.argtypes = [G, vp, vp, vp, i32, vp]
+        L.mgfea_restrict.argtypes = [G, vp, vp, i32, i64, vp, i32, i32, f32, vp, i32, vp]
+        L.mgfea_smooth_residual_restrict.argtypes = [G, vp, vp, vp, i32, i32, vp, i32, vp, i32, i64, vp, i32, i32, f32,
+                                                     vp, i32, vp]
+        L.mgfea_prolong_correct_smooth.argtypes = [G, G, vp, vp, vp, vp, i32, vp, i32, i32, f32, vp, i32, i32, vp, i32,
+                                                   i32, vp]
+        L.mgfea_restrict_channels.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+        L.mgfea_prolong_channels.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+        L.mgfea_residual_norm.argtypes = [G, vp, vp, vp, vp, vp, i32, vp]
+        L.mgfea_vcycle.argtypes = [ctypes.POINTER(Grid), ctypes.POINTER(LevelBufs), i32, ctypes.POINTER(CycleCfg), vp,
+                                   vp, vp, i32, vp]
+        _lib = L
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise MgfeaError(f"libmgfea error {rc}: {lib().mgfea_error_string(rc).decode()}")
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise MgfeaError("mgfea needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(lib().mgfea_launch_count())
+
+
+def set_loader(use_tma: bool) -> int:
+    return int(lib().mgfea_set_loader(1 if use_tma else 0))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# padded-pitch fields
+# ----------------------------------------------------------------------------------------------------------
+def pitch_for(N: int) -> int:
+    """row pitch in floats: rows start on 128-byte boundaries (N = 2^k + 1 is odd)"""
+    return (N + 31) // 32 * 32
+
+
+class Field:
+    """fp32 field [B][N][pitch] in HBM; `.view` is the (B,1,N,N) strided torch view handed to API users."""
+
+    __slots__ = ("store", "B", "N", "pitch")
+
+    def __init__(self, B: int, N: int, device=None, store: Optional[torch.Tensor] = None):
+        self.B, self.N, self.pitch = B, N, pitch_for(N)
+        if store is None:
+            store = torch.zeros((B, N, self.pitch), dtype=torch.float32, device=device or require_cuda())
+        self.store = store
+
+    @property
+    def plane(self) -> int:
+        return self.N * self.pitch
+
+    @property
+    def ptr(self) -> int:
+        return self.store.data_ptr()
+
+    @property
+    def view(self) -> torch.Tensor:
+        v = self.store[:, None, :, : self.N]
+        v._mgfea_field = self  # lets as_field() recognise our own buffers without a copy
+        return v
+
+    def zero_(self):
+        self.store.zero_()
+        return self
+
+
+def as_field(x: torch.Tensor, device=None) -> Field:
+    """Accept a (B,1,N,N) / (B,N,N) / (N,N) tensor on any device and return a padded device Field.
+    Our own strided views are used in place; anything else is copied (H2D if needed) and packed by mgfea_pack."""
+    fld = getattr(x, "_mgfea_field", None)
+    if fld is not None and x.is_cuda and x.data_ptr() == fld.ptr:
+        return fld
+    dev = device or require_cuda()
+    if x.dim() == 4:
+        if x.shape[1] != 1:
+            raise MgfeaError(f"expected a single-channel field, got {tuple(x.shape)}")
+        x3 = x[:, 0]
+    elif x.dim() == 2:
+        x3 = x[None]
+    else:
+        x3 = x
+    B, N, N2 = x3.shape
+    if N != N2:
+        raise MgfeaError("fields must be square")
+    xc = x3.detach().to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+    out = Field(B, N, dev, store=torch.empty((B, N, pitch_for(N)), dtype=torch.float32, device=dev))
+    check(lib().mgfea_pack(xc.data_ptr(), out.ptr, N, out.pitch, out.plane, B, stream_ptr()))
+    return out
+
+
+def to_contiguous(fld: Field) -> torch.Tensor:
+    out = torch.empty((fld.B, 1, fld.N, fld.N), dtype=torch.float32, device=fld.store.device)
+    check(lib().mgfea_unpack(fld.ptr, out.data_ptr(), fld.N, fld.pitch, fld.plane, fld.B, stream_ptr()))
+    return out
+
+
+def pack_keys(keys_u8) -> torch.Tensor:
+    """uint8 (N,N) numpy/torch -> device tensor [N][key_pitch] with key_pitch % 16 == 0 (zero padded)"""
+    dev = require_cuda()
+    k = torch.as_tensor(keys_u8, dtype=torch.uint8)
+    N = k.shape[0]
+    kp = (N + 127) // 128 * 128
+    out = torch.zeros((N, kp), dtype=torch.uint8, device=dev)
+    out[:, :N] = k.to(dev)
+    return out
+
+
+class DeviceTable:
+    """Device copy of a small live parameter tensor, refreshed when the parameter changes (load_state_dict, in-place
+    edits bump torch's version counter), so the kernels always see the current weights."""
+
+    def __init__(self):
+        self._src_id = None
+        self._dev = None
+
+    def get(self, t: torch.Tensor) -> torch.Tensor:
+        t = t.detach()
+        if t.is_cuda and t.dtype == torch.float32 and t.is_contiguous():
+            return t
+        sid = (t.data_ptr(), t._version, tuple(t.shape))
+        if sid != self._src_id:
+            self._dev = t.to(device=require_cuda(), dtype=torch.float32).contiguous()
+            self._src_id = sid
+        return self._dev

@@ -1,0 +1,1210 @@
+// libmgfea.so -- sm_100a kernels + C ABI (include/mgfea.h) for the Multigrid-FEANet V-cycle.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC mgfea.cu -o libmgfea.so
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../../include/mgfea.h"
+#include "mgfea_tile.cuh"
+
+namespace mgfea {
+
+// =========================================================================================================
+// The tile kernel
+// =========================================================================================================
+struct StageBufs {
+    float *U, *F, *VC, *IDX, *BVAL;
+    unsigned char *K, *KC;
+};
+
+__device__ __forceinline__ StageBufs stage_bufs(unsigned char *smem, const TileParams &p, int s) {
+    unsigned char *base = smem + p.off_stage0 + s * p.stage_bytes;
+    StageBufs sb;
+    sb.U = reinterpret_cast<float *>(base + p.so_u);
+    sb.F = reinterpret_cast<float *>(base + p.so_f);
+    sb.K = base + p.so_k;
+    sb.VC = reinterpret_cast<float *>(base + p.so_vc);
+    sb.KC = base + p.so_kc;
+    sb.IDX = reinterpret_cast<float *>(base + p.so_idx);
+    sb.BVAL = reinterpret_cast<float *>(base + p.so_bval);
+    return sb;
+}
+
+struct TileCoord {
+    int b, y0, x0, gy0, gx0, cy0, cx0;
+};
+__device__ __forceinline__ TileCoord tile_coord(const TileParams &p, int t) {
+    TileCoord tc;
+    const int per = p.ntx * p.nty;
+    tc.b = t / per;
+    const int rem = t - tc.b * per;
+    const int ty = rem / p.ntx, tx = rem - ty * p.ntx;
+    tc.y0 = ty * p.TH;
+    tc.x0 = tx * p.TWI;
+    tc.gy0 = tc.y0 - p.HT;
+    tc.gx0 = tc.x0 - p.HX;
+    tc.cy0 = tc.gy0 >> 1;  // floor
+    tc.cx0 = tc.gx0 >> 1;
+    return tc;
+}
+
+// cooperative cp.async copy of a [rows][rowbytes] box; CH = chunk bytes (4, 8 or 16), zero fill outside
+template <int CHB>
+__device__ __forceinline__ void cpasync_box(unsigned char *dst, const unsigned char *gbase, long long gpitch_bytes,
+                                            int nrows_glob, int pitch_bytes_valid, int gy0, int gxb0, int rows,
+                                            int rowbytes) {
+    const int cpr = rowbytes / CHB;
+    for (int i = threadIdx.x; i < rows * cpr; i += NTHREADS) {
+        const int r = i / cpr, cb = (i - r * cpr) * CHB;
+        const int gy = gy0 + r, gxb = gxb0 + cb;
+        const bool ok = (gy >= 0 && gy < nrows_glob && gxb >= 0 && gxb + CHB <= pitch_bytes_valid);
+        const unsigned char *src = ok ? (gbase + (long long)gy * gpitch_bytes + gxb) : gbase;
+        unsigned char *d = dst + r * rowbytes + cb;
+        if (CHB == 16) {
+            cp_async16(d, src, ok);
+        } else {
+            const uint32_t sz = ok ? (uint32_t)CHB : 0u;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(smem_u32(d)), "l"(src), "n"(CHB),
+                         "r"(sz)
+                         : "memory");
+        }
+    }
+}
+
+template <bool KEYS, bool GBC>
+__device__ __forceinline__ void issue_loads(unsigned char *smem, const TileMaps &maps, const TileParams &p,
+                                            Tables &T, int t, int s) {
+    const TileCoord tc = tile_coord(p, t);
+    const StageBufs sb = stage_bufs(smem, p, s);
+    const bool need_u = !p.zero_init;
+    const bool need_f = (p.nsweeps > 0) || (p.out_mode != OUT_NONE && p.out_mode != OUT_KU);
+    const int bcb = (p.bc_plane == 0) ? 0 : tc.b;
+    if (p.use_tma) {
+        if (threadIdx.x == 0) {
+            uint64_t *bar = reinterpret_cast<uint64_t *>(&T.mbar[s]);
+            mbar_arrive_expect_tx(bar, p.tx_bytes);
+            if (need_u) tma_load_3d(sb.U, &maps.u, bar, tc.gx0, tc.gy0, tc.b);
+            if (need_f) tma_load_3d(sb.F, &maps.f, bar, tc.gx0, tc.gy0, tc.b);
+            if (KEYS) tma_load_2d(sb.K, &maps.k, bar, tc.gx0, tc.gy0);
+            if (p.prolong_mode) {
+                tma_load_3d(sb.VC, &maps.vc, bar, tc.cx0, tc.cy0, tc.b);
+                if (p.keys_c) tma_load_2d(sb.KC, &maps.kc, bar, tc.cx0, tc.cy0);
+            }
+            if (GBC) {
+                tma_load_3d(sb.IDX, &maps.idx, bar, tc.gx0, tc.gy0, bcb);
+                tma_load_3d(sb.BVAL, &maps.bval, bar, tc.gx0, tc.gy0, bcb);
+            }
+        }
+    } else {
+        const long long pb = (long long)p.pitch * 4;
+        if (need_u)
+            cpasync_box<16>(reinterpret_cast<unsigned char *>(sb.U),
+                            reinterpret_cast<const unsigned char *>(p.u_in + (long long)tc.b * p.plane), pb, p.N,
+                            p.pitch * 4, tc.gy0, tc.gx0 * 4, p.BH, BW * 4);
+        if (need_f)
+            cpasync_box<16>(reinterpret_cast<unsigned char *>(sb.F),
+                            reinterpret_cast<const unsigned char *>(p.f + (long long)tc.b * p.plane), pb, p.N,
+                            p.pitch * 4, tc.gy0, tc.gx0 * 4, p.BH, BW * 4);
+        if (KEYS) cpasync_box<4>(sb.K, p.keys, p.key_pitch, p.N, p.key_pitch, tc.gy0, tc.gx0, p.BH, BW);
+        if (p.prolong_mode) {
+            cpasync_box<8>(reinterpret_cast<unsigned char *>(sb.VC),
+                           reinterpret_cast<const unsigned char *>(p.vc + (long long)tc.b * p.plane_c),
+                           (long long)p.pitch_c * 4, p.Nc, p.pitch_c * 4, tc.cy0, tc.cx0 * 4, p.CH, CW * 4);
+            if (p.keys_c) {  // coarse key box starts at an even (2-byte aligned) column: plain byte loads
+                for (int i = threadIdx.x; i < p.CH * KCW; i += NTHREADS) {
+                    const int r = i / KCW, cb = i - r * KCW;
+                    const int gy = tc.cy0 + r, gx = tc.cx0 + cb;
+                    sb.KC[i] = (gy >= 0 && gy < p.Nc && gx >= 0 && gx < p.Nc)
+                                   ? p.keys_c[(long long)gy * p.key_pitch_c + gx]
+                                   : (unsigned char)0;
+                }
+            }
+        }
+        if (GBC) {
+            cpasync_box<16>(reinterpret_cast<unsigned char *>(sb.IDX),
+                            reinterpret_cast<const unsigned char *>(p.bc_idx + (long long)bcb * p.bc_plane), pb, p.N,
+                            p.pitch * 4, tc.gy0, tc.gx0 * 4, p.BH, BW * 4);
+            cpasync_box<16>(reinterpret_cast<unsigned char *>(sb.BVAL),
+                            reinterpret_cast<const unsigned char *>(p.bc_val + (long long)bcb * p.bc_plane), pb, p.N,
+                            p.pitch * 4, tc.gy0, tc.gx0 * 4, p.BH, BW * 4);
+        }
+        cp_async_commit();
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <bool KEYS, bool GBC>
+__global__ void __launch_bounds__(NTHREADS) mg_tile_kernel(const __grid_constant__ TileMaps maps,
+                                                           const TileParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    Tables &T = *reinterpret_cast<Tables *>(smem);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (p.ctl != nullptr && ld_volatile_s32(&reinterpret_cast<const Ctl *>(p.ctl)->done) != 0) return;
+
+    // ---- tables (live weights are read from device memory at every launch) and barriers
+    for (int i = tid; i < MAXPAT * 9; i += NTHREADS) {
+        T.ktab[i] = (p.ktab != nullptr && i < p.npat * 9) ? p.ktab[i] : 0.0f;
+        T.rtab[i] = (p.rtab != nullptr && i < p.rtab_n * 9) ? p.rtab[i] : 0.0f;
+        T.ptab[i] = (p.ptab != nullptr && i < p.ptab_n * 9) ? p.ptab[i] : 0.0f;
+    }
+    if (tid < MAXPAT) T.invd[tid] = (p.invd != nullptr && tid < p.npat) ? p.invd[tid] : 0.0f;
+    if (tid < MAXLAYERS * 9) T.hw[tid] = (p.hw != nullptr && tid < p.nlayers * 9) ? p.hw[tid] : 0.0f;
+    if (tid == 0) {
+        T.r_scale = p.r_scale_dev ? *p.r_scale_dev : p.r_scale;
+        T.p_scale = p.p_scale_dev ? *p.p_scale_dev : p.p_scale;
+        mbar_init(reinterpret_cast<uint64_t *>(&T.mbar[0]), 1);
+        mbar_init(reinterpret_cast<uint64_t *>(&T.mbar[1]), 1);
+        fence_mbar_init();
+        if (p.use_tma) {
+            tma_prefetch_desc(&maps.u);
+            tma_prefetch_desc(&maps.f);
+        }
+    }
+    __syncthreads();
+
+    float *W1 = reinterpret_cast<float *>(smem + p.off_w1);
+    float *W2 = reinterpret_cast<float *>(smem + p.off_w2);
+    float *W3 = reinterpret_cast<float *>(smem + p.off_w3);
+
+    int s = 0;
+    uint32_t phase[2] = {0u, 0u};
+    int t = blockIdx.x;
+    if (t < p.ntiles) issue_loads<KEYS, GBC>(smem, maps, p, T, t, 0);
+
+    for (; t < p.ntiles; t += gridDim.x) {
+        const int tn = t + gridDim.x;
+        const bool has_next = tn < p.ntiles;
+        if (has_next) issue_loads<KEYS, GBC>(smem, maps, p, T, tn, s ^ 1);
+        if (p.use_tma) {
+            mbar_wait(reinterpret_cast<uint64_t *>(&T.mbar[s]), phase[s]);
+            phase[s] ^= 1u;
+        } else {
+            if (has_next)
+                cp_async_wait<1>();
+            else
+                cp_async_wait<0>();
+            __syncthreads();
+        }
+
+        // ---- tile context
+        const TileCoord tc = tile_coord(p, t);
+        const StageBufs sb = stage_bufs(smem, p, s);
+        TileCtx c;
+        c.U = sb.U;
+        c.F = sb.F;
+        c.K = sb.K;
+        c.VC = sb.VC;
+        c.KC = p.keys_c ? sb.KC : nullptr;
+        c.IDX = sb.IDX;
+        c.BVAL = sb.BVAL;
+        c.W1 = W1;
+        c.W2 = W2;
+        c.W3 = W3;
+        c.gy0 = tc.gy0;
+        c.gx0 = tc.gx0;
+        c.cy0 = tc.cy0;
+        c.cx0 = tc.cx0;
+        c.b = tc.b;
+        c.BH = p.BH;
+        c.N = p.N;
+        c.keys_uniform = true;
+        c.k0 = 0;
+        c.touches_edge = (tc.gy0 <= 0) || (tc.gy0 + p.BH - 1 >= p.N - 1) || (tc.gx0 <= 0) || (tc.gx0 + BW - 1 >= p.N - 1);
+        if (KEYS) {
+            const unsigned int *kw = reinterpret_cast<const unsigned int *>(c.K);
+            const unsigned int first = (unsigned int)c.K[0] * 0x01010101u;
+            int ok = 1;
+            for (int i = tid; i < p.BH * (BW / 4); i += NTHREADS) ok &= (kw[i] == first);
+            c.keys_uniform = __syncthreads_and(ok) != 0;
+            c.k0 = c.K[0];
+        }
+        if (p.zero_init) {
+            for (int i = tid; i < p.BH * (BW / 4); i += NTHREADS)
+                reinterpret_cast<float4 *>(c.U)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncthreads();
+        }
+
+        // ---- program
+        int d = 0;
+        float *cur = c.U;
+        if (p.prolong_mode) {
+            stage_prolong<GBC>(c, T, p, c.U);
+            __syncthreads();
+        }
+        if (p.nsweeps == 0 && p.smoother == 2) {  // reset_boundary only
+            stage_reset<GBC>(c, cur, cur, 0, p.BH);
+            __syncthreads();
+        }
+        for (int sw = 0; sw < p.nsweeps; ++sw) {
+            if (p.smoother == 0) {
+                if (GBC || (sw == 0 && c.touches_edge)) {
+                    stage_reset<GBC>(c, cur, cur, d, p.BH - d);
+                    __syncthreads();
+                }
+                float *dst = (cur == c.U) ? W1 : c.U;
+                stage_jacobi<KEYS, GBC, false>(c, T, cur, dst, nullptr, nullptr, d + 1, p.BH - d - 1);
+                __syncthreads();
+                cur = dst;
+                d += 1;
+            } else {
+                stage_reset<GBC>(c, cur, W3, d, p.BH - d);
+                __syncthreads();
+                stage_jacobi<KEYS, GBC, true>(c, T, W3, W1, cur, W2, d + 1, p.BH - d - 1);
+                __syncthreads();
+                float *src = W2, *dst = W3;
+                for (int l = 0; l < p.nlayers; ++l) {
+                    const int dd = d + 2 + l;
+                    if (l == p.nlayers - 1)
+                        stage_hlayer<GBC, true>(c, T.hw + 9 * l, src, cur, W1, dd, p.BH - dd);
+                    else
+                        stage_hlayer<GBC, false>(c, T.hw + 9 * l, src, dst, nullptr, dd, p.BH - dd);
+                    __syncthreads();
+                    float *tmp = src;
+                    src = dst;
+                    dst = tmp;
+                }
+                d += 1 + p.nlayers;
+            }
+        }
+        if (p.store_u) stage_store_u(c, p, cur);
+        if (p.out_mode == OUT_RESIDUAL) {
+            stage_out<KEYS, OUT_RESIDUAL>(c, T, p, cur, nullptr, d + 1, p.BH - d - 1);
+        } else if (p.out_mode == OUT_KU) {
+            stage_out<KEYS, OUT_KU>(c, T, p, cur, nullptr, d + 1, p.BH - d - 1);
+        } else if (p.out_mode == OUT_RESTRICT) {
+            stage_out<KEYS, OUT_RESTRICT>(c, T, p, cur, c.F, d + 1, p.BH - d - 1);
+            __syncthreads();
+            stage_restrict<KEYS>(c, T, p, c.F);
+        } else if (p.out_mode == OUT_NORM) {
+            double part = stage_out<KEYS, OUT_NORM>(c, T, p, cur, nullptr, d + 1, p.BH - d - 1);
+            part = warp_sum(part);
+            if (lane == 0) T.red[warp] = part;
+            __syncthreads();
+            if (tid == 0) {
+                double sum = 0.0;
+#pragma unroll
+                for (int w = 0; w < NWARPS; ++w) sum += T.red[w];
+                p.tile_partials[t] = sum;
+            }
+        }
+        // generic-proxy accesses to this stage's buffers are done; order them before the next TMA write into it
+        fence_proxy_async_smem();
+        __syncthreads();
+        s ^= 1;
+    }
+
+    // ---- deterministic final reduction of the per-tile partial sums by the last CTA to finish
+    if (p.out_mode == OUT_NORM) {
+        __threadfence();
+        if (tid == 0) {
+            const unsigned int ticket = atomicAdd(p.counter, 1u);
+            T.flag = (ticket == gridDim.x - 1) ? 1 : 0;
+        }
+        __syncthreads();
+        if (T.flag) {
+            __threadfence();
+            const int per = p.ntx * p.nty;
+            Ctl *ctl = reinterpret_cast<Ctl *>(p.ctl);
+            double tot = 0.0, mx = 0.0;
+            for (int b = 0; b < p.B; ++b) {
+                double v = 0.0;
+                for (int i = tid; i < per; i += NTHREADS) v += __ldcg(p.tile_partials + (long long)b * per + i);
+                v = warp_sum(v);
+                __syncthreads();
+                if (lane == 0) T.red[warp] = v;
+                __syncthreads();
+                if (tid == 0) {
+                    double sum = 0.0;
+                    for (int w = 0; w < NWARPS; ++w) sum += T.red[w];
+                    if (p.sumsq) p.sumsq[b] = sum;
+                    if (ctl && p.hist && ctl->cycle < ctl->max_cycles) p.hist[(long long)ctl->cycle * p.B + b] = sum;
+                    tot += sum;
+                    mx = sum > mx ? sum : mx;
+                }
+            }
+            if (tid == 0) {
+                if (ctl) {
+                    const int cyc = ctl->cycle + 1;
+                    ctl->cycle = cyc;
+                    const double metric = (ctl->conv_rule == 1) ? mx : tot;
+                    bool done = false;
+                    if (ctl->eps2 >= 0.0 && cyc >= ctl->min_cycles && metric <= ctl->eps2) done = true;
+                    if (cyc >= ctl->max_cycles) done = true;
+                    if (!(metric == metric) || metric > 1.7e308) done = true;  // NaN / Inf divergence guard
+                    if (done) ctl->done = 1;
+                }
+                *p.counter = 0u;
+                __threadfence();
+            }
+        }
+    }
+}
+
+// =========================================================================================================
+// small layout / API-only kernels
+// =========================================================================================================
+__global__ void pack_kernel(const float *__restrict__ src, float *__restrict__ dst, int N, int pitch, long long plane,
+                            int B) {
+    const long long total = (long long)B * N * pitch;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % pitch);
+        const long long ry = i / pitch;
+        const int y = (int)(ry % N);
+        const long long b = ry / N;
+        dst[b * plane + (long long)y * pitch + x] = (x < N) ? src[(b * N + y) * (long long)N + x] : 0.0f;
+    }
+}
+__global__ void unpack_kernel(const float *__restrict__ src, float *__restrict__ dst, int N, int pitch,
+                              long long plane, int B) {
+    const long long total = (long long)B * N * N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % N);
+        const long long ry = i / N;
+        const int y = (int)(ry % N);
+        const long long b = ry / N;
+        dst[i] = src[b * plane + (long long)y * pitch + x];
+    }
+}
+__global__ void split_kernel(const float *__restrict__ x, float *__restrict__ out, const unsigned char *keys,
+                             int key_pitch, int C, int N, int pitch, long long plane, int B) {
+    const long long total = (long long)B * C * N * N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int xx = (int)(i % N);
+        long long r = i / N;
+        const int y = (int)(r % N);
+        r /= N;
+        const int c = (int)(r % C);
+        const long long b = r / C;
+        const int k = keys ? keys[(long long)y * key_pitch + xx] : 0;
+        out[i] = (k == c) ? x[b * plane + (long long)y * pitch + xx] : 0.0f;
+    }
+}
+
+
+// API-compat only (MultiGrid.Restrict / .Interpolate called directly with an already split (B,C,.,.) tensor; the V-cycle
+// itself uses the fused key-indexed stages).  Contiguous tensors.  Tap-major, channel-inner FMA chain: for a genuine
+// one-hot split this is bit-identical to the key-indexed form.
+__global__ void restrict_channels_kernel(const float *__restrict__ rF, float *__restrict__ fc,
+                                         const float *__restrict__ rtab, int C, int N, int B) {
+    const int Nc = (N - 1) / 2 + 1;
+    const long long total = (long long)B * Nc * Nc;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int J = (int)(i % Nc);
+        const int I = (int)((i / Nc) % Nc);
+        const long long b = i / ((long long)Nc * Nc);
+        float acc = 0.0f;
+        if (I >= 1 && J >= 1 && I <= Nc - 2 && J <= Nc - 2) {
+            for (int a = 0; a < 3; ++a)
+                for (int cc = 0; cc < 3; ++cc)
+                    for (int c = 0; c < C; ++c)
+                        acc = __fmaf_rn(rtab[9 * c + 3 * a + cc],
+                                        rF[((b * C + c) * N + (2 * I - 1 + a)) * (long long)N + (2 * J - 1 + cc)], acc);
+        }
+        fc[i] = acc;
+    }
+}
+__global__ void prolong_channels_kernel(const float *__restrict__ eFC, float *__restrict__ out,
+                                        const float *__restrict__ ptab, int C, int Nc, int B) {
+    const int N = 2 * Nc - 1;
+    const long long total = (long long)B * N * N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % N);
+        const int y = (int)((i / N) % N);
+        const long long b = i / ((long long)N * N);
+        float acc = 0.0f;
+        for (int a = 0; a < 3; ++a) {
+            if ((y + 1 - a) & 1) continue;
+            const int I = (y + 1 - a) / 2;
+            if (I < 0 || I >= Nc) continue;
+            for (int cc = 0; cc < 3; ++cc) {
+                if ((x + 1 - cc) & 1) continue;
+                const int J = (x + 1 - cc) / 2;
+                if (J < 0 || J >= Nc) continue;
+                for (int c = 0; c < C; ++c)
+                    acc = __fmaf_rn(ptab[9 * c + 3 * a + cc], eFC[((b * C + c) * Nc + I) * (long long)Nc + J], acc);
+            }
+        }
+        out[i] = acc;
+    }
+}
+
+// =========================================================================================================
+// host side
+// =========================================================================================================
+static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_use_tma{1};
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    });
+    return fn;
+}
+
+struct MapKey {
+    const void *ptr;
+    int dtype, rank;
+    unsigned long long d0, d1, d2, s1, s2;
+    unsigned int b0, b1;
+    bool operator==(const MapKey &o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapCache {
+    std::mutex mu;
+    std::vector<std::pair<MapKey, CUtensorMap>> items;
+};
+static MapCache g_maps;
+
+// rank 3 (fields, [B][rows][pitch]) or rank 2 (keys)
+static int make_map(CUtensorMap *out, const void *ptr, bool is_u8, int rank, unsigned long long d0,
+                    unsigned long long d1, unsigned long long d2, unsigned long long s1_bytes,
+                    unsigned long long s2_bytes, unsigned int b0, unsigned int b1) {
+    MapKey key;
+    memset(&key, 0, sizeof(key));
+    key.ptr = ptr;
+    key.dtype = is_u8;
+    key.rank = rank;
+    key.d0 = d0;
+    key.d1 = d1;
+    key.d2 = d2;
+    key.s1 = s1_bytes;
+    key.s2 = s2_bytes;
+    key.b0 = b0;
+    key.b1 = b1;
+    {
+        std::lock_guard<std::mutex> lk(g_maps.mu);
+        for (auto &it : g_maps.items)
+            if (it.first == key) {
+                *out = it.second;
+                return 0;
+            }
+    }
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return MGFEA_EDRIVER;
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {s1_bytes, s2_bytes};
+    cuuint32_t box[3] = {b0, b1, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(out, is_u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+                     const_cast<void *>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return MGFEA_EDRIVER;
+    std::lock_guard<std::mutex> lk(g_maps.mu);
+    if (g_maps.items.size() > 4096) g_maps.items.clear();
+    g_maps.items.emplace_back(key, *out);
+    return 0;
+}
+
+struct DeviceScratch {
+    int dev = -1;
+    int num_sms = 0;
+    double *tile_partials = nullptr;
+    size_t partial_cap = 0;
+    unsigned int *counter = nullptr;
+};
+static DeviceScratch g_scr[16];
+static std::mutex g_scr_mu;
+
+static int get_scratch(size_t ntiles, DeviceScratch **out) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    if (dev < 0 || dev >= 16) return MGFEA_EUNSUPPORTED;
+    std::lock_guard<std::mutex> lk(g_scr_mu);
+    DeviceScratch &s = g_scr[dev];
+    if (s.dev != dev) {
+        s.dev = dev;
+        cudaDeviceGetAttribute(&s.num_sms, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaMalloc(&s.counter, 64);
+        if (e != cudaSuccess) return (int)e;
+        cudaMemset(s.counter, 0, 64);
+    }
+    if (ntiles > s.partial_cap) {
+        // grow-only and never freed: a captured graph may still hold the previous pointer
+        size_t cap = ntiles < (1u << 20) ? (1u << 20) : ntiles * 2;
+        double *np = nullptr;
+        e = cudaMalloc(&np, cap * sizeof(double));
+        if (e != cudaSuccess) return (int)e;
+        s.tile_partials = np;
+        s.partial_cap = cap;
+    }
+    *out = &s;
+    return 0;
+}
+
+struct Program {
+    // inputs
+    const mgfea_grid *g = nullptr;
+    int B = 1;
+    const float *u_in = nullptr;  // NULL -> zero
+    float *u_out = nullptr;       // NULL -> no store
+    const float *f = nullptr;
+    int nsweeps = 0, smoother = 0, nlayers = 0;
+    const float *hw = nullptr;
+    int reset_only = 0;
+    // prolong
+    int prolong_mode = 0;
+    const mgfea_grid *gc = nullptr;
+    const float *vc = nullptr;
+    const float *ptab = nullptr;
+    int ptab_n = 0, p_has_scale = 0;
+    float p_scale = 1.0f;
+    const float *p_scale_dev = nullptr;
+    // out
+    int out_mode = OUT_NONE;
+    float *r_out = nullptr;
+    float *fc = nullptr;
+    int pitch_c = 0;
+    long long plane_c = 0;
+    const float *rtab = nullptr;
+    int rtab_n = 0, r_has_scale = 0;
+    float r_scale = 1.0f;
+    const float *r_scale_dev = nullptr;
+    double *sumsq = nullptr;
+    mgfea_ctl *ctl = nullptr;
+    double *hist = nullptr;
+    const float *ktab_override = nullptr;  // load_vector: single table instead of g->ktab
+    int ignore_keys = 0;
+};
+
+static inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
+
+template <bool KEYS, bool GBC>
+static cudaError_t launch_tile(const TileMaps &maps, const TileParams &p, int grid, size_t smem, cudaStream_t st) {
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(mg_tile_kernel<KEYS, GBC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             232448);
+        if (e != cudaSuccess) return e;
+        configured = 232448;
+    }
+    mg_tile_kernel<KEYS, GBC><<<grid, NTHREADS, smem, st>>>(maps, p);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
+static int check_field(const void *p, int pitch, long long plane) {
+    if (!p) return MGFEA_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(p) & 15u) || (pitch & 3) || (plane & 3)) return MGFEA_EALIGN;
+    return 0;
+}
+
+static int run_program(const Program &pr, cudaStream_t st) {
+    const mgfea_grid *g = pr.g;
+    if (!g || g->N < 3 || pr.B < 1) return MGFEA_EINVAL;
+    if (g->pitch < g->N || (g->pitch & 3)) return MGFEA_EALIGN;
+    if (g->npat < 1 || g->npat > MAXPAT) return MGFEA_EINVAL;
+    const bool keys = (g->keys != nullptr) && !pr.ignore_keys;
+    const bool gbc = (g->bc_idx != nullptr) && (pr.nsweeps > 0 || pr.reset_only || pr.prolong_mode == 1);
+    if (keys && (g->key_pitch & 15)) return MGFEA_EALIGN;
+    int rc;
+    if (pr.u_in && (rc = check_field(pr.u_in, g->pitch, g->plane))) return rc;
+    if (pr.u_out && (rc = check_field(pr.u_out, g->pitch, g->plane))) return rc;
+    if (pr.f && (rc = check_field(pr.f, g->pitch, g->plane))) return rc;
+    if (pr.nlayers > MAXLAYERS) return MGFEA_EUNSUPPORTED;
+
+    TileParams p;
+    memset(&p, 0, sizeof(p));
+    TileMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    p.N = g->N;
+    p.B = pr.B;
+    p.pitch = g->pitch;
+    p.plane = g->plane;
+    p.use_tma = g_use_tma.load();
+    p.zero_init = (pr.u_in == nullptr);
+    p.prolong_mode = pr.prolong_mode;
+    p.prolong_seq = (g->N <= 33);
+    p.nsweeps = pr.nsweeps;
+    p.smoother = pr.reset_only ? 2 : pr.smoother;
+    p.store_u = (pr.u_out != nullptr);
+    p.out_mode = pr.out_mode;
+    p.u_in = pr.u_in;
+    p.u_out = pr.u_out;
+    p.f = pr.f;
+    p.keys = keys ? g->keys : nullptr;
+    p.key_pitch = g->key_pitch;
+    p.npat = pr.ktab_override ? 1 : g->npat;
+    p.ktab = pr.ktab_override ? pr.ktab_override : g->ktab;
+    p.invd = g->invd;
+    p.bc_idx = gbc ? g->bc_idx : nullptr;
+    p.bc_val = gbc ? g->bc_val : nullptr;
+    p.bc_plane = g->bc_plane;
+    p.hw = pr.hw;
+    p.nlayers = pr.nlayers;
+    if (gbc && !g->bc_val) return MGFEA_EINVAL;
+    if (pr.nsweeps > 0 && (!pr.f || !g->invd || !p.ktab)) return MGFEA_EINVAL;
+    if (pr.nsweeps > 0 && pr.smoother == MGFEA_SMOOTH_HJACOBI && (!pr.hw || pr.nlayers < 1)) return MGFEA_EINVAL;
+
+    const bool need_f = (pr.nsweeps > 0) || (pr.out_mode != OUT_NONE && pr.out_mode != OUT_KU);
+    if (need_f && !pr.f) return MGFEA_EINVAL;
+
+    // ---- halo depth
+    const int sweep_depth = (pr.smoother == MGFEA_SMOOTH_HJACOBI) ? 1 + pr.nlayers : 1;
+    const int dS = pr.nsweeps * sweep_depth;
+    const int dout = (pr.out_mode != OUT_NONE) ? 1 : 0;
+    const int D = dS + dout;
+    const bool restr = (pr.out_mode == OUT_RESTRICT);
+    int HX;
+    if ((restr && D <= 3) || (!restr && D <= 4))
+        HX = 4;
+    else if ((restr && D <= 7) || (!restr && D <= 8))
+        HX = 8;
+    else
+        return MGFEA_EUNSUPPORTED;  // caller splits the sweeps over several launches
+    p.HX = HX;
+    p.TWI = BW - 2 * HX;
+    p.HT = D + (restr ? 1 : 0);
+    p.HB = D;
+    if (restr) {
+        if (!pr.fc || !pr.rtab || (pr.rtab_n != 1 && pr.rtab_n != g->npat)) return MGFEA_EINVAL;
+        if ((pr.pitch_c & 1) || (reinterpret_cast<uintptr_t>(pr.fc) & 7u) || (pr.plane_c & 1)) return MGFEA_EALIGN;
+    }
+    p.fc = pr.fc;
+    p.rtab = pr.rtab;
+    p.rtab_n = pr.rtab_n;
+    p.r_has_scale = pr.r_has_scale;
+    p.r_scale = pr.r_scale;
+    p.r_scale_dev = pr.r_scale_dev;
+    p.r_out = pr.r_out;
+    if ((pr.out_mode == OUT_RESIDUAL || pr.out_mode == OUT_KU) && (rc = check_field(pr.r_out, g->pitch, g->plane)))
+        return rc;
+    p.Nc = (g->N - 1) / 2 + 1;
+    p.pitch_c = pr.pitch_c;
+    p.plane_c = pr.plane_c;
+    if (pr.prolong_mode) {
+        if (!pr.gc || !pr.vc || pr.gc->N != p.Nc) return MGFEA_EINVAL;
+        if ((rc = check_field(pr.vc, pr.gc->pitch, pr.gc->plane))) return rc;
+        p.pitch_c = pr.gc->pitch;
+        p.plane_c = pr.gc->plane;
+        p.vc = pr.vc;
+        if (pr.prolong_mode == MGFEA_PROLONG_TABLE) {
+            if (!pr.ptab || (pr.ptab_n != 1 && pr.ptab_n != pr.gc->npat)) return MGFEA_EINVAL;
+            if (pr.ptab_n > 1 && pr.gc->keys) {
+                if (pr.gc->key_pitch & 15) return MGFEA_EALIGN;
+                p.keys_c = pr.gc->keys;
+                p.key_pitch_c = pr.gc->key_pitch;
+            }
+        }
+        p.ptab = pr.ptab;
+        p.ptab_n = pr.ptab_n;
+        p.p_has_scale = pr.p_has_scale;
+        p.p_scale = pr.p_scale;
+        p.p_scale_dev = pr.p_scale_dev;
+    }
+
+    // ---- pick TH so that the carve-up fits 227 KB
+    const bool hj = (pr.nsweeps > 0 && pr.smoother == MGFEA_SMOOTH_HJACOBI);
+    int TH = 32;
+    size_t smem = 0;
+    for (;; TH -= 8) {
+        if (TH < 8) return MGFEA_EUNSUPPORTED;
+        p.TH = TH;
+        p.BH = TH + p.HT + p.HB;
+        p.CH = p.BH / 2 + 2;
+        const int box = p.BH * BW * 4;
+        int off = 0;
+        p.so_u = off;
+        off += box;
+        p.so_f = off;
+        off += need_f ? box : 0;
+        p.so_k = off;
+        off += keys ? round_up(p.BH * BW, 128) : 0;
+        p.so_vc = off;
+        off += pr.prolong_mode ? round_up(p.CH * CW * 4, 128) : 0;
+        p.so_kc = off;
+        off += p.keys_c ? round_up(p.CH * KCW, 128) : 0;
+        p.so_idx = off;
+        off += gbc ? box : 0;
+        p.so_bval = off;
+        off += gbc ? box : 0;
+        p.stage_bytes = off;
+        p.off_stage0 = TABLES_BYTES;
+        int o = TABLES_BYTES + 2 * p.stage_bytes;
+        p.off_w1 = o;
+        o += (pr.nsweeps > 0) ? box : 0;
+        p.off_w2 = o;
+        o += hj ? box : 0;
+        p.off_w3 = o;
+        o += hj ? box : 0;
+        smem = (size_t)o;
+        if (smem <= 232448) break;
+    }
+    p.tx_bytes = 0;
+    const unsigned int boxb = (unsigned int)p.BH * BW * 4u;
+    if (!p.zero_init) p.tx_bytes += boxb;
+    if (need_f) p.tx_bytes += boxb;
+    if (keys) p.tx_bytes += (unsigned int)p.BH * BW;
+    if (pr.prolong_mode) p.tx_bytes += (unsigned int)p.CH * CW * 4u;
+    if (p.keys_c) p.tx_bytes += (unsigned int)p.CH * KCW;
+    if (gbc) p.tx_bytes += 2u * boxb;
+
+    p.ntx = (g->N + p.TWI - 1) / p.TWI;
+    p.nty = (g->N + p.TH - 1) / p.TH;
+    const long long ntiles = (long long)p.ntx * p.nty * pr.B;
+    if (ntiles > 0x3fffffffLL) return MGFEA_EUNSUPPORTED;
+    p.ntiles = (int)ntiles;
+
+    DeviceScratch *scr = nullptr;
+    if ((rc = get_scratch((size_t)ntiles, &scr))) return rc;
+    if (pr.out_mode == OUT_NORM) {
+        p.tile_partials = scr->tile_partials;
+        p.counter = scr->counter;
+        p.sumsq = pr.sumsq;
+        p.hist = pr.hist;
+    }
+    p.ctl = pr.ctl;
+
+    // ---- tensor maps
+    if (p.use_tma) {
+        const unsigned long long N = (unsigned long long)g->N, Bq = (unsigned long long)pr.B;
+        const unsigned long long s1 = (unsigned long long)g->pitch * 4, s2 = (unsigned long long)g->plane * 4;
+        if (!p.zero_init && (rc = make_map(&maps.u, pr.u_in, false, 3, N, N, Bq, s1, s2, BW, p.BH))) return rc;
+        if (need_f && (rc = make_map(&maps.f, pr.f, false, 3, N, N, Bq, s1, s2, BW, p.BH))) return rc;
+        if (keys && (rc = make_map(&maps.k, g->keys, true, 2, N, N, 1, (unsigned long long)g->key_pitch, 0, BW, p.BH)))
+            return rc;
+        if (pr.prolong_mode) {
+            const unsigned long long Nc = (unsigned long long)p.Nc;
+            if ((rc = make_map(&maps.vc, pr.vc, false, 3, Nc, Nc, Bq, (unsigned long long)p.pitch_c * 4,
+                               (unsigned long long)p.plane_c * 4, CW, p.CH)))
+                return rc;
+            if (p.keys_c &&
+                (rc = make_map(&maps.kc, p.keys_c, true, 2, Nc, Nc, 1, (unsigned long long)p.key_pitch_c, 0, KCW, p.CH)))
+                return rc;
+        }
+        if (gbc) {
+            const unsigned long long bb = g->bc_plane ? Bq : 1ull;
+            const unsigned long long sb = g->bc_plane ? (unsigned long long)g->bc_plane * 4 : s2;
+            if ((rc = check_field(g->bc_idx, g->pitch, g->bc_plane))) return rc;
+            if ((rc = check_field(g->bc_val, g->pitch, g->bc_plane))) return rc;
+            if ((rc = make_map(&maps.idx, g->bc_idx, false, 3, N, N, bb, s1, sb, BW, p.BH))) return rc;
+            if ((rc = make_map(&maps.bval, g->bc_val, false, 3, N, N, bb, s1, sb, BW, p.BH))) return rc;
+        }
+    }
+
+    // ---- grid: persistent CTAs, as many as fit per SM
+    int per_sm = (int)(232448 / smem);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    long long maxc = (long long)scr->num_sms * per_sm;
+    int grid = (int)(ntiles < maxc ? ntiles : maxc);
+
+    cudaError_t e;
+    if (keys) {
+        e = gbc ? launch_tile<true, true>(maps, p, grid, smem, st) : launch_tile<true, false>(maps, p, grid, smem, st);
+    } else {
+        e = gbc ? launch_tile<false, true>(maps, p, grid, smem, st) : launch_tile<false, false>(maps, p, grid, smem, st);
+    }
+    return (int)e;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// smoothing with sweep splitting: runs `n` sweeps from src (NULL = zero) ping-ponging between bufA/bufB; an optional
+// prolongation happens in the first launch and an optional output stage in the last.  Returns the buffer that holds
+// the result through *result.
+static int max_fused_sweeps(int smoother, int nlayers, bool with_out, bool restr) {
+    const int sd = (smoother == MGFEA_SMOOTH_HJACOBI) ? 1 + nlayers : 1;
+    const int lim = restr ? 7 : 8;
+    int k = (lim - (with_out ? 1 : 0)) / sd;
+    return k;
+}
+
+static int run_chain(Program base, const float *src, float *bufA, float *bufB, int n, float **result,
+                     cudaStream_t st) {
+    // bufA/bufB: the two buffers of the level; src is NULL (zero), bufA or bufB.  Every launch writes the buffer that
+    // is not its input.  The last launch carries the output stage; it can absorb at most kmax_last sweeps.
+    const bool has_out = base.out_mode != OUT_NONE;
+    const bool restr = base.out_mode == OUT_RESTRICT;
+    const int kmax_last = max_fused_sweeps(base.smoother, base.nlayers, has_out, restr);
+    const int kmax_mid = max_fused_sweeps(base.smoother, base.nlayers, false, false);
+    if (kmax_mid < 1) return MGFEA_EUNSUPPORTED;
+    const float *cur = src;
+    int remaining = n;
+    bool first = true;
+    for (;;) {
+        const bool last = remaining <= kmax_last;
+        const int k = last ? remaining : (remaining < kmax_mid ? remaining : kmax_mid);
+        Program pr = base;
+        pr.u_in = cur;
+        pr.nsweeps = k;
+        float *dst = (cur == bufA) ? bufB : bufA;
+        pr.u_out = dst;
+        if (!first) pr.prolong_mode = 0;
+        if (!last) pr.out_mode = OUT_NONE;
+        const int rc = run_program(pr, st);
+        if (rc) return rc;
+        cur = dst;
+        remaining -= k;
+        first = false;
+        if (last) break;
+    }
+    *result = const_cast<float *>(cur);
+    return 0;
+}
+
+}  // namespace mgfea
+
+// =========================================================================================================
+// C ABI
+// =========================================================================================================
+using namespace mgfea;
+
+extern "C" {
+
+const char *mgfea_version(void) { return "mgfea 0.1 (sm_100a; TMA tile pipeline)"; }
+
+const char *mgfea_error_string(int code) {
+    switch (code) {
+        case 0:
+            return "success";
+        case MGFEA_EINVAL:
+            return "mgfea: invalid argument";
+        case MGFEA_EALIGN:
+            return "mgfea: pointer/pitch alignment violated (need 16-byte base, pitch % 4 == 0)";
+        case MGFEA_EUNSUPPORTED:
+            return "mgfea: unsupported configuration";
+        case MGFEA_EDRIVER:
+            return "mgfea: cuTensorMapEncodeTiled unavailable or failed";
+        default:
+            return code > 0 ? cudaGetErrorString((cudaError_t)code) : "mgfea: unknown error";
+    }
+}
+
+int mgfea_set_loader(int use_tma) { return g_use_tma.exchange(use_tma ? 1 : 0); }
+uint64_t mgfea_launch_count(void) { return g_launches.load(); }
+
+int mgfea_pack(const float *src, float *dst, int N, int pitch, int64_t plane, int B, void *stream) {
+    if (!src || !dst || N < 1 || pitch < N || B < 1) return MGFEA_EINVAL;
+    const long long total = (long long)B * N * pitch;
+    int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, N, pitch, plane, B);
+    g_launches.fetch_add(1);
+    return (int)cudaGetLastError();
+}
+int mgfea_unpack(const float *src, float *dst, int N, int pitch, int64_t plane, int B, void *stream) {
+    if (!src || !dst || N < 1 || pitch < N || B < 1) return MGFEA_EINVAL;
+    const long long total = (long long)B * N * N;
+    int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    unpack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, N, pitch, plane, B);
+    g_launches.fetch_add(1);
+    return (int)cudaGetLastError();
+}
+
+int mgfea_restrict_channels(const float *rF, float *fc, const float *rtab, int C, int N, int B, void *stream) {
+    if (!rF || !fc || !rtab || C < 1 || N < 3 || B < 1) return MGFEA_EINVAL;
+    const int Nc = (N - 1) / 2 + 1;
+    const long long total = (long long)B * Nc * Nc;
+    int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    restrict_channels_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rF, fc, rtab, C, N, B);
+    g_launches.fetch_add(1);
+    return (int)cudaGetLastError();
+}
+int mgfea_prolong_channels(const float *eFC, float *out, const float *ptab, int C, int Nc, int B, void *stream) {
+    if (!eFC || !out || !ptab || C < 1 || Nc < 2 || B < 1) return MGFEA_EINVAL;
+    const int N = 2 * Nc - 1;
+    const long long total = (long long)B * N * N;
+    int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    prolong_channels_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(eFC, out, ptab, C, Nc, B);
+    g_launches.fetch_add(1);
+    return (int)cudaGetLastError();
+}
+
+int mgfea_stiffness_apply(const mgfea_grid *g, const float *u, float *out, int B, void *stream) {
+    Program pr;
+    pr.g = g;
+    pr.B = B;
+    pr.u_in = u;
+    pr.out_mode = OUT_KU;
+    pr.r_out = out;
+    if (!u || !out) return MGFEA_EINVAL;
+    return run_program(pr, (cudaStream_t)stream);
+}
+
+int mgfea_load_vector(const float *w9, const float *x, float *out, int N, int pitch, int64_t plane, int B,
+                      void *stream) {
+    if (!w9 || !x || !out) return MGFEA_EINVAL;
+    mgfea_grid g;
+    memset(&g, 0, sizeof(g));
+    g.N = N;
+    g.pitch = pitch;
+    g.plane = plane;
+    g.npat = 1;
+    g.ktab = w9;
+    Program pr;
+    pr.g = &g;
+    pr.B = B;
+    pr.u_in = x;
+    pr.out_mode = OUT_KU;
+    pr.r_out = out;
+    return run_program(pr, (cudaStream_t)stream);
+}
+
+int mgfea_split_x(const mgfea_grid *g, const float *x, float *out, int B, void *stream) {
+    if (!g || !x || !out) return MGFEA_EINVAL;
+    const long long total = (long long)B * g->npat * g->N * g->N;
+    int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    split_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, out, g->keys, g->key_pitch, g->npat, g->N, g->pitch,
+                                                          g->plane, B);
+    g_launches.fetch_add(1);
+    return (int)cudaGetLastError();
+}
+
+int mgfea_reset_boundary(const mgfea_grid *g, const float *u, float *out, int B, void *stream) {
+    if (!u || !out || u == out) return MGFEA_EINVAL;
+    Program pr;
+    pr.g = g;
+    pr.B = B;
+    pr.u_in = u;
+    pr.u_out = out;
+    pr.reset_only = 1;
+    return run_program(pr, (cudaStream_t)stream);
+}
+
+int mgfea_smooth(const mgfea_grid *g, const float *u_in, float *u_out, const float *f, int nsweeps, int smoother,
+                 const float *hw, int nlayers, int B, void *stream) {
+    if (!u_in || !u_out || u_in == u_out || nsweeps < 0) return MGFEA_EINVAL;
+    Program pr;
+    pr.g = g;
+    pr.B = B;
+    pr.f = f;
+    pr.smoother = smoother;
+    pr.hw = hw;
+    pr.nlayers = nlayers;
+    const int kmax = max_fused_sweeps(smoother, nlayers, false, false);
+    if (nsweeps <= kmax) {
+        pr.u_in = u_in;
+        pr.u_out = u_out;
+        pr.nsweeps = nsweeps;
+        return run_program(pr, (cudaStream_t)stream);
+    }
+    return MGFEA_EUNSUPPORTED;  // callers (FEANet.jacobi) loop over launches with their own ping-pong buffers
+}
+
+int mgfea_residual(const mgfea_grid *g, const float *u, const float *f, float *r, int B, void *stream) {
+    if (!u || !f || !r) return MGFEA_EINVAL;
+    Program pr;
+    pr.g = g;
+    pr.B = B;
+    pr.u_in = u;
+    pr.f = f;
+    pr.out_mode = OUT_RESIDUAL;
+    pr.r_out = r;
+    return run_program(pr, (cudaStream_t)stream);
+}
+
+int mgfea_restrict(const mgfea_grid *g, const float *r, float *fc, int pitch_c, int64_t plane_c, const float *rtab,
+                   int rtab_n, int has_scale, float scale_host, const float *scale_dev, int B, void *stream) {
+    if (!r || !fc) return MGFEA_EINVAL;
+    Program pr;  // r = f - K*0 with f := r
+    pr.g = g;
+    pr.B = B;
+    pr.f = r;
+    pr.out_mode = OUT_RESTRICT;
+    pr.fc = fc;
+    pr.pitch_c = pitch_c;
+    pr.plane_c = plane_c;
+    pr.rtab = rtab;
+    pr.rtab_n = rtab_n;
+    pr.r_has_scale = has_scale;
+    pr.r_scale = scale_host;
+    pr.r_scale_dev = scale_dev;
+    return run_program(pr, (cudaStream_t)stream);
+}
+
+int mgfea_smooth_residual_restrict(const mgfea_grid *g, const float *u_in, float *u_out, const float *f, int nsweeps,
+                                   int smoother, const float *hw, int nlayers, float *fc, int pitch_c,
+                                   int64_t plane_c, const float *rtab, int rtab_n, int has_scale, float scale_host,
+                                   const float *scale_dev, int B, void *stream) {
+    if (!u_out || !f || !fc || u_in == u_out) return MGFEA_EINVAL;
+    Program pr;
+    pr.g = g;
+    pr.B = B;
+    pr.u_in = u_in;
+    pr.u_out = u_out;
+    pr.f = f;
+    pr.nsweeps = nsweeps;
+    pr.smoother = smoother;
+    pr.hw = hw;
+    pr.nlayers = nlayers;
+    pr.out_mode = OUT_RESTRICT;
+    pr.fc = fc;
+    pr.pitch_c = pitch_c;
+    pr.plane_c = plane_c;
+    pr.rtab = rtab;
+    pr.rtab_n = rtab_n;
+    pr.r_has_scale = has_scale;
+    pr.r_scale = scale_host;
+    pr.r_scale_dev = scale_dev;
+    return run_program(pr, (cudaStream_t)stream);
+}
+
+int mgfea_prolong_correct_smooth(const mgfea_grid *g, const mgfea_grid *gc, const float *vc, const float *u_in,
+                                 float *u_out, const float *f, int mode, const float *ptab, int ptab_n,
+                                 int has_scale, float scale_host, const float *scale_dev, int nsweeps, int smoother,
+                                 const float *hw, int nlayers, int B, void *stream) {
+    if (!u_in || !u_out || !vc || u_in == u_out) return MGFEA_EINVAL;
+    if (mode != MGFEA_PROLONG_BILINEAR && mode != MGFEA_PROLONG_TABLE) return MGFEA_EINVAL;
+    Program pr;
+    pr.g = g;
+    pr.B = B;
+    pr.u_in = u_in;
+    pr.u_out = u_out;
+    pr.f = f;
+    pr.nsweeps = nsweeps;
+    pr.smoother = smoother;
+    pr.hw = hw;
+    pr.nlayers = nlayers;
+    pr.prolong_mode = mode;
+    pr.gc = gc;
+    pr.vc = vc;
+    pr.ptab = ptab;
+    pr.ptab_n = ptab_n;
+    pr.p_has_scale = has_scale;
+    pr.p_scale = scale_host;
+    pr.p_scale_dev = scale_dev;
+    return run_program(pr, (cudaStream_t)stream);
+}
+
+int mgfea_residual_norm(const mgfea_grid *g, const float *u, const float *f, double *sumsq, mgfea_ctl *ctl,
+                        double *hist, int B, void *stream) {
+    if (!u || !f) return MGFEA_EINVAL;
+    Program pr;
+    pr.g = g;
+    pr.B = B;
+    pr.u_in = u;
+    pr.f = f;
+    pr.out_mode = OUT_NORM;
+    pr.sumsq = sumsq;
+    pr.ctl = ctl;
+    pr.hist = hist;
+    return run_program(pr, (cudaStream_t)stream);
+}
+
+int mgfea_vcycle(const mgfea_grid *grids, const mgfea_level_bufs *bufs, int nlevels, const mgfea_cycle_cfg *cfg,
+                 double *sumsq, mgfea_ctl *ctl, double *hist, int B, void *stream) {
+    if (!grids || !bufs || !cfg || nlevels < 1 || nlevels > 32) return MGFEA_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int L = nlevels;
+    float *cur[32];   // buffer holding the current iterate of each level (NULL = zero)
+    for (int l = 0; l < L; ++l) cur[l] = (l == 0) ? bufs[0].u : nullptr;
+    int rc;
+
+    auto base_prog = [&](int l) {
+        Program pr;
+        pr.g = &grids[l];
+        pr.B = B;
+        pr.f = bufs[l].f;
+        pr.smoother = cfg->smoother;
+        pr.hw = cfg->hw;
+        pr.nlayers = cfg->nlayers;
+        pr.ctl = ctl;
+        return pr;
+    };
+    auto set_restrict = [&](Program &pr, int l) {
+        pr.out_mode = OUT_RESTRICT;
+        pr.fc = bufs[l + 1].f;
+        pr.pitch_c = grids[l + 1].pitch;
+        pr.plane_c = grids[l + 1].plane;
+        pr.rtab = cfg->rtab;
+        pr.rtab_n = (cfg->rtab_n > 1 && grids[l].npat == 1) ? 1 : cfg->rtab_n;
+        pr.r_has_scale = cfg->r_has_scale;
+        pr.r_scale = cfg->r_scale_host;
+        pr.r_scale_dev = cfg->r_scale_dev;
+    };
+
+    // ---- down leg
+    for (int l = 0; l < L; ++l) {
+        if (cfg->quirk_level0 && l > 0) {
+            // pre-smooth is applied to level 0 instead of level l (MM_Interface_error.ipynb cell 2)
+            if (cfg->nu1 > 0) {
+                Program pr = base_prog(0);
+                float *res = nullptr;
+                if ((rc = run_chain(pr, cur[0], bufs[0].u, bufs[0].u_alt, cfg->nu1, &res, st))) return rc;
+                cur[0] = res;
+            }
+            if (l < L - 1) {
+                Program pr = base_prog(l);
+                set_restrict(pr, l);
+                float *res = nullptr;
+                if ((rc = run_chain(pr, cur[l], bufs[l].u, bufs[l].u_alt, 0, &res, st))) return rc;
+                cur[l] = res;
+            }
+            continue;
+        }
+        if (l < L - 1) {
+            Program pr = base_prog(l);
+            set_restrict(pr, l);
+            float *res = nullptr;
+            if ((rc = run_chain(pr, cur[l], bufs[l].u, bufs[l].u_alt, cfg->nu1, &res, st))) return rc;
+            cur[l] = res;
+        } else {
+            // coarsest: nu1 pre-sweeps here; the nu2 post-sweeps follow in the up leg (same chain when L > 1)
+            Program pr = base_prog(l);
+            const int n = cfg->nu1;
+            if (n > 0 || cur[l] == nullptr) {
+                float *res = nullptr;
+                if ((rc = run_chain(pr, cur[l], bufs[l].u, bufs[l].u_alt, n, &res, st))) return rc;
+                cur[l] = res;
+            }
+        }
+    }
+    // ---- up leg
+    for (int l = L - 1; l >= 0; --l) {
+        Program pr = base_prog(l);
+        if (l < L - 1) {
+            pr.prolong_mode = cfg->prolong_mode;
+            pr.gc = &grids[l + 1];
+            pr.vc = cur[l + 1];
+            pr.ptab = cfg->ptab;
+            pr.ptab_n = (cfg->ptab_n > 1 && grids[l + 1].npat == 1) ? 1 : cfg->ptab_n;
+            pr.p_has_scale = cfg->p_has_scale;
+            pr.p_scale = cfg->p_scale_host;
+            pr.p_scale_dev = cfg->p_scale_dev;
+        }
+        if (l == 0 && cfg->compute_norm) {
+            pr.out_mode = OUT_NORM;
+            pr.sumsq = sumsq;
+            pr.hist = hist;
+        }
+        if (l == L - 1 && cfg->nu2 == 0 && !(l == 0 && cfg->compute_norm)) continue;
+        float *res = nullptr;
+        if ((rc = run_chain(pr, cur[l], bufs[l].u, bufs[l].u_alt, cfg->nu2, &res, st))) return rc;
+        cur[l] = res;
+    }
+    // ---- result must be in bufs[0].u
+    if (cur[0] != bufs[0].u) {
+        Program pr = base_prog(0);
+        pr.u_in = cur[0];
+        pr.u_out = bufs[0].u;
+        pr.f = nullptr;
+        if ((rc = run_program(pr, st))) return rc;
+    }
+    return 0;
+}
+
+}  // extern "C"

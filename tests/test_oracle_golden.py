@@ -246,3 +246,26 @@ def test_committed_multigrid_iterate(tag):
         ref = np.array(h["res"][it])
         assert (np.abs(got - ref) / ref < 3e-5 * 4 ** it).all(), (it, got, ref)
     close(x, ARR[f"iterate_{tag}_u"][:, 0], rtol=1e-4)
+
+
+def test_feanet_torch_matches_reference_histories():
+    """the ATen-call-for-call restatement used as cpu_baseline reproduces the reference's golden residuals exactly
+    (same op sequence on the same torch build => bit-identical; allow 1e-6 for a different build)"""
+    import torch
+
+    from oracle import feanet_torch as FT
+
+    for tag in ("modelA_n64_v11", "modelA_n64_L4_v11", "modelA_n256_v11"):
+        h = HIST[tag]
+        n = h["n"]
+        lv = FT.make_levels(n, h["L"])
+        u0 = torch.from_numpy(model_u0(n)).reshape(1, 1, n + 1, n + 1)
+        _, res = FT.solve(lv, u0, torch.zeros(1, 1, n + 1, n + 1), n_iter=8)
+        ref = np.array(h["res"][:8])
+        assert (np.abs(np.array(res) - ref) / ref < 1e-6).all(), (tag, res, ref)
+    # two-phase: Level.K with 16 channels equals the oracle's key-indexed stencil bit for bit
+    N = 33
+    keys, ktab = setup("c20", N)
+    lvl = FT.Level(N, ktab, keys)
+    u = torch.from_numpy(OPS[f"u_{N}"])
+    assert np.array_equal(lvl.K(u).numpy()[:, 0], O.stiffness_apply(OPS[f"u_{N}"], keys, ktab))
