@@ -5,6 +5,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -37,6 +38,7 @@ __device__ __forceinline__ StageBufs stage_bufs(unsigned char *smem, const TileP
 
 struct TileCoord {
     int b, y0, x0, gy0, gx0, cy0, cx0;
+    int kx0, vx0, kcx0;  // 16-byte aligned start columns of the key / coarse value / coarse key boxes
 };
 __device__ __forceinline__ TileCoord tile_coord(const TileParams &p, int t) {
     TileCoord tc;
@@ -50,6 +52,9 @@ __device__ __forceinline__ TileCoord tile_coord(const TileParams &p, int t) {
     tc.gx0 = tc.x0 - p.HX;
     tc.cy0 = tc.gy0 >> 1;  // floor
     tc.cx0 = tc.gx0 >> 1;
+    tc.kx0 = tc.gx0 & ~15;   // floor to 16 bytes (uint8)
+    tc.vx0 = tc.cx0 & ~3;    // floor to 4 floats
+    tc.kcx0 = tc.cx0 & ~15;  // floor to 16 bytes (uint8)
     return tc;
 }
 
@@ -90,10 +95,10 @@ __device__ __forceinline__ void issue_loads(unsigned char *smem, const TileMaps 
             mbar_arrive_expect_tx(bar, p.tx_bytes);
             if (need_u) tma_load_3d(sb.U, &maps.u, bar, tc.gx0, tc.gy0, tc.b);
             if (need_f) tma_load_3d(sb.F, &maps.f, bar, tc.gx0, tc.gy0, tc.b);
-            if (KEYS) tma_load_2d(sb.K, &maps.k, bar, tc.gx0, tc.gy0);
+            if (KEYS) tma_load_2d(sb.K, &maps.k, bar, tc.kx0, tc.gy0);
             if (p.prolong_mode) {
-                tma_load_3d(sb.VC, &maps.vc, bar, tc.cx0, tc.cy0, tc.b);
-                if (p.keys_c) tma_load_2d(sb.KC, &maps.kc, bar, tc.cx0, tc.cy0);
+                tma_load_3d(sb.VC, &maps.vc, bar, tc.vx0, tc.cy0, tc.b);
+                if (p.keys_c) tma_load_2d(sb.KC, &maps.kc, bar, tc.kcx0, tc.cy0);
             }
             if (GBC) {
                 tma_load_3d(sb.IDX, &maps.idx, bar, tc.gx0, tc.gy0, bcb);
@@ -110,15 +115,15 @@ __device__ __forceinline__ void issue_loads(unsigned char *smem, const TileMaps 
             cpasync_box<16>(reinterpret_cast<unsigned char *>(sb.F),
                             reinterpret_cast<const unsigned char *>(p.f + (long long)tc.b * p.plane), pb, p.N,
                             p.pitch * 4, tc.gy0, tc.gx0 * 4, p.BH, BW * 4);
-        if (KEYS) cpasync_box<4>(sb.K, p.keys, p.key_pitch, p.N, p.key_pitch, tc.gy0, tc.gx0, p.BH, BW);
+        if (KEYS) cpasync_box<16>(sb.K, p.keys, p.key_pitch, p.N, p.key_pitch, tc.gy0, tc.kx0, p.BH, KBW);
         if (p.prolong_mode) {
-            cpasync_box<8>(reinterpret_cast<unsigned char *>(sb.VC),
-                           reinterpret_cast<const unsigned char *>(p.vc + (long long)tc.b * p.plane_c),
-                           (long long)p.pitch_c * 4, p.Nc, p.pitch_c * 4, tc.cy0, tc.cx0 * 4, p.CH, CW * 4);
+            cpasync_box<16>(reinterpret_cast<unsigned char *>(sb.VC),
+                            reinterpret_cast<const unsigned char *>(p.vc + (long long)tc.b * p.plane_c),
+                            (long long)p.pitch_c * 4, p.Nc, p.pitch_c * 4, tc.cy0, tc.vx0 * 4, p.CH, CW * 4);
             if (p.keys_c) {  // coarse key box starts at an even (2-byte aligned) column: plain byte loads
                 for (int i = threadIdx.x; i < p.CH * KCW; i += NTHREADS) {
                     const int r = i / KCW, cb = i - r * KCW;
-                    const int gy = tc.cy0 + r, gx = tc.cx0 + cb;
+                    const int gy = tc.cy0 + r, gx = tc.kcx0 + cb;
                     sb.KC[i] = (gy >= 0 && gy < p.Nc && gx >= 0 && gx < p.Nc)
                                    ? p.keys_c[(long long)gy * p.key_pitch_c + gx]
                                    : (unsigned char)0;
@@ -141,6 +146,75 @@ __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// The per-tile program (see mgfea_tile.cuh).  EDGE tiles carry the default-BC / domain masks, interior tiles do not.
+template <bool KEYS, bool GBC, bool EDGE>
+__device__ __forceinline__ void run_tile(TileCtx &c, Tables &T, const RegW &W, const TileParams &p, int t) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float *W1 = c.W1, *W2 = c.W2, *W3 = c.W3;
+    int d = 0;
+    float *cur = c.U;
+    if (p.prolong_mode) {
+        stage_prolong<GBC>(c, T, p, c.U);
+        __syncthreads();
+    }
+    if (p.nsweeps == 0 && p.smoother == 2) {  // reset_boundary only
+        stage_reset<GBC>(c, cur, cur, 0, p.BH);
+        __syncthreads();
+    }
+    for (int sw = 0; sw < p.nsweeps; ++sw) {
+        if (p.smoother == 0) {
+            if (GBC || (EDGE && sw == 0)) {
+                stage_reset<GBC>(c, cur, cur, d, p.BH - d);
+                __syncthreads();
+            }
+            float *dst = (cur == c.U) ? W1 : c.U;
+            stage_jacobi<KEYS, GBC, false, EDGE>(c, T, W, cur, dst, nullptr, nullptr, d + 1, p.BH - d - 1);
+            __syncthreads();
+            cur = dst;
+            d += 1;
+        } else {
+            stage_reset<GBC>(c, cur, W3, d, p.BH - d);
+            __syncthreads();
+            stage_jacobi<KEYS, GBC, true, EDGE>(c, T, W, W3, W1, cur, W2, d + 1, p.BH - d - 1);
+            __syncthreads();
+            float *src = W2, *dst = W3;
+            for (int l = 0; l < p.nlayers; ++l) {
+                const int dd = d + 2 + l;
+                if (l == p.nlayers - 1)
+                    stage_hlayer<GBC, true, EDGE>(c, T.hw + 9 * l, src, cur, W1, dd, p.BH - dd);
+                else
+                    stage_hlayer<GBC, false, EDGE>(c, T.hw + 9 * l, src, dst, nullptr, dd, p.BH - dd);
+                __syncthreads();
+                float *tmp = src;
+                src = dst;
+                dst = tmp;
+            }
+            d += 1 + p.nlayers;
+        }
+    }
+    if (p.store_u) stage_store_u(c, p, cur);
+    if (p.out_mode == OUT_RESIDUAL) {
+        stage_out<KEYS, OUT_RESIDUAL, EDGE>(c, T, W, p, cur, nullptr, d + 1, p.BH - d - 1);
+    } else if (p.out_mode == OUT_KU) {
+        stage_out<KEYS, OUT_KU, EDGE>(c, T, W, p, cur, nullptr, d + 1, p.BH - d - 1);
+    } else if (p.out_mode == OUT_RESTRICT) {
+        stage_out<KEYS, OUT_RESTRICT, EDGE>(c, T, W, p, cur, c.F, d + 1, p.BH - d - 1);
+        __syncthreads();
+        stage_restrict<KEYS, EDGE>(c, T, W, p, c.F);
+    } else if (p.out_mode == OUT_NORM) {
+        double part = stage_out<KEYS, OUT_NORM, EDGE>(c, T, W, p, cur, nullptr, d + 1, p.BH - d - 1);
+        part = warp_sum(part);
+        if (lane == 0) T.red[warp] = part;
+        __syncthreads();
+        if (tid == 0) {
+            double sum = 0.0;
+#pragma unroll
+            for (int w = 0; w < NWARPS; ++w) sum += T.red[w];
+            p.tile_partials[t] = sum;
+        }
+    }
 }
 
 template <bool KEYS, bool GBC>
@@ -176,15 +250,29 @@ __global__ void __launch_bounds__(NTHREADS) mg_tile_kernel(const __grid_constant
     float *W1 = reinterpret_cast<float *>(smem + p.off_w1);
     float *W2 = reinterpret_cast<float *>(smem + p.off_w2);
     float *W3 = reinterpret_cast<float *>(smem + p.off_w3);
+    RegW W;
+    auto load_regw = [&](int k0) {
+        const int kr = (p.rtab_n > 1) ? k0 : 0;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+            W.kw[q] = T.ktab[9 * k0 + q];
+            W.rw[q] = T.rtab[9 * kr + q];
+        }
+        W.inv = T.invd[k0];
+    };
+    load_regw(0);
+    int cur_k0 = 0;
 
     int s = 0;
     uint32_t phase[2] = {0u, 0u};
     int t = blockIdx.x;
-    if (t < p.ntiles) issue_loads<KEYS, GBC>(smem, maps, p, T, t, 0);
+    const bool dbuf = (p.nstages == 2);
+    if (dbuf && t < p.ntiles) issue_loads<KEYS, GBC>(smem, maps, p, T, t, 0);
 
     for (; t < p.ntiles; t += gridDim.x) {
         const int tn = t + gridDim.x;
-        const bool has_next = tn < p.ntiles;
+        const bool has_next = dbuf && (tn < p.ntiles);
+        if (!dbuf) issue_loads<KEYS, GBC>(smem, maps, p, T, t, 0);
         if (has_next) issue_loads<KEYS, GBC>(smem, maps, p, T, tn, s ^ 1);
         if (p.use_tma) {
             mbar_wait(reinterpret_cast<uint64_t *>(&T.mbar[s]), phase[s]);
@@ -203,7 +291,7 @@ __global__ void __launch_bounds__(NTHREADS) mg_tile_kernel(const __grid_constant
         TileCtx c;
         c.U = sb.U;
         c.F = sb.F;
-        c.K = sb.K;
+        c.K = sb.K + (tc.gx0 - tc.kx0);  // column gx0 of the 16-byte aligned key box
         c.VC = sb.VC;
         c.KC = p.keys_c ? sb.KC : nullptr;
         c.IDX = sb.IDX;
@@ -215,6 +303,8 @@ __global__ void __launch_bounds__(NTHREADS) mg_tile_kernel(const __grid_constant
         c.gx0 = tc.gx0;
         c.cy0 = tc.cy0;
         c.cx0 = tc.cx0;
+        c.vcofs = tc.cx0 - tc.vx0;
+        c.kcofs = tc.cx0 - tc.kcx0;
         c.b = tc.b;
         c.BH = p.BH;
         c.N = p.N;
@@ -222,10 +312,10 @@ __global__ void __launch_bounds__(NTHREADS) mg_tile_kernel(const __grid_constant
         c.k0 = 0;
         c.touches_edge = (tc.gy0 <= 0) || (tc.gy0 + p.BH - 1 >= p.N - 1) || (tc.gx0 <= 0) || (tc.gx0 + BW - 1 >= p.N - 1);
         if (KEYS) {
-            const unsigned int *kw = reinterpret_cast<const unsigned int *>(c.K);
-            const unsigned int first = (unsigned int)c.K[0] * 0x01010101u;
+            const unsigned int *kw = reinterpret_cast<const unsigned int *>(sb.K);
+            const unsigned int first = (unsigned int)sb.K[0] * 0x01010101u;
             int ok = 1;
-            for (int i = tid; i < p.BH * (BW / 4); i += NTHREADS) ok &= (kw[i] == first);
+            for (int i = tid; i < p.BH * (KBW / 4); i += NTHREADS) ok &= (kw[i] == first);
             c.keys_uniform = __syncthreads_and(ok) != 0;
             c.k0 = c.K[0];
         }
@@ -235,73 +325,19 @@ __global__ void __launch_bounds__(NTHREADS) mg_tile_kernel(const __grid_constant
             __syncthreads();
         }
 
+        if (KEYS && c.k0 != cur_k0) {
+            load_regw(c.k0);
+            cur_k0 = c.k0;
+        }
         // ---- program
-        int d = 0;
-        float *cur = c.U;
-        if (p.prolong_mode) {
-            stage_prolong<GBC>(c, T, p, c.U);
-            __syncthreads();
-        }
-        if (p.nsweeps == 0 && p.smoother == 2) {  // reset_boundary only
-            stage_reset<GBC>(c, cur, cur, 0, p.BH);
-            __syncthreads();
-        }
-        for (int sw = 0; sw < p.nsweeps; ++sw) {
-            if (p.smoother == 0) {
-                if (GBC || (sw == 0 && c.touches_edge)) {
-                    stage_reset<GBC>(c, cur, cur, d, p.BH - d);
-                    __syncthreads();
-                }
-                float *dst = (cur == c.U) ? W1 : c.U;
-                stage_jacobi<KEYS, GBC, false>(c, T, cur, dst, nullptr, nullptr, d + 1, p.BH - d - 1);
-                __syncthreads();
-                cur = dst;
-                d += 1;
-            } else {
-                stage_reset<GBC>(c, cur, W3, d, p.BH - d);
-                __syncthreads();
-                stage_jacobi<KEYS, GBC, true>(c, T, W3, W1, cur, W2, d + 1, p.BH - d - 1);
-                __syncthreads();
-                float *src = W2, *dst = W3;
-                for (int l = 0; l < p.nlayers; ++l) {
-                    const int dd = d + 2 + l;
-                    if (l == p.nlayers - 1)
-                        stage_hlayer<GBC, true>(c, T.hw + 9 * l, src, cur, W1, dd, p.BH - dd);
-                    else
-                        stage_hlayer<GBC, false>(c, T.hw + 9 * l, src, dst, nullptr, dd, p.BH - dd);
-                    __syncthreads();
-                    float *tmp = src;
-                    src = dst;
-                    dst = tmp;
-                }
-                d += 1 + p.nlayers;
-            }
-        }
-        if (p.store_u) stage_store_u(c, p, cur);
-        if (p.out_mode == OUT_RESIDUAL) {
-            stage_out<KEYS, OUT_RESIDUAL>(c, T, p, cur, nullptr, d + 1, p.BH - d - 1);
-        } else if (p.out_mode == OUT_KU) {
-            stage_out<KEYS, OUT_KU>(c, T, p, cur, nullptr, d + 1, p.BH - d - 1);
-        } else if (p.out_mode == OUT_RESTRICT) {
-            stage_out<KEYS, OUT_RESTRICT>(c, T, p, cur, c.F, d + 1, p.BH - d - 1);
-            __syncthreads();
-            stage_restrict<KEYS>(c, T, p, c.F);
-        } else if (p.out_mode == OUT_NORM) {
-            double part = stage_out<KEYS, OUT_NORM>(c, T, p, cur, nullptr, d + 1, p.BH - d - 1);
-            part = warp_sum(part);
-            if (lane == 0) T.red[warp] = part;
-            __syncthreads();
-            if (tid == 0) {
-                double sum = 0.0;
-#pragma unroll
-                for (int w = 0; w < NWARPS; ++w) sum += T.red[w];
-                p.tile_partials[t] = sum;
-            }
-        }
+        if (c.touches_edge)
+            run_tile<KEYS, GBC, true>(c, T, W, p, t);
+        else
+            run_tile<KEYS, GBC, false>(c, T, W, p, t);
         // generic-proxy accesses to this stage's buffers are done; order them before the next TMA write into it
         fence_proxy_async_smem();
         __syncthreads();
-        s ^= 1;
+        if (dbuf) s ^= 1;
     }
 
     // ---- deterministic final reduction of the per-tile partial sums by the last CTA to finish
@@ -594,6 +630,22 @@ struct Program {
 
 static inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
 
+// tuning knobs (defaults chosen from the measurements in profiles/); overridable through the environment for sweeps
+struct Knobs {
+    int th = 32, stages = 2, ctas = 0;
+    Knobs() {
+        if (const char *e = getenv("MGFEA_TH")) th = atoi(e);
+        if (const char *e = getenv("MGFEA_STAGES")) stages = atoi(e);
+        if (const char *e = getenv("MGFEA_CTAS")) ctas = atoi(e);
+        if (th < 8 || th > 64 || (th & 7)) th = 32;
+        if (stages != 1) stages = 2;
+    }
+};
+static const Knobs &knobs() {
+    static Knobs k;
+    return k;
+}
+
 template <bool KEYS, bool GBC>
 static cudaError_t launch_tile(const TileMaps &maps, const TileParams &p, int grid, size_t smem, cudaStream_t st) {
     static size_t configured = 0;
@@ -720,7 +772,8 @@ static int run_program(const Program &pr, cudaStream_t st) {
 
     // ---- pick TH so that the carve-up fits 227 KB
     const bool hj = (pr.nsweeps > 0 && pr.smoother == MGFEA_SMOOTH_HJACOBI);
-    int TH = 32;
+    int TH = knobs().th;
+    p.nstages = knobs().stages;
     size_t smem = 0;
     for (;; TH -= 8) {
         if (TH < 8) return MGFEA_EUNSUPPORTED;
@@ -734,7 +787,7 @@ static int run_program(const Program &pr, cudaStream_t st) {
         p.so_f = off;
         off += need_f ? box : 0;
         p.so_k = off;
-        off += keys ? round_up(p.BH * BW, 128) : 0;
+        off += keys ? round_up(p.BH * KBW, 128) : 0;
         p.so_vc = off;
         off += pr.prolong_mode ? round_up(p.CH * CW * 4, 128) : 0;
         p.so_kc = off;
@@ -745,7 +798,7 @@ static int run_program(const Program &pr, cudaStream_t st) {
         off += gbc ? box : 0;
         p.stage_bytes = off;
         p.off_stage0 = TABLES_BYTES;
-        int o = TABLES_BYTES + 2 * p.stage_bytes;
+        int o = TABLES_BYTES + p.nstages * p.stage_bytes;
         p.off_w1 = o;
         o += (pr.nsweeps > 0) ? box : 0;
         p.off_w2 = o;
@@ -759,7 +812,7 @@ static int run_program(const Program &pr, cudaStream_t st) {
     const unsigned int boxb = (unsigned int)p.BH * BW * 4u;
     if (!p.zero_init) p.tx_bytes += boxb;
     if (need_f) p.tx_bytes += boxb;
-    if (keys) p.tx_bytes += (unsigned int)p.BH * BW;
+    if (keys) p.tx_bytes += (unsigned int)p.BH * KBW;
     if (pr.prolong_mode) p.tx_bytes += (unsigned int)p.CH * CW * 4u;
     if (p.keys_c) p.tx_bytes += (unsigned int)p.CH * KCW;
     if (gbc) p.tx_bytes += 2u * boxb;
@@ -786,7 +839,7 @@ static int run_program(const Program &pr, cudaStream_t st) {
         const unsigned long long s1 = (unsigned long long)g->pitch * 4, s2 = (unsigned long long)g->plane * 4;
         if (!p.zero_init && (rc = make_map(&maps.u, pr.u_in, false, 3, N, N, Bq, s1, s2, BW, p.BH))) return rc;
         if (need_f && (rc = make_map(&maps.f, pr.f, false, 3, N, N, Bq, s1, s2, BW, p.BH))) return rc;
-        if (keys && (rc = make_map(&maps.k, g->keys, true, 2, N, N, 1, (unsigned long long)g->key_pitch, 0, BW, p.BH)))
+        if (keys && (rc = make_map(&maps.k, g->keys, true, 2, N, N, 1, (unsigned long long)g->key_pitch, 0, KBW, p.BH)))
             return rc;
         if (pr.prolong_mode) {
             const unsigned long long Nc = (unsigned long long)p.Nc;
@@ -811,6 +864,7 @@ static int run_program(const Program &pr, cudaStream_t st) {
     int per_sm = (int)(232448 / smem);
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 4) per_sm = 4;
+    if (knobs().ctas > 0) per_sm = knobs().ctas;
     long long maxc = (long long)scr->num_sms * per_sm;
     int grid = (int)(ntiles < maxc ? ntiles : maxc);
 

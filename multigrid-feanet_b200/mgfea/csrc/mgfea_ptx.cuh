@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace mgfea {
 
@@ -37,7 +38,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 22)) __trap();
+        if (++spins > (1u << 22)) {
+            printf("mgfea: mbarrier wait timed out (block %d thread %d parity %u)\n", (int)blockIdx.x, (int)threadIdx.x,
+                   parity);
+            __trap();
+        }
     }
 }
 

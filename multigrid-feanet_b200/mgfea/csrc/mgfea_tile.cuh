@@ -24,8 +24,13 @@ constexpr int NTHREADS = 256;  // 8 warps
 constexpr int NWARPS = NTHREADS / 32;
 constexpr int MAXPAT = 16;
 constexpr int MAXLAYERS = 8;
-constexpr int CW = 68;   // coarse box width in floats (BW/2 + 1, rounded up to 4)
-constexpr int KCW = 80;  // coarse key box width in bytes (multiple of 16)
+// TMA tiled loads (no swizzle) fault with "illegal instruction" unless the innermost start coordinate is a multiple of
+// 16 bytes (measured on B200, tools/tma_probe.cu).  The fp32 field boxes start at x0-HX (a multiple of 4 floats); the
+// uint8 key box and the coarse boxes are therefore started at the 16-byte boundary below their first needed column
+// and carry the offset (kofs / vcofs / kcofs).
+constexpr int KBW = 144;  // key box width in bytes: up to 12 bytes of alignment slack + 128
+constexpr int CW = 68;    // coarse box width in floats: up to 3 floats of slack + BW/2 + 1
+constexpr int KCW = 80;   // coarse key box width in bytes: up to 15 bytes of slack + BW/2 + 1
 
 enum OutMode { OUT_NONE = 0, OUT_RESIDUAL = 1, OUT_KU = 2, OUT_RESTRICT = 3, OUT_NORM = 4 };
 
@@ -39,7 +44,7 @@ struct TileParams {
     long long plane;
     int TH, HX, HT, HB, BH, TWI;  // tile interior rows, column halo, top/bottom halo rows, box rows, interior cols
     int ntx, nty, ntiles;         // tiles per sample in x / y, total tiles (all samples)
-    int use_tma;
+    int use_tma, nstages;
     // program
     int zero_init, prolong_mode, prolong_seq, nsweeps, smoother, store_u, out_mode;
     // level data
@@ -108,17 +113,18 @@ struct Row6 {
     float a[6];  // box columns 4l-1 .. 4l+4
 };
 
-__device__ __forceinline__ Row6 load_row6(const float *buf, int row, int lane) {
+// One LDS.128 per lane + the two edge values from the neighbouring lanes.  Lane 0 / 31 get their OWN value for the
+// missing neighbour (box column -1 / 128 does not exist); that only perturbs box columns 0 / 127, which are more than
+// `depth` columns away from the tile interior, so it never reaches a stored value.
+__device__ __forceinline__ Row6 load_row6(const float *rowp) {
     Row6 o;
-    const float4 v = *reinterpret_cast<const float4 *>(buf + row * BW + 4 * lane);
-    float l = __shfl_up_sync(0xffffffffu, v.w, 1);
-    float r = __shfl_down_sync(0xffffffffu, v.x, 1);
-    o.a[0] = (lane == 0) ? 0.0f : l;
+    const float4 v = *reinterpret_cast<const float4 *>(rowp);
+    o.a[0] = __shfl_up_sync(0xffffffffu, v.w, 1);
     o.a[1] = v.x;
     o.a[2] = v.y;
     o.a[3] = v.z;
     o.a[4] = v.w;
-    o.a[5] = (lane == 31) ? 0.0f : r;
+    o.a[5] = __shfl_down_sync(0xffffffffu, v.x, 1);
     return o;
 }
 
@@ -127,7 +133,7 @@ struct Key6 {
 };
 __device__ __forceinline__ Key6 load_key6(const unsigned char *kbuf, int row, int lane) {
     Key6 o;
-    const unsigned int w = *reinterpret_cast<const unsigned int *>(kbuf + row * BW + 4 * lane);
+    const unsigned int w = *reinterpret_cast<const unsigned int *>(kbuf + row * KBW + 4 * lane);
     unsigned int l = __shfl_up_sync(0xffffffffu, w, 1);
     unsigned int r = __shfl_down_sync(0xffffffffu, w, 1);
     o.k[0] = (lane == 0) ? 0 : (int)(l >> 24);
@@ -179,12 +185,21 @@ struct TileCtx {
     float *U, *F, *W1, *W2, *W3, *VC, *IDX, *BVAL;
     unsigned char *K, *KC;
     int gy0, gx0;  // global row / column of box element (0,0)
-    int cy0, cx0;  // global coarse row / column of coarse box element (0,0)
+    int cy0, cx0;  // global coarse row / column of the first coarse node the box needs
+    int vcofs, kcofs;  // column of cx0 inside the (16-byte aligned) coarse value / coarse key boxes
     int b;         // sample
     int BH, N;
     bool keys_uniform;  // every key of the box equals k0
     int k0;
     bool touches_edge;  // box intersects the ring or the outside of the domain
+};
+
+// Weights that are uniform for a tile, held in registers for the lifetime of the kernel (single-pattern meshes) or
+// refreshed per tile (two-phase meshes, uniform-key tiles).
+struct RegW {
+    float kw[9];  // stiffness stencil of pattern k0
+    float inv;    // omega/d of pattern k0
+    float rw[9];  // restriction kernel of pattern k0 (or the single kernel)
 };
 
 // split rows [lo, hi) of a stage among the warps: contiguous chunks
@@ -214,6 +229,28 @@ __device__ __forceinline__ unsigned int col_domain_bits(const TileCtx &c, int la
         if (gx >= 0 && gx <= c.N - 1) m |= 1u << e;
     }
     return m;
+}
+
+// Row loop with a rotating 3-row register window (unrolled by 3 so the rotation costs no moves).  `body(r, t, m, b)`
+// is called for every row r in [ra, rb) with the rows r-1, r, r+1 of `src`.
+template <class Body>
+__device__ __forceinline__ void for_rows3(const float *src, int ra, int rb, int lane, Body body) {
+    const float *ps = src + (ra - 1) * BW + 4 * lane;
+    Row6 r0 = load_row6(ps), r1 = load_row6(ps + BW), r2;
+    ps += 2 * BW;
+    int r = ra;
+    for (;;) {
+        r2 = load_row6(ps);
+        body(r, r0, r1, r2);
+        if (++r >= rb) break;
+        r0 = load_row6(ps + BW);
+        body(r, r1, r2, r0);
+        if (++r >= rb) break;
+        r1 = load_row6(ps + 2 * BW);
+        body(r, r2, r0, r1);
+        if (++r >= rb) break;
+        ps += 3 * BW;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -246,51 +283,69 @@ __device__ __forceinline__ void stage_reset(const TileCtx &c, const float *src, 
 // ---------------------------------------------------------------------------------------------------------
 // One weighted-Jacobi update on box rows [lo,hi) (src must be reset and valid on [lo-1,hi+1)):
 //   dst = BC( invd[key] * (f - K src) + src ).   If XOUT: also xdst = dst - raw (HNet input, raw = un-reset u).
-template <bool KEYS, bool GBC, bool XOUT>
-__device__ __forceinline__ void stage_jacobi(const TileCtx &c, const Tables &T, const float *src, float *dst,
-                                             const float *raw, float *xdst, int lo, int hi) {
+// EDGE = the box touches the ring / outside of the domain (default-BC masks needed); interior tiles skip all masking.
+template <bool KEYS, bool GBC, bool XOUT, bool EDGE>
+__device__ __forceinline__ void stage_jacobi(const TileCtx &c, const Tables &T, const RegW &W, const float *src,
+                                             float *dst, const float *raw, float *xdst, int lo, int hi) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int ra, rb;
     warp_rows(lo, hi, warp, ra, rb);
     if (ra >= rb) return;
-    const unsigned int cin = col_interior_bits(c, lane);
     const bool slow = KEYS && !c.keys_uniform;
-    float w[9];
-    float inv0;
-    {
-        const int k0 = KEYS ? c.k0 : 0;
+    if (!slow) {
+        unsigned int cin = 0xfu;
+        if (EDGE && !GBC) cin = col_interior_bits(c, lane);
+        const int lofs = 4 * lane;
+        for_rows3(src, ra, rb, lane, [&](int r, const Row6 &t, const Row6 &m, const Row6 &b) {
+            float acc[4];
+            stencil4(W.kw, t, m, b, acc);
+            const int o4 = r * BW + lofs;
+            const float4 fv = *reinterpret_cast<const float4 *>(c.F + o4);
+            float o[4];
+            o[0] = __fadd_rn(__fmul_rn(W.inv, __fsub_rn(fv.x, acc[0])), m.a[1]);
+            o[1] = __fadd_rn(__fmul_rn(W.inv, __fsub_rn(fv.y, acc[1])), m.a[2]);
+            o[2] = __fadd_rn(__fmul_rn(W.inv, __fsub_rn(fv.z, acc[2])), m.a[3]);
+            o[3] = __fadd_rn(__fmul_rn(W.inv, __fsub_rn(fv.w, acc[3])), m.a[4]);
+            if (GBC) {
+                const float4 g = *reinterpret_cast<const float4 *>(c.IDX + o4);
+                const float4 bv = *reinterpret_cast<const float4 *>(c.BVAL + o4);
+                o[0] = __fadd_rn(__fmul_rn(o[0], g.x), bv.x);
+                o[1] = __fadd_rn(__fmul_rn(o[1], g.y), bv.y);
+                o[2] = __fadd_rn(__fmul_rn(o[2], g.z), bv.z);
+                o[3] = __fadd_rn(__fmul_rn(o[3], g.w), bv.w);
+            } else if (EDGE) {
+                const int gy = c.gy0 + r;
+                const unsigned int mk = (gy >= 1 && gy <= c.N - 2) ? cin : 0u;
 #pragma unroll
-        for (int t = 0; t < 9; ++t) w[t] = T.ktab[9 * k0 + t];
-        inv0 = T.invd[k0];
+                for (int e = 0; e < 4; ++e) o[e] = ((mk >> e) & 1u) ? o[e] : 0.0f;
+            }
+            *reinterpret_cast<float4 *>(dst + o4) = make_float4(o[0], o[1], o[2], o[3]);
+            if (XOUT) {
+                const float4 rv = *reinterpret_cast<const float4 *>(raw + o4);
+                *reinterpret_cast<float4 *>(xdst + o4) = make_float4(__fsub_rn(o[0], rv.x), __fsub_rn(o[1], rv.y),
+                                                                     __fsub_rn(o[2], rv.z), __fsub_rn(o[3], rv.w));
+            }
+        });
+        return;
     }
-    Row6 t = load_row6(src, ra - 1, lane), m = load_row6(src, ra, lane);
-    Key6 kt, km, kb;
-    if (slow) {
-        kt = load_key6(c.K, ra - 1, lane);
-        km = load_key6(c.K, ra, lane);
-    }
+    // per-node pattern lookup (tiles crossed by the material interface)
+    const unsigned int cin = col_interior_bits(c, lane);
+    Row6 t = load_row6(src + (ra - 1) * BW + 4 * lane), m = load_row6(src + ra * BW + 4 * lane);
+    Key6 kt = load_key6(c.K, ra - 1, lane), km = load_key6(c.K, ra, lane), kb;
     for (int r = ra; r < rb; ++r) {
-        const Row6 b = load_row6(src, r + 1, lane);
-        float acc[4];
-        float inv[4] = {inv0, inv0, inv0, inv0};
-        if (slow) {
-            kb = load_key6(c.K, r + 1, lane);
-            stencil4_keys(T.ktab, t, m, b, kt, km, kb, acc);
+        const Row6 b = load_row6(src + (r + 1) * BW + 4 * lane);
+        float acc[4], inv[4];
+        kb = load_key6(c.K, r + 1, lane);
+        stencil4_keys(T.ktab, t, m, b, kt, km, kb, acc);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) inv[e] = T.invd[km.k[e + 1]];
-            kt = km;
-            km = kb;
-        } else {
-            stencil4(w, t, m, b, acc);
-        }
+        for (int e = 0; e < 4; ++e) inv[e] = T.invd[km.k[e + 1]];
+        kt = km;
+        km = kb;
         const float4 fv = *reinterpret_cast<const float4 *>(c.F + r * BW + 4 * lane);
         const float ff[4] = {fv.x, fv.y, fv.z, fv.w};
         float o[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float res = __fsub_rn(ff[e], acc[e]);
-            o[e] = __fadd_rn(__fmul_rn(inv[e], res), m.a[e + 1]);
-        }
+        for (int e = 0; e < 4; ++e) o[e] = __fadd_rn(__fmul_rn(inv[e], __fsub_rn(ff[e], acc[e])), m.a[e + 1]);
         if (GBC) {
             const float4 g = *reinterpret_cast<const float4 *>(c.IDX + r * BW + 4 * lane);
             const float4 bv = *reinterpret_cast<const float4 *>(c.BVAL + r * BW + 4 * lane);
@@ -317,45 +372,44 @@ __device__ __forceinline__ void stage_jacobi(const TileCtx &c, const Tables &T, 
 
 // ---------------------------------------------------------------------------------------------------------
 // One HNet layer on rows [lo,hi): dst = geometry_idx * (w9 (*) src) ; if ADD: dst = base + that  (u = J + H(x))
-template <bool GBC, bool ADD>
+template <bool GBC, bool ADD, bool EDGE>
 __device__ __forceinline__ void stage_hlayer(const TileCtx &c, const float *w9, const float *src, float *dst,
                                              const float *base, int lo, int hi) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int ra, rb;
     warp_rows(lo, hi, warp, ra, rb);
     if (ra >= rb) return;
-    const unsigned int cin = col_interior_bits(c, lane);
+    unsigned int cin = 0xfu;
+    if (EDGE && !GBC) cin = col_interior_bits(c, lane);
     float w[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) w[t] = w9[t];
-    Row6 t = load_row6(src, ra - 1, lane), m = load_row6(src, ra, lane);
-    for (int r = ra; r < rb; ++r) {
-        const Row6 b = load_row6(src, r + 1, lane);
+    const int lofs = 4 * lane;
+    for_rows3(src, ra, rb, lane, [&](int r, const Row6 &t, const Row6 &m, const Row6 &b) {
         float o[4];
         stencil4(w, t, m, b, o);
+        const int o4 = r * BW + lofs;
         if (GBC) {
-            const float4 g = *reinterpret_cast<const float4 *>(c.IDX + r * BW + 4 * lane);
+            const float4 g = *reinterpret_cast<const float4 *>(c.IDX + o4);
             o[0] = __fmul_rn(o[0], g.x);
             o[1] = __fmul_rn(o[1], g.y);
             o[2] = __fmul_rn(o[2], g.z);
             o[3] = __fmul_rn(o[3], g.w);
-        } else {
+        } else if (EDGE) {
             const int gy = c.gy0 + r;
-            const bool rin = (gy >= 1 && gy <= c.N - 2);
+            const unsigned int mk = (gy >= 1 && gy <= c.N - 2) ? cin : 0u;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) o[e] = (rin && ((cin >> e) & 1u)) ? o[e] : 0.0f;
+            for (int e = 0; e < 4; ++e) o[e] = ((mk >> e) & 1u) ? o[e] : 0.0f;
         }
         if (ADD) {
-            const float4 jv = *reinterpret_cast<const float4 *>(base + r * BW + 4 * lane);
+            const float4 jv = *reinterpret_cast<const float4 *>(base + o4);
             o[0] = __fadd_rn(jv.x, o[0]);
             o[1] = __fadd_rn(jv.y, o[1]);
             o[2] = __fadd_rn(jv.z, o[2]);
             o[3] = __fadd_rn(jv.w, o[3]);
         }
-        *reinterpret_cast<float4 *>(dst + r * BW + 4 * lane) = make_float4(o[0], o[1], o[2], o[3]);
-        t = m;
-        m = b;
-    }
+        *reinterpret_cast<float4 *>(dst + o4) = make_float4(o[0], o[1], o[2], o[3]);
+    });
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -363,70 +417,92 @@ __device__ __forceinline__ void stage_hlayer(const TileCtx &c, const float *w9, 
 //   OUT_RESIDUAL / OUT_KU : store tile-interior values to global r_out
 //   OUT_RESTRICT          : write r into rdst (smem) for stage_restrict
 //   OUT_NORM              : accumulate sum of squares over interior nodes of the tile interior
-template <bool KEYS, int MODE>
-__device__ __forceinline__ double stage_out(const TileCtx &c, const Tables &T, const TileParams &p, const float *src,
-                                            float *rdst, int lo, int hi) {
+template <bool KEYS, int MODE, bool EDGE>
+__device__ __forceinline__ double stage_out(const TileCtx &c, const Tables &T, const RegW &W, const TileParams &p,
+                                            const float *src, float *rdst, int lo, int hi) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int ra, rb;
     warp_rows(lo, hi, warp, ra, rb);
     double part = 0.0;
     if (ra >= rb) return part;
-    const unsigned int cin = col_interior_bits(c, lane);
-    const unsigned int cdom = col_domain_bits(c, lane);
     const bool slow = KEYS && !c.keys_uniform;
     const bool lane_int = (4 * lane >= p.HX) && (4 * lane < BW - p.HX);
-    float w[9];
-    {
-        const int k0 = KEYS ? c.k0 : 0;
+    unsigned int cin = 0xfu, cdom = 0xfu;
+    if (EDGE) {
+        cin = col_interior_bits(c, lane);
+        cdom = col_domain_bits(c, lane);
+    }
+    const int lofs = 4 * lane;
+    auto emit = [&](int r, float (&o)[4]) {
+        const int o4 = r * BW + lofs;
+        if (MODE == OUT_RESTRICT) {
+            *reinterpret_cast<float4 *>(rdst + o4) = make_float4(o[0], o[1], o[2], o[3]);
+        } else if (MODE == OUT_NORM) {
+            bool ok = lane_int && (r >= p.HT) && (r < p.HT + p.TH);
+            unsigned int mk = 0xfu;
+            if (EDGE) {
+                const int gy = c.gy0 + r;
+                ok = ok && (gy >= 1 && gy <= c.N - 2);
+                mk = cin;
+            }
+            if (ok) {
+                float s0 = (mk & 1u) ? o[0] : 0.0f, s1 = (mk & 2u) ? o[1] : 0.0f;
+                float s2 = (mk & 4u) ? o[2] : 0.0f, s3 = (mk & 8u) ? o[3] : 0.0f;
+                part += (double)s0 * (double)s0 + (double)s1 * (double)s1;
+                part += (double)s2 * (double)s2 + (double)s3 * (double)s3;
+            }
+        } else {  // global store of the tile interior; columns >= N of a straddling chunk are written as zero
+            bool ok = lane_int && (r >= p.HT) && (r < p.HT + p.TH);
+            const int gy = c.gy0 + r;
+            if (EDGE) {
+                ok = ok && (gy >= 0 && gy <= c.N - 1) && (cdom & 1u);
 #pragma unroll
-        for (int t = 0; t < 9; ++t) w[t] = T.ktab[9 * k0 + t];
-    }
-    Row6 t = load_row6(src, ra - 1, lane), m = load_row6(src, ra, lane);
-    Key6 kt, km, kb;
-    if (slow) {
-        kt = load_key6(c.K, ra - 1, lane);
-        km = load_key6(c.K, ra, lane);
-    }
-    for (int r = ra; r < rb; ++r) {
-        const Row6 b = load_row6(src, r + 1, lane);
-        float acc[4];
-        if (slow) {
-            kb = load_key6(c.K, r + 1, lane);
-            stencil4_keys(T.ktab, t, m, b, kt, km, kb, acc);
-            kt = km;
-            km = kb;
-        } else {
-            stencil4(w, t, m, b, acc);
+                for (int e = 0; e < 4; ++e) o[e] = ((cdom >> e) & 1u) ? o[e] : 0.0f;
+            }
+            if (ok) {
+                float *gp = p.r_out + (long long)c.b * p.plane + (long long)gy * p.pitch + (c.gx0 + lofs);
+                st_global_v4(gp, make_float4(o[0], o[1], o[2], o[3]));
+            }
         }
-        float o[4];
+    };
+    if (!slow) {
+        for_rows3(src, ra, rb, lane, [&](int r, const Row6 &t, const Row6 &m, const Row6 &b) {
+            float acc[4], o[4];
+            stencil4(W.kw, t, m, b, acc);
+            if (MODE == OUT_KU) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = acc[e];
+            } else {
+                const float4 fv = *reinterpret_cast<const float4 *>(c.F + r * BW + lofs);
+                o[0] = __fsub_rn(fv.x, acc[0]);
+                o[1] = __fsub_rn(fv.y, acc[1]);
+                o[2] = __fsub_rn(fv.z, acc[2]);
+                o[3] = __fsub_rn(fv.w, acc[3]);
+            }
+            emit(r, o);
+        });
+        return part;
+    }
+    Row6 t = load_row6(src + (ra - 1) * BW + lofs), m = load_row6(src + ra * BW + lofs);
+    Key6 kt = load_key6(c.K, ra - 1, lane), km = load_key6(c.K, ra, lane), kb;
+    for (int r = ra; r < rb; ++r) {
+        const Row6 b = load_row6(src + (r + 1) * BW + lofs);
+        float acc[4], o[4];
+        kb = load_key6(c.K, r + 1, lane);
+        stencil4_keys(T.ktab, t, m, b, kt, km, kb, acc);
+        kt = km;
+        km = kb;
         if (MODE == OUT_KU) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) o[e] = acc[e];
         } else {
-            const float4 fv = *reinterpret_cast<const float4 *>(c.F + r * BW + 4 * lane);
+            const float4 fv = *reinterpret_cast<const float4 *>(c.F + r * BW + lofs);
             o[0] = __fsub_rn(fv.x, acc[0]);
             o[1] = __fsub_rn(fv.y, acc[1]);
             o[2] = __fsub_rn(fv.z, acc[2]);
             o[3] = __fsub_rn(fv.w, acc[3]);
         }
-        const int gy = c.gy0 + r;
-        if (MODE == OUT_RESTRICT) {
-            *reinterpret_cast<float4 *>(rdst + r * BW + 4 * lane) = make_float4(o[0], o[1], o[2], o[3]);
-        } else if (MODE == OUT_NORM) {
-            const bool rin = (gy >= 1 && gy <= c.N - 2) && (r >= p.HT) && (r < p.HT + p.TH) && lane_int;
-            if (rin) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if ((cin >> e) & 1u) part += (double)o[e] * (double)o[e];
-            }
-        } else {  // global store of the tile interior, columns >= N of a straddling chunk are written as zero
-            if (gy >= 0 && gy <= c.N - 1 && r >= p.HT && r < p.HT + p.TH && lane_int && (cdom & 1u)) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) o[e] = ((cdom >> e) & 1u) ? o[e] : 0.0f;
-                float *gp = p.r_out + (long long)c.b * p.plane + (long long)gy * p.pitch + (c.gx0 + 4 * lane);
-                st_global_v4(gp, make_float4(o[0], o[1], o[2], o[3]));
-            }
-        }
+        emit(r, o);
         t = m;
         m = b;
     }
@@ -436,22 +512,21 @@ __device__ __forceinline__ double stage_out(const TileCtx &c, const Tables &T, c
 // ---------------------------------------------------------------------------------------------------------
 // Full-weighting style restriction of r (smem, valid on rows [HT-1, HT+TH]) to the coarse rows owned by this tile:
 //   fc[I][J] = scale * chain_{a,c} R[key(src)][3a+c] * r[2I-1+a][2J-1+c],  1 <= I,J <= Nc-2, ring = 0
-template <bool KEYS>
-__device__ __forceinline__ void stage_restrict(const TileCtx &c, const Tables &T, const TileParams &p,
+template <bool KEYS, bool EDGE>
+__device__ __forceinline__ void stage_restrict(const TileCtx &c, const Tables &T, const RegW &W, const TileParams &p,
                                                const float *rbuf) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool lane_int = (4 * lane >= p.HX) && (4 * lane < BW - p.HX);
     const bool slow = KEYS && (p.rtab_n > 1) && !c.keys_uniform;
-    const int kk = (KEYS && p.rtab_n > 1) ? c.k0 : 0;
-    float w[9];
-#pragma unroll
-    for (int t = 0; t < 9; ++t) w[t] = T.rtab[9 * kk + t];
     const int ncr = p.TH / 2;
+    const int lofs = 4 * lane;
+    const int J0 = (c.gx0 + lofs) >> 1;  // even
     for (int q = warp; q < ncr; q += NWARPS) {
         const int r = p.HT + 2 * q;  // box row of fine row 2I
         const int I = (c.gy0 + r) >> 1;
-        if (I > p.Nc - 1) break;
-        const Row6 t = load_row6(rbuf, r - 1, lane), m = load_row6(rbuf, r, lane), b = load_row6(rbuf, r + 1, lane);
+        if (EDGE && I > p.Nc - 1) break;
+        const float *pr = rbuf + (r - 1) * BW + lofs;
+        const Row6 t = load_row6(pr), m = load_row6(pr + BW), b = load_row6(pr + 2 * BW);
         float o[2];
         if (slow) {
             const Key6 kt = load_key6(c.K, r - 1, lane), km = load_key6(c.K, r, lane), kb = load_key6(c.K, r + 1, lane);
@@ -473,30 +548,33 @@ __device__ __forceinline__ void stage_restrict(const TileCtx &c, const Tables &T
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int e = 2 * h;
-                float s = __fmul_rn(w[0], t.a[e]);
-                s = __fmaf_rn(w[1], t.a[e + 1], s);
-                s = __fmaf_rn(w[2], t.a[e + 2], s);
-                s = __fmaf_rn(w[3], m.a[e], s);
-                s = __fmaf_rn(w[4], m.a[e + 1], s);
-                s = __fmaf_rn(w[5], m.a[e + 2], s);
-                s = __fmaf_rn(w[6], b.a[e], s);
-                s = __fmaf_rn(w[7], b.a[e + 1], s);
-                s = __fmaf_rn(w[8], b.a[e + 2], s);
+                float s = __fmul_rn(W.rw[0], t.a[e]);
+                s = __fmaf_rn(W.rw[1], t.a[e + 1], s);
+                s = __fmaf_rn(W.rw[2], t.a[e + 2], s);
+                s = __fmaf_rn(W.rw[3], m.a[e], s);
+                s = __fmaf_rn(W.rw[4], m.a[e + 1], s);
+                s = __fmaf_rn(W.rw[5], m.a[e + 2], s);
+                s = __fmaf_rn(W.rw[6], b.a[e], s);
+                s = __fmaf_rn(W.rw[7], b.a[e + 1], s);
+                s = __fmaf_rn(W.rw[8], b.a[e + 2], s);
                 o[h] = s;
             }
         }
-        if (!lane_int) continue;
-        const int J0 = (c.gx0 + 4 * lane) >> 1;  // even
-        if (J0 > p.Nc - 1) continue;
-        const bool Iin = (I >= 1 && I <= p.Nc - 2);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int J = J0 + h;
-            float v = p.r_has_scale ? __fmul_rn(T.r_scale, o[h]) : o[h];
-            o[h] = (Iin && J >= 1 && J <= p.Nc - 2) ? v : 0.0f;
+        if (p.r_has_scale) {
+            o[0] = __fmul_rn(T.r_scale, o[0]);
+            o[1] = __fmul_rn(T.r_scale, o[1]);
         }
-        float *gp = p.fc + (long long)c.b * p.plane_c + (long long)I * p.pitch_c + J0;
-        *reinterpret_cast<float2 *>(gp) = make_float2(o[0], o[1]);
+        bool ok = lane_int;
+        if (EDGE) {
+            ok = ok && (J0 <= p.Nc - 1);
+            const bool Iin = (I >= 1 && I <= p.Nc - 2);
+            o[0] = (Iin && J0 >= 1 && J0 <= p.Nc - 2) ? o[0] : 0.0f;
+            o[1] = (Iin && J0 + 1 <= p.Nc - 2) ? o[1] : 0.0f;
+        }
+        if (ok) {
+            float *gp = p.fc + (long long)c.b * p.plane_c + (long long)I * p.pitch_c + J0;
+            *reinterpret_cast<float2 *>(gp) = make_float2(o[0], o[1]);
+        }
     }
 }
 
@@ -519,11 +597,11 @@ __device__ __forceinline__ void stage_prolong(const TileCtx &c, const Tables &T,
         int ktop[3] = {0, 0, 0}, kbot[3] = {0, 0, 0};
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-            top[q] = c.VC[I0 * CW + cc + q];
-            if (odd) bot[q] = c.VC[(I0 + 1) * CW + cc + q];
+            top[q] = c.VC[I0 * CW + c.vcofs + cc + q];
+            if (odd) bot[q] = c.VC[(I0 + 1) * CW + c.vcofs + cc + q];
             if (pkeys) {
-                ktop[q] = c.KC[I0 * KCW + cc + q];
-                if (odd) kbot[q] = c.KC[(I0 + 1) * KCW + cc + q];
+                ktop[q] = c.KC[I0 * KCW + c.kcofs + cc + q];
+                if (odd) kbot[q] = c.KC[(I0 + 1) * KCW + c.kcofs + cc + q];
             }
         }
         float e[4];

@@ -249,6 +249,8 @@ def gen_solve():
     run64("modelA_n64_v11", 64, None, 20)
     run64("modelA_n64_rhs", 64, None, 12, rhs_seed=5)
     run64("modelA_n1024_L10", 1024, 10, 15)
+    run64("modelA_n1024_L8", 1024, 8, 10)
+    run64("modelA_n64_L4_v11", 64, 4, 20)
 
     # ---- MM_Interface_error.ipynb: two-phase circle a=[1,20], n=64, f=fnet(ones), u0=0, EPS=5e-5 (quirk variant)
     nsI = H.notebook_namespace("MM_Interface_error.ipynb", [0, 1, 2])
