@@ -13,6 +13,10 @@
 #include "../../../include/mgfea.h"
 #include "mgfea_tile.cuh"
 
+#ifndef MGFEA_MINBLOCKS
+#define MGFEA_MINBLOCKS 3
+#endif
+
 namespace mgfea {
 
 // =========================================================================================================
@@ -40,12 +44,20 @@ struct TileCoord {
     int b, y0, x0, gy0, gx0, cy0, cx0;
     int kx0, vx0, kcx0;  // 16-byte aligned start columns of the key / coarse value / coarse key boxes
 };
+// exact t / d for 0 <= t < 2^24 without an integer division (float estimate + one correction step)
+__device__ __forceinline__ int fast_div(int t, int d, float inv) {
+    int q = __float2int_rz(__int2float_rn(t) * inv);
+    int r = t - q * d;
+    if (r < 0) --q;
+    else if (r >= d) ++q;
+    return q;
+}
 __device__ __forceinline__ TileCoord tile_coord(const TileParams &p, int t) {
     TileCoord tc;
     const int per = p.ntx * p.nty;
-    tc.b = t / per;
+    tc.b = (p.B == 1) ? 0 : fast_div(t, per, p.inv_per);
     const int rem = t - tc.b * per;
-    const int ty = rem / p.ntx, tx = rem - ty * p.ntx;
+    const int ty = fast_div(rem, p.ntx, p.inv_ntx), tx = rem - ty * p.ntx;
     tc.y0 = ty * p.TH;
     tc.x0 = tx * p.TWI;
     tc.gy0 = tc.y0 - p.HT;
@@ -84,13 +96,14 @@ __device__ __forceinline__ void cpasync_box(unsigned char *dst, const unsigned c
 template <bool KEYS, bool GBC>
 __device__ __forceinline__ void issue_loads(unsigned char *smem, const TileMaps &maps, const TileParams &p,
                                             Tables &T, int t, int s) {
+    if (p.use_tma && threadIdx.x != 0) return;  // one elected thread drives the TMA unit
     const TileCoord tc = tile_coord(p, t);
     const StageBufs sb = stage_bufs(smem, p, s);
     const bool need_u = !p.zero_init;
     const bool need_f = (p.nsweeps > 0) || (p.out_mode != OUT_NONE && p.out_mode != OUT_KU);
     const int bcb = (p.bc_plane == 0) ? 0 : tc.b;
     if (p.use_tma) {
-        if (threadIdx.x == 0) {
+        {
             uint64_t *bar = reinterpret_cast<uint64_t *>(&T.mbar[s]);
             mbar_arrive_expect_tx(bar, p.tx_bytes);
             if (need_u) tma_load_3d(sb.U, &maps.u, bar, tc.gx0, tc.gy0, tc.b);
@@ -156,7 +169,7 @@ __device__ __forceinline__ void run_tile(TileCtx &c, Tables &T, const RegW &W, c
     int d = 0;
     float *cur = c.U;
     if (p.prolong_mode) {
-        stage_prolong<GBC>(c, T, p, c.U);
+        stage_prolong<GBC, EDGE>(c, T, p, c.U);
         __syncthreads();
     }
     if (p.nsweeps == 0 && p.smoother == 2) {  // reset_boundary only
@@ -218,7 +231,7 @@ __device__ __forceinline__ void run_tile(TileCtx &c, Tables &T, const RegW &W, c
 }
 
 template <bool KEYS, bool GBC>
-__global__ void __launch_bounds__(NTHREADS) mg_tile_kernel(const __grid_constant__ TileMaps maps,
+__global__ void __launch_bounds__(NTHREADS, MGFEA_MINBLOCKS) mg_tile_kernel(const __grid_constant__ TileMaps maps,
                                                            const TileParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     Tables &T = *reinterpret_cast<Tables *>(smem);
@@ -632,13 +645,15 @@ static inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
 
 // tuning knobs (defaults chosen from the measurements in profiles/); overridable through the environment for sweeps
 struct Knobs {
-    int th = 32, stages = 2, ctas = 0;
+    int th = 32, stages = 1, ctas = 0, threads = 256;
     Knobs() {
         if (const char *e = getenv("MGFEA_TH")) th = atoi(e);
         if (const char *e = getenv("MGFEA_STAGES")) stages = atoi(e);
         if (const char *e = getenv("MGFEA_CTAS")) ctas = atoi(e);
-        if (th < 8 || th > 64 || (th & 7)) th = 32;
-        if (stages != 1) stages = 2;
+        if (const char *e = getenv("MGFEA_THREADS")) threads = atoi(e);
+        threads = 256;
+        if (th < 8 || th > 64 || (th & 1)) th = 32;
+        if (stages != 2) stages = 1;
     }
 };
 static const Knobs &knobs() {
@@ -647,7 +662,8 @@ static const Knobs &knobs() {
 }
 
 template <bool KEYS, bool GBC>
-static cudaError_t launch_tile(const TileMaps &maps, const TileParams &p, int grid, size_t smem, cudaStream_t st) {
+static cudaError_t launch_tile(const TileMaps &maps, const TileParams &p, int grid, int threads, size_t smem,
+                               cudaStream_t st) {
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(mg_tile_kernel<KEYS, GBC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -655,6 +671,7 @@ static cudaError_t launch_tile(const TileMaps &maps, const TileParams &p, int gr
         if (e != cudaSuccess) return e;
         configured = 232448;
     }
+    (void)threads;
     mg_tile_kernel<KEYS, GBC><<<grid, NTHREADS, smem, st>>>(maps, p);
     g_launches.fetch_add(1);
     return cudaGetLastError();
@@ -775,7 +792,7 @@ static int run_program(const Program &pr, cudaStream_t st) {
     int TH = knobs().th;
     p.nstages = knobs().stages;
     size_t smem = 0;
-    for (;; TH -= 8) {
+    for (;; TH -= 4) {
         if (TH < 8) return MGFEA_EUNSUPPORTED;
         p.TH = TH;
         p.BH = TH + p.HT + p.HB;
@@ -822,6 +839,9 @@ static int run_program(const Program &pr, cudaStream_t st) {
     const long long ntiles = (long long)p.ntx * p.nty * pr.B;
     if (ntiles > 0x3fffffffLL) return MGFEA_EUNSUPPORTED;
     p.ntiles = (int)ntiles;
+    if (ntiles >= (1 << 24)) return MGFEA_EUNSUPPORTED;
+    p.inv_per = 1.0f / (float)(p.ntx * p.nty);
+    p.inv_ntx = 1.0f / (float)p.ntx;
 
     DeviceScratch *scr = nullptr;
     if ((rc = get_scratch((size_t)ntiles, &scr))) return rc;
@@ -869,10 +889,11 @@ static int run_program(const Program &pr, cudaStream_t st) {
     int grid = (int)(ntiles < maxc ? ntiles : maxc);
 
     cudaError_t e;
+    const int th = knobs().threads;
     if (keys) {
-        e = gbc ? launch_tile<true, true>(maps, p, grid, smem, st) : launch_tile<true, false>(maps, p, grid, smem, st);
+        e = gbc ? launch_tile<true, true>(maps, p, grid, th, smem, st) : launch_tile<true, false>(maps, p, grid, th, smem, st);
     } else {
-        e = gbc ? launch_tile<false, true>(maps, p, grid, smem, st) : launch_tile<false, false>(maps, p, grid, smem, st);
+        e = gbc ? launch_tile<false, true>(maps, p, grid, th, smem, st) : launch_tile<false, false>(maps, p, grid, th, smem, st);
     }
     return (int)e;
 }

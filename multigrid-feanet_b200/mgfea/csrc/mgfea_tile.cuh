@@ -22,6 +22,7 @@ namespace mgfea {
 constexpr int BW = 128;        // box width in floats == 32 lanes x 4
 constexpr int NTHREADS = 256;  // 8 warps
 constexpr int NWARPS = NTHREADS / 32;
+constexpr int MAXWARPS = NWARPS;
 constexpr int MAXPAT = 16;
 constexpr int MAXLAYERS = 8;
 // TMA tiled loads (no swizzle) fault with "illegal instruction" unless the innermost start coordinate is a multiple of
@@ -44,6 +45,7 @@ struct TileParams {
     long long plane;
     int TH, HX, HT, HB, BH, TWI;  // tile interior rows, column halo, top/bottom halo rows, box rows, interior cols
     int ntx, nty, ntiles;         // tiles per sample in x / y, total tiles (all samples)
+    float inv_per, inv_ntx;       // reciprocals for the division-free tile index decomposition
     int use_tma, nstages;
     // program
     int zero_init, prolong_mode, prolong_seq, nsweeps, smoother, store_u, out_mode;
@@ -103,7 +105,7 @@ struct Tables {
     float hw[MAXLAYERS * 9];
     float r_scale, p_scale;
     unsigned long long mbar[2];
-    double red[NWARPS];
+    double red[MAXWARPS];
     int flag;
 };
 constexpr int TABLES_BYTES = 4096;
@@ -231,25 +233,38 @@ __device__ __forceinline__ unsigned int col_domain_bits(const TileCtx &c, int la
     return m;
 }
 
-// Row loop with a rotating 3-row register window (unrolled by 3 so the rotation costs no moves).  `body(r, t, m, b)`
-// is called for every row r in [ra, rb) with the rows r-1, r, r+1 of `src`.
+// Row loop over a warp's rows [ra, rb): TWO output rows per iteration from a 4-row register window (rows r-1..r+2).
+// The two `body` calls of an iteration are independent (8 FMA chains per lane in flight instead of 4) and both row
+// loads are issued together, which hides the LDS.128 -> SHFL -> FFMA latency at the modest occupancy that the staged
+// boxes allow.  Unrolled by two iterations so that the window rotation costs no register moves.
+// `body(r, t, m, b)` is called once for every row r with the rows r-1, r, r+1 of `src`.
 template <class Body>
 __device__ __forceinline__ void for_rows3(const float *src, int ra, int rb, int lane, Body body) {
     const float *ps = src + (ra - 1) * BW + 4 * lane;
-    Row6 r0 = load_row6(ps), r1 = load_row6(ps + BW), r2;
-    ps += 2 * BW;
+    Row6 a = load_row6(ps), b = load_row6(ps + BW), c, d;
     int r = ra;
-    for (;;) {
-        r2 = load_row6(ps);
-        body(r, r0, r1, r2);
-        if (++r >= rb) break;
-        r0 = load_row6(ps + BW);
-        body(r, r1, r2, r0);
-        if (++r >= rb) break;
-        r1 = load_row6(ps + 2 * BW);
-        body(r, r2, r0, r1);
-        if (++r >= rb) break;
-        ps += 3 * BW;
+    while (r + 1 < rb) {
+        c = load_row6(ps + 2 * BW);
+        d = load_row6(ps + 3 * BW);
+        body(r, a, b, c);
+        body(r + 1, b, c, d);
+        r += 2;
+        ps += 2 * BW;
+        if (r + 1 >= rb) {
+            a = c;
+            b = d;
+            break;
+        }
+        a = load_row6(ps + 2 * BW);
+        b = load_row6(ps + 3 * BW);
+        body(r, c, d, a);
+        body(r + 1, d, a, b);
+        r += 2;
+        ps += 2 * BW;
+    }
+    if (r < rb) {
+        c = load_row6(ps + 2 * BW);
+        body(r, a, b, c);
     }
 }
 
@@ -580,9 +595,54 @@ __device__ __forceinline__ void stage_restrict(const TileCtx &c, const Tables &T
 
 // ---------------------------------------------------------------------------------------------------------
 // Prolongation + correction on all box rows: U += scale * P(vc)   (coarse box VC, coarse keys KC)
-template <bool GBC>
+template <bool GBC, bool EDGE>
 __device__ __forceinline__ void stage_prolong(const TileCtx &c, const Tables &T, const TileParams &p, float *U) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (!EDGE && !GBC && p.prolong_mode == 1) {
+        // interior tile, bilinear: every node of the box is an interior node of the domain, no masks needed
+        const float *vbase = c.VC + c.vcofs + 2 * lane;  // 8-byte aligned (vcofs is even)
+        const bool seq = p.prolong_seq != 0;
+        for (int r = warp; r < c.BH; r += NWARPS) {
+            const int gy = c.gy0 + r;
+            const float *vt = vbase + ((gy >> 1) - c.cy0) * CW;
+            const float2 t01 = *reinterpret_cast<const float2 *>(vt);
+            const float t2 = vt[2];
+            float e0, e1, e2, e3;
+            if (!(gy & 1)) {
+                e0 = t01.x;
+                e1 = __fadd_rn(__fmul_rn(0.5f, t01.x), __fmul_rn(0.5f, t01.y));
+                e2 = t01.y;
+                e3 = __fadd_rn(__fmul_rn(0.5f, t01.y), __fmul_rn(0.5f, t2));
+            } else {
+                const float2 b01 = *reinterpret_cast<const float2 *>(vt + CW);
+                const float b2 = vt[CW + 2];
+                e0 = __fadd_rn(__fmul_rn(0.5f, t01.x), __fmul_rn(0.5f, b01.x));
+                e2 = __fadd_rn(__fmul_rn(0.5f, t01.y), __fmul_rn(0.5f, b01.y));
+                if (seq) {
+                    e1 = __fadd_rn(__fmul_rn(0.25f, t01.x), __fmul_rn(0.25f, t01.y));
+                    e1 = __fadd_rn(e1, __fmul_rn(0.25f, b01.x));
+                    e1 = __fadd_rn(e1, __fmul_rn(0.25f, b01.y));
+                    e3 = __fadd_rn(__fmul_rn(0.25f, t01.y), __fmul_rn(0.25f, t2));
+                    e3 = __fadd_rn(e3, __fmul_rn(0.25f, b01.y));
+                    e3 = __fadd_rn(e3, __fmul_rn(0.25f, b2));
+                } else {
+                    const float ta = __fadd_rn(__fmul_rn(0.5f, t01.x), __fmul_rn(0.5f, t01.y));
+                    const float ba = __fadd_rn(__fmul_rn(0.5f, b01.x), __fmul_rn(0.5f, b01.y));
+                    e1 = __fadd_rn(__fmul_rn(0.5f, ta), __fmul_rn(0.5f, ba));
+                    const float tb = __fadd_rn(__fmul_rn(0.5f, t01.y), __fmul_rn(0.5f, t2));
+                    const float bb = __fadd_rn(__fmul_rn(0.5f, b01.y), __fmul_rn(0.5f, b2));
+                    e3 = __fadd_rn(__fmul_rn(0.5f, tb), __fmul_rn(0.5f, bb));
+                }
+            }
+            float4 uv = *reinterpret_cast<float4 *>(U + r * BW + 4 * lane);
+            uv.x = __fadd_rn(uv.x, e0);
+            uv.y = __fadd_rn(uv.y, e1);
+            uv.z = __fadd_rn(uv.z, e2);
+            uv.w = __fadd_rn(uv.w, e3);
+            *reinterpret_cast<float4 *>(U + r * BW + 4 * lane) = uv;
+        }
+        return;
+    }
     const unsigned int cin = col_interior_bits(c, lane);
     const unsigned int cdom = col_domain_bits(c, lane);
     const int cc = 2 * lane;  // coarse box column of fine box column 4*lane (gx0 even, cx0 = gx0/2)
