@@ -12,6 +12,7 @@
 
 #include "../../../include/mgfea.h"
 #include "mgfea_tile.cuh"
+#include "mgfea_tail.cuh"
 
 #ifndef MGFEA_MINBLOCKS
 #define MGFEA_MINBLOCKS 3
@@ -942,6 +943,103 @@ static int run_chain(Program base, const float *src, float *bufA, float *bufB, i
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// coarse tail launch: levels [lt, L) of the hierarchy in one CTA per sample
+static int run_tail(const mgfea_grid *grids, const mgfea_level_bufs *bufs, int lt, int L, const mgfea_cycle_cfg *cfg,
+                    mgfea_ctl *ctl, int B, cudaStream_t st) {
+    TailParams p;
+    memset(&p, 0, sizeof(p));
+    p.nlev = L - lt;
+    if (p.nlev < 1 || p.nlev > TAIL_MAXLEV) return MGFEA_EUNSUPPORTED;
+    p.B = B;
+    const bool hj = (cfg->smoother == MGFEA_SMOOTH_HJACOBI);
+    bool keys = false;
+    int off = 0;  // floats
+    for (int i = 0; i < p.nlev; ++i) {
+        const mgfea_grid &g = grids[lt + i];
+        TailLevel &tl = p.lv[i];
+        if (g.N > TAIL_MAXN || g.bc_idx != nullptr) return MGFEA_EUNSUPPORTED;
+        tl.N = g.N;
+        tl.S = round_up(g.N, 4) + 8;
+        const int sz = (g.N + 2) * tl.S;
+        tl.off_u = off;
+        off += sz;
+        tl.off_v = off;
+        off += sz;
+        tl.off_f = off;
+        off += sz;
+        tl.off_t0 = off;
+        off += sz;
+        tl.off_t1 = off;
+        off += hj ? sz : 0;
+        tl.off_t2 = off;
+        off += hj ? sz : 0;
+        tl.npat = g.npat;
+        tl.keys = g.keys;
+        tl.key_pitch = g.key_pitch;
+        tl.ktab = g.ktab;
+        tl.invd = g.invd;
+        tl.off_k = -1;
+        if (g.keys) keys = true;
+        if (!g.ktab || !g.invd || g.npat < 1 || g.npat > MAXPAT) return MGFEA_EINVAL;
+    }
+    p.total_floats = off;  // multiple of 4
+    p.off_tab = off;
+    off += p.nlev * (MAXPAT * 9 + MAXPAT);
+    int bytes = off * 4;
+    if (keys) {
+        for (int i = 0; i < p.nlev; ++i) {
+            TailLevel &tl = p.lv[i];
+            if (!tl.keys) continue;
+            tl.off_k = bytes;
+            bytes += round_up((tl.N + 2) * tl.S, 16);
+        }
+    }
+    if (bytes > 232448 - 2048) return MGFEA_EUNSUPPORTED;
+    p.f_in = bufs[lt].f;
+    p.u_out = bufs[lt].u;
+    p.pitch = grids[lt].pitch;
+    p.plane = grids[lt].plane;
+    p.nu1 = cfg->nu1;
+    p.nu2 = cfg->nu2;
+    p.smoother = cfg->smoother;
+    p.nlayers = cfg->nlayers;
+    p.hw = cfg->hw;
+    p.prolong_mode = cfg->prolong_mode;
+    p.quirk = cfg->quirk_level0;
+    p.rtab = cfg->rtab;
+    p.rtab_n = cfg->rtab_n;
+    p.r_has_scale = cfg->r_has_scale;
+    p.r_scale = cfg->r_scale_host;
+    p.r_scale_dev = cfg->r_scale_dev;
+    p.ptab = cfg->ptab;
+    p.ptab_n = cfg->ptab_n;
+    p.p_has_scale = cfg->p_has_scale;
+    p.p_scale = cfg->p_scale_host;
+    p.p_scale_dev = cfg->p_scale_dev;
+    p.ctl = ctl;
+    if (hj && (!cfg->hw || cfg->nlayers < 1 || cfg->nlayers > MAXLAYERS)) return MGFEA_EINVAL;
+    static bool configured[2] = {false, false};
+    cudaError_t e;
+    if (keys) {
+        if (!configured[1]) {
+            e = cudaFuncSetAttribute(mg_tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 2048);
+            if (e != cudaSuccess) return (int)e;
+            configured[1] = true;
+        }
+        mg_tail_kernel<true><<<B, TAIL_THREADS, bytes, st>>>(p);
+    } else {
+        if (!configured[0]) {
+            e = cudaFuncSetAttribute(mg_tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 2048);
+            if (e != cudaSuccess) return (int)e;
+            configured[0] = true;
+        }
+        mg_tail_kernel<false><<<B, TAIL_THREADS, bytes, st>>>(p);
+    }
+    g_launches.fetch_add(1);
+    return (int)cudaGetLastError();
+}
+
 }  // namespace mgfea
 
 // =========================================================================================================
@@ -1212,8 +1310,23 @@ int mgfea_vcycle(const mgfea_grid *grids, const mgfea_level_bufs *bufs, int nlev
         pr.r_scale_dev = cfg->r_scale_dev;
     };
 
+    // ---- which levels run inside the single coarse-tail kernel
+    int lt = L;  // first tail level (L = no tail)
+    {
+        const int tmax = cfg->tail_max_n == 0 ? TAIL_MAXN : cfg->tail_max_n;
+        if (tmax > 0) {
+            for (int l = 1; l < L; ++l)
+                if (grids[l].N <= (tmax < TAIL_MAXN ? tmax : TAIL_MAXN)) {
+                    lt = l;
+                    break;
+                }
+            if (L - lt > TAIL_MAXLEV) lt = L;
+            for (int l = lt; l < L; ++l)  // tail levels: default Dirichlet ring, keys on all levels or on none
+                if (grids[l].bc_idx || ((grids[l].keys != nullptr) != (grids[lt < L ? lt : l].keys != nullptr))) lt = L;
+        }
+    }
     // ---- down leg
-    for (int l = 0; l < L; ++l) {
+    for (int l = 0; l < lt; ++l) {
         if (cfg->quirk_level0 && l > 0) {
             // pre-smooth is applied to level 0 instead of level l (MM_Interface_error.ipynb cell 2)
             if (cfg->nu1 > 0) {
@@ -1248,8 +1361,18 @@ int mgfea_vcycle(const mgfea_grid *grids, const mgfea_level_bufs *bufs, int nlev
             }
         }
     }
+    if (lt < L) {
+        if (cfg->quirk_level0 && cfg->nu1 > 0) {  // the pre-smoothing steps of the tail levels go to level 0
+            Program pr = base_prog(0);
+            float *res = nullptr;
+            if ((rc = run_chain(pr, cur[0], bufs[0].u, bufs[0].u_alt, cfg->nu1 * (L - lt), &res, st))) return rc;
+            cur[0] = res;
+        }
+        if ((rc = run_tail(grids, bufs, lt, L, cfg, ctl, B, st))) return rc;
+        cur[lt] = bufs[lt].u;
+    }
     // ---- up leg
-    for (int l = L - 1; l >= 0; --l) {
+    for (int l = lt - 1; l >= 0; --l) {
         Program pr = base_prog(l);
         if (l < L - 1) {
             pr.prolong_mode = cfg->prolong_mode;
