@@ -13,6 +13,7 @@
 #include "../../../include/mgfea.h"
 #include "mgfea_tile.cuh"
 #include "mgfea_tail.cuh"
+#include "mgfea_stream.cuh"
 
 #ifndef MGFEA_MINBLOCKS
 #define MGFEA_MINBLOCKS 3
@@ -647,10 +648,14 @@ static inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
 // tuning knobs (defaults chosen from the measurements in profiles/); overridable through the environment for sweeps
 struct Knobs {
     int th = 32, stages = 1, ctas = 0, threads = 256;
+    int stream_min_n = 2049;  // levels with N >= this use the register-chained streaming kernels (0 disables)
+    int stream_r = 0;         // rows per strip (0 = auto)
     Knobs() {
         if (const char *e = getenv("MGFEA_TH")) th = atoi(e);
         if (const char *e = getenv("MGFEA_STAGES")) stages = atoi(e);
         if (const char *e = getenv("MGFEA_CTAS")) ctas = atoi(e);
+        if (const char *e = getenv("MGFEA_STREAM_MIN_N")) stream_min_n = atoi(e);
+        if (const char *e = getenv("MGFEA_STREAM_R")) stream_r = atoi(e);
         if (const char *e = getenv("MGFEA_THREADS")) threads = atoi(e);
         threads = 256;
         if (th < 8 || th > 64 || (th & 1)) th = 32;
@@ -684,6 +689,105 @@ static int check_field(const void *p, int pitch, long long plane) {
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// streaming kernels (mgfea_stream.cuh): eligibility + launch
+static bool stream_eligible(const Program &pr, bool keys, bool gbc) {
+    const int minn = knobs().stream_min_n;
+    if (minn <= 0 || pr.g->N < minn) return false;
+    if (keys || gbc || pr.reset_only || pr.ktab_override) return false;
+    if (pr.smoother != MGFEA_SMOOTH_JACOBI || pr.nsweeps != 1 || !pr.u_out || !pr.f) return false;
+    if (pr.out_mode == OUT_RESTRICT && pr.prolong_mode == 0) return pr.rtab_n == 1;
+    if (pr.prolong_mode == MGFEA_PROLONG_BILINEAR && (pr.out_mode == OUT_NONE || pr.out_mode == OUT_NORM))
+        return pr.u_in != nullptr;
+    return false;
+}
+
+static int run_stream(const Program &pr, cudaStream_t st) {
+    const mgfea_grid *g = pr.g;
+    StreamParams p;
+    memset(&p, 0, sizeof(p));
+    const int mode = (pr.out_mode == OUT_RESTRICT) ? 0 : 1;
+    p.N = g->N;
+    p.B = pr.B;
+    p.pitch = g->pitch;
+    p.plane = g->plane;
+    p.ntx = (g->N + ST_TWI - 1) / ST_TWI;
+    DeviceScratch *scr = nullptr;
+    int rc;
+    // rows per strip: about one resident wave of warps (2 CTAs x 8 warps per SM), even, >= 8
+    int R = knobs().stream_r;
+    if (R <= 0) {
+        if ((rc = get_scratch(1, &scr))) return rc;
+        const double slots = (double)scr->num_sms * 2 * ST_WARPS;
+        R = (int)((double)(g->N - 1) * p.ntx * pr.B / slots + 0.5);
+        R = (R + 1) & ~1;
+        int best = 8;
+        for (int c = 8; c <= 256; c *= 2)  // powers of two divide N-1 = 2^k exactly
+            if (abs(c - R) < abs(best - R)) best = c;
+        R = best;
+    }
+    if (R < 8) R = 8;
+    R &= ~1;
+    p.R = R;
+    p.nry = (g->N - 1) / R;
+    if (p.nry < 1) p.nry = 1;
+    p.nstrips = p.ntx * p.nry;
+    const long long total = (long long)p.nstrips * pr.B;
+    if (total >= (1 << 24)) return MGFEA_EUNSUPPORTED;
+    p.inv_nstrips = 1.0f / (float)p.nstrips;
+    p.inv_ntx = 1.0f / (float)p.ntx;
+    p.u_in = pr.u_in;
+    p.u_out = pr.u_out;
+    p.f = pr.f;
+    p.ktab = g->ktab;
+    p.invd = g->invd;
+    p.Nc = (g->N - 1) / 2 + 1;
+    if (mode == 0) {
+        p.fc = pr.fc;
+        p.pitch_c = pr.pitch_c;
+        p.plane_c = pr.plane_c;
+        p.rtab = pr.rtab;
+        p.r_has_scale = pr.r_has_scale;
+        p.r_scale = pr.r_scale;
+        p.r_scale_dev = pr.r_scale_dev;
+        if (!pr.fc || !pr.rtab || (pr.pitch_c & 1) || (reinterpret_cast<uintptr_t>(pr.fc) & 7u)) return MGFEA_EALIGN;
+    } else {
+        if (!pr.gc || !pr.vc || pr.gc->N != p.Nc) return MGFEA_EINVAL;
+        p.vc = pr.vc;
+        p.pitch_c = pr.gc->pitch;
+        p.plane_c = pr.gc->plane;
+        p.prolong_seq = (g->N <= 33);
+        p.want_norm = (pr.out_mode == OUT_NORM);
+    }
+    if ((rc = get_scratch((size_t)total, &scr))) return rc;
+    p.partials = scr->tile_partials;
+    p.counter = scr->counter;
+    p.sumsq = pr.sumsq;
+    p.hist = pr.hist;
+    p.ctl = pr.ctl;
+    const size_t smem = (size_t)ST_WARPS * ST_RING_F4 * 32 * 16;
+    long long ctas = (total + ST_WARPS - 1) / ST_WARPS;
+    const long long maxc = (long long)scr->num_sms * 2;
+    const int grid = (int)(ctas < maxc ? ctas : maxc);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(mg_stream_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(mg_stream_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(mg_stream_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    if (mode == 0) {
+        if (pr.u_in)
+            mg_stream_kernel<0, false><<<grid, ST_WARPS * 32, smem, st>>>(p);
+        else
+            mg_stream_kernel<0, true><<<grid, ST_WARPS * 32, smem, st>>>(p);
+    } else {
+        mg_stream_kernel<1, false><<<grid, ST_WARPS * 32, smem, st>>>(p);
+    }
+    g_launches.fetch_add(1);
+    return (int)cudaGetLastError();
+}
+
 static int run_program(const Program &pr, cudaStream_t st) {
     const mgfea_grid *g = pr.g;
     if (!g || g->N < 3 || pr.B < 1) return MGFEA_EINVAL;
@@ -693,6 +797,12 @@ static int run_program(const Program &pr, cudaStream_t st) {
     const bool gbc = (g->bc_idx != nullptr) && (pr.nsweeps > 0 || pr.reset_only || pr.prolong_mode == 1);
     if (keys && (g->key_pitch & 15)) return MGFEA_EALIGN;
     int rc;
+    if (stream_eligible(pr, keys, gbc)) {
+        if (pr.u_in && (rc = check_field(pr.u_in, g->pitch, g->plane))) return rc;
+        if ((rc = check_field(pr.u_out, g->pitch, g->plane))) return rc;
+        if ((rc = check_field(pr.f, g->pitch, g->plane))) return rc;
+        return run_stream(pr, st);
+    }
     if (pr.u_in && (rc = check_field(pr.u_in, g->pitch, g->plane))) return rc;
     if (pr.u_out && (rc = check_field(pr.u_out, g->pitch, g->plane))) return rc;
     if (pr.f && (rc = check_field(pr.f, g->pitch, g->plane))) return rc;
