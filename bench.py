@@ -292,9 +292,9 @@ def run_ours(args):
     alg_down = 4 * (3 * M0 + 2 * M0 + M1)      # pre-smooth (u,f -> u) + residual->restrict (u,f -> f_c)
     alg_up = 4 * (2 * M0 + M1 + 3 * M0)        # prolong->correct (v_c,u -> u) + post-smooth (u,f -> u)
     if ms_down >= ms_up:
-        kname, kms, kalg = "mg_tile_kernel<iso> level-0 down leg (smooth+residual+restrict)", ms_down, alg_down
+        kname, kms, kalg = "mg_stream2_kernel<down> level-0 (smooth+residual+restrict)", ms_down, alg_down
     else:
-        kname, kms, kalg = "mg_tile_kernel<iso> level-0 up leg (prolong+correct+smooth)", ms_up, alg_up
+        kname, kms, kalg = "mg_stream2_kernel<up> level-0 (prolong+correct+smooth)", ms_up, alg_up
     ach = kalg / (kms * 1e-3) / 1e9
     balg = algorithmic_bytes_per_cycle(n, L)
     cyc_ms = ms / steps

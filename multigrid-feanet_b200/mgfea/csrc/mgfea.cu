@@ -650,12 +650,14 @@ struct Knobs {
     int th = 32, stages = 1, ctas = 0, threads = 256;
     int stream_min_n = 2049;  // levels with N >= this use the register-chained streaming kernels (0 disables)
     int stream_r = 0;         // rows per strip (0 = auto)
+    int stream_packed = 1;    // 1: FFMA2 (fma.rn.f32x2) streaming kernels, 0: scalar FFMA
     Knobs() {
         if (const char *e = getenv("MGFEA_TH")) th = atoi(e);
         if (const char *e = getenv("MGFEA_STAGES")) stages = atoi(e);
         if (const char *e = getenv("MGFEA_CTAS")) ctas = atoi(e);
         if (const char *e = getenv("MGFEA_STREAM_MIN_N")) stream_min_n = atoi(e);
         if (const char *e = getenv("MGFEA_STREAM_R")) stream_r = atoi(e);
+        if (const char *e = getenv("MGFEA_STREAM_PACKED")) stream_packed = atoi(e);
         if (const char *e = getenv("MGFEA_THREADS")) threads = atoi(e);
         threads = 256;
         if (th < 8 || th > 64 || (th & 1)) th = 32;
@@ -774,15 +776,23 @@ static int run_stream(const Program &pr, cudaStream_t st) {
         cudaFuncSetAttribute(mg_stream_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(mg_stream_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(mg_stream_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(mg_stream2_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(mg_stream2_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(mg_stream2_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
+    const bool pk = knobs().stream_packed != 0;
     if (mode == 0) {
-        if (pr.u_in)
-            mg_stream_kernel<0, false><<<grid, ST_WARPS * 32, smem, st>>>(p);
-        else
-            mg_stream_kernel<0, true><<<grid, ST_WARPS * 32, smem, st>>>(p);
+        if (pr.u_in) {
+            if (pk) mg_stream2_kernel<0, false><<<grid, ST_WARPS * 32, smem, st>>>(p);
+            else mg_stream_kernel<0, false><<<grid, ST_WARPS * 32, smem, st>>>(p);
+        } else {
+            if (pk) mg_stream2_kernel<0, true><<<grid, ST_WARPS * 32, smem, st>>>(p);
+            else mg_stream_kernel<0, true><<<grid, ST_WARPS * 32, smem, st>>>(p);
+        }
     } else {
-        mg_stream_kernel<1, false><<<grid, ST_WARPS * 32, smem, st>>>(p);
+        if (pk) mg_stream2_kernel<1, false><<<grid, ST_WARPS * 32, smem, st>>>(p);
+        else mg_stream_kernel<1, false><<<grid, ST_WARPS * 32, smem, st>>>(p);
     }
     g_launches.fetch_add(1);
     return (int)cudaGetLastError();

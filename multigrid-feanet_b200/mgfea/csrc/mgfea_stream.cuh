@@ -21,7 +21,7 @@
 namespace mgfea {
 
 constexpr int ST_WARPS = 8;    // warps per CTA
-constexpr int ST_DEPTH = 6;    // prefetch ring depth (rows)
+constexpr int ST_DEPTH = 8;    // prefetch ring depth (rows); the packed kernel keeps rows k-2..k for f re-reads
 constexpr int ST_TWI = BW - 8; // interior columns per strip (HX = 4)
 constexpr int ST_RING_F4 = 2 * ST_DEPTH + ST_DEPTH / 2;  // float4 units per lane: u ring, f ring, coarse float2 ring
 
@@ -98,6 +98,74 @@ __device__ __forceinline__ float4 mask4(float4 v, unsigned int m) {
     v.z = (m & 4u) ? v.z : 0.0f;
     v.w = (m & 8u) ? v.w : 0.0f;
     return v;
+}
+
+
+// ---- packed fp32x2 helpers (Blackwell FFMA2 / FADD2 / FMUL2): IEEE round-to-nearest per lane, like the scalar ops
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+    u64 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+struct RP {
+    u64 q[5];  // q[i] = (a[i], a[i+1]) for the 6 values a[0..5] = box columns 4l-1 .. 4l+4
+};
+__device__ __forceinline__ RP widen2(float a1, float a2, float a3, float a4) {
+    const float a0 = __shfl_up_sync(0xffffffffu, a4, 1);
+    const float a5 = __shfl_down_sync(0xffffffffu, a1, 1);
+    RP o;
+    o.q[0] = pack2(a0, a1);
+    o.q[1] = pack2(a1, a2);
+    o.q[2] = pack2(a2, a3);
+    o.q[3] = pack2(a3, a4);
+    o.q[4] = pack2(a4, a5);
+    return o;
+}
+// (e0,e1) -> lo, (e2,e3) -> hi; per lane the same row-major FMA chain as stencil_rows
+__device__ __forceinline__ void stencil_rows2(const u64 (&w)[9], const RP &t, const RP &m, const RP &b, u64 &lo,
+                                              u64 &hi) {
+    lo = mul2(w[0], t.q[0]);
+    hi = mul2(w[0], t.q[2]);
+    lo = fma2(w[1], t.q[1], lo);
+    hi = fma2(w[1], t.q[3], hi);
+    lo = fma2(w[2], t.q[2], lo);
+    hi = fma2(w[2], t.q[4], hi);
+    lo = fma2(w[3], m.q[0], lo);
+    hi = fma2(w[3], m.q[2], hi);
+    lo = fma2(w[4], m.q[1], lo);
+    hi = fma2(w[4], m.q[3], hi);
+    lo = fma2(w[5], m.q[2], lo);
+    hi = fma2(w[5], m.q[4], hi);
+    lo = fma2(w[6], b.q[0], lo);
+    hi = fma2(w[6], b.q[2], hi);
+    lo = fma2(w[7], b.q[1], lo);
+    hi = fma2(w[7], b.q[3], hi);
+    lo = fma2(w[8], b.q[2], lo);
+    hi = fma2(w[8], b.q[4], hi);
 }
 
 // MODE 0: down leg (Jacobi sweep, store u, residual, restriction -> fc)
@@ -301,6 +369,337 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream_kernel(const Strea
                         r.y = __fsub_rn(f2.y, ku2.y);
                         r.z = __fsub_rn(f2.z, ku2.z);
                         r.w = __fsub_rn(f2.w, ku2.w);
+                        if (MODE == 1) {
+                            if (p.want_norm && lane_int && (!GUARD || (yr >= y0 && yr < y1)) &&
+                                (!EDGE || (yr >= 1 && yr <= N - 2))) {
+                                const float4 q = EDGE ? mask4(r, cin) : r;
+                                part += (double)q.x * (double)q.x + (double)q.y * (double)q.y;
+                                part += (double)q.z * (double)q.z + (double)q.w * (double)q.w;
+                            }
+                        } else {
+                            R6 rr;
+                            rr.a[0] = __shfl_up_sync(0xffffffffu, r.w, 1);
+                            rr.a[1] = r.x;
+                            rr.a[2] = r.y;
+                            rr.a[3] = r.z;
+                            rr.a[4] = r.w;
+                            rr.a[5] = 0.0f;
+                            C[(ph + 2) % 3] = rr;
+                            // ---- coarse row (a-3)/2 when a-3 is even (k even since y0 is even)
+                            if ((ph & 1) == 0 && (!GUARD || k >= 6)) {
+                                const int yc = a - 3;
+                                if (!GUARD || (yc >= y0 && yc < y1)) {
+                                    const R6 &ct = C[(ph + 0) % 3], &cm = C[(ph + 1) % 3], &cb = C[(ph + 2) % 3];
+                                    float o2[2];
+#pragma unroll
+                                    for (int h = 0; h < 2; ++h) {
+                                        const int e = 2 * h;
+                                        float sacc = __fmul_rn(rw[0], ct.a[e]);
+                                        sacc = __fmaf_rn(rw[1], ct.a[e + 1], sacc);
+                                        sacc = __fmaf_rn(rw[2], ct.a[e + 2], sacc);
+                                        sacc = __fmaf_rn(rw[3], cm.a[e], sacc);
+                                        sacc = __fmaf_rn(rw[4], cm.a[e + 1], sacc);
+                                        sacc = __fmaf_rn(rw[5], cm.a[e + 2], sacc);
+                                        sacc = __fmaf_rn(rw[6], cb.a[e], sacc);
+                                        sacc = __fmaf_rn(rw[7], cb.a[e + 1], sacc);
+                                        sacc = __fmaf_rn(rw[8], cb.a[e + 2], sacc);
+                                        o2[h] = p.r_has_scale ? __fmul_rn(rscale, sacc) : sacc;
+                                    }
+                                    const int I = yc >> 1;
+                                    if (EDGE) {
+                                        const bool Iin = (I >= 1 && I <= p.Nc - 2);
+                                        o2[0] = (Iin && cxl >= 1 && cxl <= p.Nc - 2) ? o2[0] : 0.0f;
+                                        o2[1] = (Iin && cxl + 1 >= 1 && cxl + 1 <= p.Nc - 2) ? o2[1] : 0.0f;
+                                    }
+                                    if (fc_ok)
+                                        *reinterpret_cast<float2 *>(fco + (long long)I * p.pitch_c) =
+                                            make_float2(o2[0], o2[1]);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        };
+        using T_ = std::true_type;
+        using F_ = std::false_type;
+        // steady state: k0 >= 6 (pipeline full, all store rows >= y0) and k0 + 5 <= K - 4 (all store rows < y1)
+        int k0 = 0;
+        if (edge) {
+            for (; k0 < K; k0 += 6) block6(T_{}, T_{}, k0);
+        } else {
+            block6(T_{}, F_{}, 0);
+            for (k0 = 6; k0 + 5 <= K - 4; k0 += 6) block6(F_{}, F_{}, k0);
+            for (; k0 < K; k0 += 6) block6(T_{}, F_{}, k0);
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (MODE == 1 && p.want_norm) {
+            part = warp_sum_d(part);
+            if (lane == 0) p.partials[s] = part;
+        }
+    }
+
+    // ---- deterministic final reduction of the per-strip partial sums by the last CTA to finish
+    if (MODE == 1 && p.want_norm) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int ticket = atomicAdd(p.counter, 1u);
+            lastflag = (ticket == gridDim.x - 1) ? 1 : 0;
+        }
+        __syncthreads();
+        if (lastflag) {
+            __threadfence();
+            Ctl *ctl = reinterpret_cast<Ctl *>(p.ctl);
+            double tot = 0.0, mx = 0.0;
+            for (int b = 0; b < p.B; ++b) {
+                double v = 0.0;
+                for (int i = threadIdx.x; i < p.nstrips; i += blockDim.x)
+                    v += __ldcg(p.partials + (long long)b * p.nstrips + i);
+                v = warp_sum_d(v);
+                __syncthreads();
+                if (lane == 0) red[warp] = v;
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    double sum = 0.0;
+                    for (int w = 0; w < ST_WARPS; ++w) sum += red[w];
+                    if (p.sumsq) p.sumsq[b] = sum;
+                    if (ctl && p.hist && ctl->cycle < ctl->max_cycles) p.hist[(long long)ctl->cycle * p.B + b] = sum;
+                    tot += sum;
+                    mx = sum > mx ? sum : mx;
+                }
+            }
+            if (threadIdx.x == 0) {
+                if (ctl) {
+                    const int cyc = ctl->cycle + 1;
+                    ctl->cycle = cyc;
+                    const double metric = (ctl->conv_rule == 1) ? mx : tot;
+                    bool done = false;
+                    if (ctl->eps2 >= 0.0 && cyc >= ctl->min_cycles && metric <= ctl->eps2) done = true;
+                    if (cyc >= ctl->max_cycles) done = true;
+                    if (!(metric == metric) || metric > 1.7e308) done = true;
+                    if (done) ctl->done = 1;
+                }
+                *p.counter = 0u;
+                __threadfence();
+            }
+        }
+    }
+}
+
+
+// Packed variant: the two stencil chains per row run on fma.rn.f32x2 (FFMA2): same IEEE result per lane, half the
+// issue slots.  Rows are kept as 5 overlapping column PAIRS q[i] = (a[i], a[i+1]).
+// MODE 0: down leg (Jacobi sweep, store u, residual, restriction -> fc)
+// MODE 1: up leg   (bilinear prolongation + correction, Jacobi sweep, store u, optional interior residual norm)
+template <int MODE, bool ZERO_INIT>
+__global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const StreamParams p) {
+    extern __shared__ __align__(16) unsigned char st_smem[];
+    __shared__ double red[ST_WARPS];
+    __shared__ int lastflag;
+    if (p.ctl != nullptr && ld_volatile_s32(&reinterpret_cast<const Ctl *>(p.ctl)->done) != 0) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int N = p.N;
+
+    // ---- weights in registers for the whole kernel
+    float kw[9], rw[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+        kw[q] = p.ktab[q];
+        rw[q] = (MODE == 0) ? p.rtab[q] : 0.0f;
+    }
+    const float inv = p.invd[0];
+    u64 kw2[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) kw2[q] = pack2(kw[q], kw[q]);
+    const u64 inv2 = pack2(inv, inv);
+    const float rscale = (MODE == 0 && p.r_has_scale) ? (p.r_scale_dev ? *p.r_scale_dev : p.r_scale) : 1.0f;
+
+    // ---- per-lane prefetch ring: [slot][lane] float4 for u and for f, float2 for the coarse row (up leg)
+    float4 *ring_u = reinterpret_cast<float4 *>(st_smem) + warp * (ST_RING_F4 * 32);
+    float4 *ring_f = ring_u + ST_DEPTH * 32;
+    float2 *ring_c = reinterpret_cast<float2 *>(ring_f + ST_DEPTH * 32);
+
+    const int total = p.nstrips * p.B;
+    for (int s = blockIdx.x * ST_WARPS + warp; s < total; s += gridDim.x * ST_WARPS) {
+        // strip coordinates
+        int b = 0, rem = s;
+        if (p.B > 1) {
+            b = __float2int_rz(__int2float_rn(s) * p.inv_nstrips);
+            int r0 = s - b * p.nstrips;
+            if (r0 < 0) {
+                --b;
+                r0 += p.nstrips;
+            } else if (r0 >= p.nstrips) {
+                ++b;
+                r0 -= p.nstrips;
+            }
+            rem = r0;
+        }
+        int ry = __float2int_rz(__int2float_rn(rem) * p.inv_ntx);
+        int tx = rem - ry * p.ntx;
+        if (tx < 0) {
+            --ry;
+            tx += p.ntx;
+        } else if (tx >= p.ntx) {
+            ++ry;
+            tx -= p.ntx;
+        }
+        const int y0 = ry * p.R;
+        const int y1 = (ry == p.nry - 1) ? N : y0 + p.R;  // exclusive
+        const int gx = tx * ST_TWI - 4 + 4 * lane;         // first global column of this lane
+        const bool lane_int = (lane >= 1 && lane <= 30);
+        // column masks of this lane's 4 columns
+        unsigned int cin = 0, cdom = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (gx + e >= 1 && gx + e <= N - 2) cin |= 1u << e;
+            if (gx + e >= 0 && gx + e <= N - 1) cdom |= 1u << e;
+        }
+        const bool col_ok = (gx >= 0) && (gx + 3 < p.pitch);  // the 16-byte chunk exists in memory
+        const float *ub = ZERO_INIT ? nullptr : p.u_in + (long long)b * p.plane + gx;
+        const float *fb = p.f + (long long)b * p.plane + gx;
+        float *uo = p.u_out + (long long)b * p.plane + gx;
+        const int cxl = gx >> 1;  // coarse column of this lane's first fine column (gx is even)
+        const bool ccol_ok = (MODE == 1) && (cxl >= 0) && (cxl + 1 < p.pitch_c);
+        const float *cbp = (MODE == 1) ? p.vc + (long long)b * p.plane_c + cxl : nullptr;
+        float *fco = (MODE == 0) ? p.fc + (long long)b * p.plane_c + cxl : nullptr;
+        const bool fc_ok = lane_int && cxl >= 0 && cxl <= p.Nc - 1;
+        // a strip whose whole streamed box lies strictly inside the domain needs no masks at all
+        const bool edge = (y0 - 3 <= 0) || (y1 + 2 >= N - 1) || (tx == 0) || ((tx + 1) * ST_TWI + 4 >= N - 1);
+
+        const int a0 = y0 - 3;  // first streamed row
+        // last streamed row: y1+1 (u1 row y1 for the residual row y1-1); the last strip of the down leg goes one
+        // further so that the coarse ring row (N-1)/2 is produced (as zeros) too
+        const int K = ((MODE == 0 && y1 == N) ? y1 + 2 : y1 + 1) - a0 + 1;
+        auto prefetch = [&](int k) {
+            const int a = a0 + k;
+            const bool ok = col_ok && (a >= 0) && (a < N) && (k < K);
+            const long long off = ok ? (long long)a * p.pitch : 0;
+            const int slot = (k % ST_DEPTH) * 32 + lane;
+            if (!ZERO_INIT) st_cp16(&ring_u[slot], ok ? (const void *)(ub + off) : (const void *)p.f, ok);
+            st_cp16(&ring_f[slot], ok ? (const void *)(fb + off) : (const void *)p.f, ok);
+            if (MODE == 1) {  // coarse row ceil(a/2): the row an even fine row copies / an odd row's lower partner
+                const int I = (a + 1) >> 1;
+                const bool okc = ccol_ok && (I >= 0) && (I < p.Nc) && (k < K);
+                const void *src = okc ? (const void *)(cbp + (long long)I * p.pitch_c) : (const void *)p.f;
+                const uint32_t sz = okc ? 8u : 0u;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(&ring_c[slot])), "l"(src),
+                             "r"(sz)
+                             : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+#pragma unroll
+        for (int k = 0; k < ST_DEPTH - 3; ++k) prefetch(k);
+
+        // rotating windows (indices are compile-time after unrolling by 6)
+        RP A[3];   // input rows (u0, or corrected u for the up leg): a-2, a-1, a
+        RP Bw[3];  // smoothed rows: a-3, a-2, a-1
+        R6 C[3];   // residual rows (down leg): a-4, a-3, a-2
+        float vt[3] = {0.f, 0.f, 0.f};  // coarse row floor(a/2) at coarse columns cxl, cxl+1, cxl+2 (up leg)
+        double part = 0.0;
+        if (MODE == 1 && (a0 & 1) && a0 >= 1) {  // the strip starts on an odd row: fetch its upper coarse row directly
+            const float *row = p.vc + (long long)b * p.plane_c + (long long)(a0 >> 1) * p.pitch_c;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int c = cxl + q;
+                vt[q] = (c >= 0 && c < p.Nc) ? __ldg(row + c) : 0.0f;
+            }
+        }
+
+        // one block of 6 row steps.  GUARD: start-up / drain steps (pipeline fill, store ranges); EDGE: masks needed.
+        auto block6 = [&](auto guard_tag, auto edge_tag, int k0) {
+            constexpr bool GUARD = decltype(guard_tag)::value;
+            constexpr bool EDGE = decltype(edge_tag)::value;
+#pragma unroll
+            for (int ph = 0; ph < 6; ++ph) {
+                const int k = k0 + ph;
+                if (GUARD && k >= K) break;
+                const int a = a0 + k;
+                prefetch(k + ST_DEPTH - 3);  // rows k-2..k stay in the ring: f rows are re-read from it
+                asm volatile("cp.async.wait_group %0;" ::"n"(ST_DEPTH - 3) : "memory");
+                const int slot = (k % ST_DEPTH) * 32 + lane;
+                float4 uv = ZERO_INIT ? make_float4(0.f, 0.f, 0.f, 0.f) : ring_u[slot];
+                const bool arow_in = !EDGE || (a >= 1 && a <= N - 2);
+                if (MODE == 1) {
+                    // u += reset(bilinear P v_c) on row a
+                    const float2 cv = ring_c[slot];
+                    const float c2 = __shfl_down_sync(0xffffffffu, cv.x, 1);
+                    if (!EDGE || (a >= 0 && a <= N - 1)) {
+                        float4 e;
+                        if ((ph & 1) != 0) {  // k odd <=> a even (a0 is odd): copy / horizontal average of coarse row a/2
+                            vt[0] = cv.x;
+                            vt[1] = cv.y;
+                            vt[2] = c2;
+                            e.x = vt[0];
+                            e.y = __fadd_rn(__fmul_rn(0.5f, vt[0]), __fmul_rn(0.5f, vt[1]));
+                            e.z = vt[1];
+                            e.w = __fadd_rn(__fmul_rn(0.5f, vt[1]), __fmul_rn(0.5f, vt[2]));
+                        } else {  // a odd: between coarse rows (a-1)/2 (vt, kept from the previous step) and (a+1)/2
+                            const float vb0 = cv.x, vb1 = cv.y, vb2 = c2;
+                            e.x = __fadd_rn(__fmul_rn(0.5f, vt[0]), __fmul_rn(0.5f, vb0));
+                            e.z = __fadd_rn(__fmul_rn(0.5f, vt[1]), __fmul_rn(0.5f, vb1));
+                            if (p.prolong_seq) {
+                                float v = __fadd_rn(__fmul_rn(0.25f, vt[0]), __fmul_rn(0.25f, vt[1]));
+                                v = __fadd_rn(v, __fmul_rn(0.25f, vb0));
+                                e.y = __fadd_rn(v, __fmul_rn(0.25f, vb1));
+                                v = __fadd_rn(__fmul_rn(0.25f, vt[1]), __fmul_rn(0.25f, vt[2]));
+                                v = __fadd_rn(v, __fmul_rn(0.25f, vb1));
+                                e.w = __fadd_rn(v, __fmul_rn(0.25f, vb2));
+                            } else {
+                                const float ta = __fadd_rn(__fmul_rn(0.5f, vt[0]), __fmul_rn(0.5f, vt[1]));
+                                const float ba = __fadd_rn(__fmul_rn(0.5f, vb0), __fmul_rn(0.5f, vb1));
+                                e.y = __fadd_rn(__fmul_rn(0.5f, ta), __fmul_rn(0.5f, ba));
+                                const float tb = __fadd_rn(__fmul_rn(0.5f, vt[1]), __fmul_rn(0.5f, vt[2]));
+                                const float bb = __fadd_rn(__fmul_rn(0.5f, vb1), __fmul_rn(0.5f, vb2));
+                                e.w = __fadd_rn(__fmul_rn(0.5f, tb), __fmul_rn(0.5f, bb));
+                            }
+                        }
+                        if (EDGE) e = mask4(e, arow_in ? cin : 0u);  // fine level's reset_boundary of the correction
+                        uv.x = __fadd_rn(uv.x, e.x);
+                        uv.y = __fadd_rn(uv.y, e.y);
+                        uv.z = __fadd_rn(uv.z, e.z);
+                        uv.w = __fadd_rn(uv.w, e.w);
+                        if (EDGE) uv = mask4(uv, cdom);
+                    }
+                }
+                // reset_boundary of the sweep's input (ring -> 0, outside stays 0)
+                if (EDGE) uv = mask4(uv, arow_in ? cin : 0u);
+                A[(ph + 2) % 3] = widen2(uv.x, uv.y, uv.z, uv.w);
+                // ---- Jacobi row a-1
+                if (!GUARD || k >= 2) {
+                    const int y = a - 1;
+                    const RP &t = A[(ph + 0) % 3], &m = A[(ph + 1) % 3], &bq = A[(ph + 2) % 3];
+                    u64 klo, khi;
+                    stencil_rows2(kw2, t, m, bq, klo, khi);
+                    const ulonglong2 ff = *reinterpret_cast<const ulonglong2 *>(&ring_f[((k + ST_DEPTH - 1) % ST_DEPTH) * 32 + lane]);
+                    u64 olo = add2(mul2(inv2, sub2(ff.x, klo)), m.q[1]);
+                    u64 ohi = add2(mul2(inv2, sub2(ff.y, khi)), m.q[3]);
+                    float o0, o1, o2, o3;
+                    unpack2(olo, o0, o1);
+                    unpack2(ohi, o2, o3);
+                    if (EDGE) {
+                        const float4 om = mask4(make_float4(o0, o1, o2, o3), (y >= 1 && y <= N - 2) ? cin : 0u);
+                        o0 = om.x;
+                        o1 = om.y;
+                        o2 = om.z;
+                        o3 = om.w;
+                    }
+                    const bool st_ok = lane_int && (!GUARD || (y >= y0 && y < y1)) && (!EDGE || (cdom & 1u));
+                    if (st_ok) st_global_v4(uo + (long long)y * p.pitch, make_float4(o0, o1, o2, o3));
+                    Bw[(ph + 2) % 3] = widen2(o0, o1, o2, o3);
+                    // ---- residual row a-2
+                    if (!GUARD || k >= 4) {
+                        const int yr = a - 2;
+                        u64 rlo, rhi;
+                        stencil_rows2(kw2, Bw[(ph + 0) % 3], Bw[(ph + 1) % 3], Bw[(ph + 2) % 3], rlo, rhi);
+                        const ulonglong2 f2 = *reinterpret_cast<const ulonglong2 *>(&ring_f[((k + ST_DEPTH - 2) % ST_DEPTH) * 32 + lane]);
+                        rlo = sub2(f2.x, rlo);
+                        rhi = sub2(f2.y, rhi);
+                        float4 r;
+                        unpack2(rlo, r.x, r.y);
+                        unpack2(rhi, r.z, r.w);
                         if (MODE == 1) {
                             if (p.want_norm && lane_int && (!GUARD || (yr >= y0 && yr < y1)) &&
                                 (!EDGE || (yr >= 1 && yr <= N - 2))) {
