@@ -22,7 +22,7 @@ for p in (ROOT, os.path.join(ROOT, "multigrid-feanet_b200")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-METRIC = "V-cycles/s (4097^2 Poisson, V(1,1), fp32)"
+METRIC = "GDOF/s of V(1,1) cycles (= V-cycles/s x DOF; 4097^2 Poisson at N=1), fp32"
 
 
 def model_u0(n, seed=123):
@@ -127,17 +127,18 @@ def run_reference(args):
         dt = time.perf_counter() - t0
     val = steps_eff / dt
     dof = (n + 1) ** 2
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "V-cycles/s", "n_gpus": 0,
+    gd = val * (n + 1) ** 2 / 1e9
+    line = {"impl": "reference", "metric": METRIC, "value": gd, "unit": "GDOF/s", "v_cycles_per_s": val, "n_gpus": 0,
             "steps": steps_eff, "warmup": min(warm, 2), "ms_per_step": 1e3 * dt / steps_eff,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "gdof_per_s": val * dof / 1e9,
             "config": {"workload": f"iso Poisson {n + 1}x{n + 1}, V(1,1), {L} levels, single RHS, f=0 model problem",
                        "n": n, "levels": L, "nu": [1, 1], "batch": 1},
-            "cpu_baseline": {"value": val, "unit": "V-cycles/s", "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": gd, "unit": "GDOF/s", "v_cycles_per_s": val, "cores": cores, "kind": "port",
                              "sample": f"{steps_eff} V-cycles (+ residual norm each) of the same {n + 1}^2 problem; "
                                        "ATen call-for-call restatement of the reference CPU torch path "
                                        "(oracle/feanet_torch.py), torch threads = all host cores"},
-            "e2e": {"value": val, "unit": "V-cycles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": gd, "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
@@ -161,7 +162,7 @@ def cpu_baseline_sample(n, L, seconds=20.0):
             _ = torch.sqrt(torch.sum(r[:, :, 1:-1, 1:-1] ** 2)).item()
             k += 1
         dt = time.perf_counter() - t0
-    return {"value": k / dt, "unit": "V-cycles/s", "cores": cores, "kind": "port",
+    return {"value": k / dt * (n + 1) ** 2 / 1e9, "unit": "GDOF/s", "v_cycles_per_s": k / dt, "cores": cores, "kind": "port",
             "sample": f"{k} V-cycles (+ residual norm) at {n + 1}^2 after 1 warm-up, torch CPU threads={cores}; "
                       "ATen call-for-call restatement of the reference (oracle/feanet_torch.py)"}
 
@@ -345,10 +346,10 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     cpu = cpu_baseline_sample(n, L) if (world == 1 and not args.no_cpu_baseline) else None
-    line = {"metric": METRIC, "value": cycles_per_s, "unit": "V-cycles/s", "n_gpus": world, "steps": steps,
+    line = {"metric": METRIC, "value": cycles_per_s * dof / 1e9, "unit": "GDOF/s", "n_gpus": world, "steps": steps,
             "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "gdof_per_s": cycles_per_s * dof / 1e9,
+            "v_cycles_per_s": cycles_per_s,
             "time_to_1e-8_rel_ms": 1e3 * t_tol, "cycles_to_1e-8_rel": len(hist),
             "config": {"workload": f"iso Poisson {N}x{N}, V(1,1), {L} levels, single RHS per GPU, f=0 model problem "
                                    "(MM_Model_convergence.ipynb cell 3), residual norm fused in every cycle",
@@ -356,7 +357,8 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (level-0 u, u', f = 201 MB > 126 MB); no explicit flush",
                        "replicas": world, "loader": "tma" if args.loader == "tma" else "cp.async"},
             "clocks": clocks,
-            "e2e": {"value": e2e_val, "unit": "V-cycles/s", "h2d_bytes_per_step": int(2 * 4 * dof / args.e2e_cycles),
+            "e2e": {"value": e2e_val * dof / 1e9, "unit": "GDOF/s", "v_cycles_per_s": e2e_val,
+                    "h2d_bytes_per_step": int(2 * 4 * dof / args.e2e_cycles),
                     "d2h_bytes_per_step": int((4 * dof + 8 * args.e2e_cycles) / args.e2e_cycles),
                     "what": f"Multigrid.Solve(n_iter={args.e2e_cycles}) from pinned host u0,f: H2D of both fields, "
                             f"{args.e2e_cycles} cycles, D2H of the residual history and of the solution; "
@@ -370,6 +372,140 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_multi(args):
+    """N > 1: ONE problem partitioned into row slabs (FEANet.distributed): NCCL halo exchange, replicated coarse levels"""
+    import ctypes
+
+    import torch
+    import torch.distributed as dist
+
+    import mgfea
+    from FEANet.distributed import SlabMultigrid
+
+    world = int(os.environ["WORLD_SIZE"])
+    rank = int(os.environ["RANK"])
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = args.n_multi or {2: 8192, 4: 8192, 8: 16384}.get(world, 8192)
+    N = n + 1
+    dof = N * N
+    L = int(np.log2(n))
+    steps, warm = args.steps, max(args.warmup, 3)
+    mg = SlabMultigrid(n)
+    lev = mg.part.levels[0]
+
+    def u_rows(row0, nrows, NN):  # same random family as the reference's model problem, generated per rank on the device
+        g = torch.Generator(device="cuda").manual_seed(123 + rank)
+        return (1.2e5 * torch.rand((nrows, NN), generator=g, device="cuda") + 1.3e5)
+
+    mg.fill_local(u_rows)
+    from FEANet.distributed import halo_exchange
+
+    halo_exchange(mg.u[0], lev, mg.rank, mg.world)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_end = time.time() + 1.0
+    while time.time() < t_end:
+        mg.cycle()
+    for _ in range(warm):
+        mg.cycle()
+    barrier()
+    c0 = mgfea.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        ss = mg.cycle()
+    ev1.record()
+    barrier()
+    launches = mgfea.launch_count() - c0
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    t_end = time.time() + 0.3
+    while time.time() < t_end:
+        mg.cycle()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    cycles_per_s = steps / (ms * 1e-3)
+
+    # dominant kernel on this rank: level-0 slab down leg
+    peak, peak_src = hbm_peak()
+    ops = mg.ops
+    reps = 20
+
+    def down():
+        ops.down(0, mg.u[0], mg.u_alt[0], mg.f[0], mg.f[1] if mg.part.ld > 1 else ops.coarse_f())
+
+    for _ in range(3):
+        down()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        down()
+    b.record()
+    torch.cuda.synchronize()
+    kms = a.elapsed_time(b) / reps
+    mloc = (lev["own1"] - lev["own0"]) * N
+    kalg = 4 * (5 * mloc + mloc // 4)
+    ach = kalg / (kms * 1e-3) / 1e9
+    balg = algorithmic_bytes_per_cycle(n, L)
+
+    # end to end: local rows from pinned host memory, 13 cycles with the per-cycle residual all-reduce, D2H of owned rows
+    hu = torch.empty((lev["nrows"], N), dtype=torch.float32).pin_memory()
+    hu.copy_(mg.u[0][0, :, :N])
+    hf = torch.zeros((lev["nrows"], N), dtype=torch.float32).pin_memory()
+    hout = torch.empty((lev["own1"] - lev["own0"], N), dtype=torch.float32).pin_memory()
+
+    def e2e_once():
+        mg.u[0][0, :, :N].copy_(hu, non_blocking=True)
+        mg.f[0][0, :, :N].copy_(hf, non_blocking=True)
+        hist = mg.Solve(n_iter=args.e2e_cycles)
+        hout.copy_(mg.u[0][0, lev["own0"] - lev["row0"]: lev["own1"] - lev["row0"], :N], non_blocking=True)
+        torch.cuda.synchronize()
+        return hist
+
+    e2e_once()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        e2e_once()
+    barrier()
+    e2e_dt = (time.perf_counter() - t0) / 2
+    te = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_dt = float(te.item())
+    if rank == 0:
+        line = {"metric": METRIC, "value": cycles_per_s * dof / 1e9, "unit": "GDOF/s", "n_gpus": world, "steps": steps,
+                "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "v_cycles_per_s": cycles_per_s,
+                "config": {"workload": f"iso Poisson {N}x{N}, V(1,1), {L} levels, single RHS partitioned into {world} "
+                                       f"row slabs (NCCL halo exchange, levels N<2049 replicated), f=0 model problem; "
+                                       f"{dof / world / 1e6:.1f} MDOF per GPU (N=1 runs 16.8 MDOF)",
+                           "n": n, "levels": L, "nu": [1, 1], "batch": 1, "first_replicated_level": mg.part.ld,
+                           "l2": "inputs larger than L2 per GPU at level 0; no explicit flush"},
+                "clocks": clocks,
+                "e2e": {"value": args.e2e_cycles * dof / e2e_dt / 1e9, "unit": "GDOF/s",
+                        "h2d_bytes_per_step": int(2 * 4 * dof / args.e2e_cycles),
+                        "d2h_bytes_per_step": int(4 * dof / args.e2e_cycles),
+                        "what": f"SlabMultigrid.Solve(n_iter={args.e2e_cycles}) from pinned host slabs on every rank, "
+                                "D2H of the owned rows; bytes are whole-job per V-cycle", "ms_per_solve": 1e3 * e2e_dt},
+                "gpu_launches": int(launches), "gpu_launches_per_step": int(launches // steps),
+                "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                             "traffic": None, "kernel": "mg_stream2_kernel<down> level-0 slab (rank 0)",
+                             "kernel_ms": kms, "algorithmic_bytes_per_launch": kalg, "peak_source": peak_src,
+                             "cycle": {"algorithmic_bytes": balg, "ms": ms / steps,
+                                       "achieved": balg / (ms / steps * 1e-3) / 1e9,
+                                       "frac": balg / (ms / steps * 1e-3) / 1e9 / (peak * world)}}}
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -380,6 +516,7 @@ def main():
     ap.add_argument("--e2e-cycles", type=int, default=13)
     ap.add_argument("--loader", default="tma", choices=["tma", "cpasync"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--n-multi", type=int, default=0, help="grid intervals for the row-slab run at N > 1 (default by N)")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps == 200:
@@ -389,7 +526,12 @@ def main():
     import mgfea
 
     mgfea.set_loader(args.loader == "tma")
-    run_ours(args)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        if args.steps == 200:
+            args.steps = 50
+        run_multi(args)
+    else:
+        run_ours(args)
 
 
 if __name__ == "__main__":

@@ -132,6 +132,30 @@ int mgfea_prolong_correct_smooth(const mgfea_grid *g, const mgfea_grid *gc, cons
 int mgfea_residual_norm(const mgfea_grid *g, const float *u, const float *f, double *sumsq, mgfea_ctl *ctl,
                         double *hist, int B, void *stream);
 
+/* ---- row-slab partition (multi-GPU) ------------------------------------------------------------------- */
+/* Fine levels are split into contiguous row slabs, one per GPU.  A rank's arrays hold the global
+ * rows [row0, row0+nrows) of the N x N level: its owned rows [own0, own1) plus ghost rows that the caller fills by halo
+ * exchange (>= 3 above / below the owned range for the fused legs).  own0 must be even, so that fine row 2I and coarse
+ * row I live on the same rank.  Single-pattern grids with the default Dirichlet ring only (streaming kernels). */
+typedef struct mgfea_slab {
+    int32_t row0;   /* global row index of local row 0 */
+    int32_t nrows;  /* rows held locally (owned + ghost) */
+    int32_t own0;   /* first owned global row */
+    int32_t own1;   /* one past the last owned global row */
+} mgfea_slab;
+/* down leg on a slab: one Jacobi sweep (u_in == NULL: zero guess), u_out (owned rows), fc = scale*R(f - K u_out) on the
+ * owned coarse rows [own0/2, own1/2) of the coarse slab `sc` (only sc->row0 / sc->nrows are used) */
+int mgfea_slab_smooth_residual_restrict(const mgfea_grid *g, const mgfea_slab *s, const float *u_in, float *u_out,
+                                        const float *f, float *fc, const mgfea_slab *sc, int pitch_c, int64_t plane_c,
+                                        const float *rtab, int has_scale, float scale_host, const float *scale_dev,
+                                        int B, void *stream);
+/* up leg on a slab: u_out = smooth(u_in + reset(bilinear P vc)) on the owned rows; vc is the coarse slab `sc` (with
+ * ghost rows); if sumsq != NULL the interior residual sum of squares over the OWNED rows is written per sample (the
+ * caller all-reduces it) */
+int mgfea_slab_prolong_correct_smooth(const mgfea_grid *g, const mgfea_slab *s, const float *vc, const mgfea_slab *sc,
+                                      int pitch_c, int64_t plane_c, const float *u_in, float *u_out, const float *f,
+                                      double *sumsq, int B, void *stream);
+
 /* ---- whole V-cycle ----------------------------------------------------------------------------------- */
 typedef struct mgfea_cycle_cfg {
     int32_t nu1, nu2;      /* pre / post sweeps (coarsest level gets nu1 + nu2) */

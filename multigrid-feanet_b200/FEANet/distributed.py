@@ -1,0 +1,293 @@
+"""Row-slab multi-GPU V-cycle (the reference has no distributed code at all).
+
+One process per GPU (``torch.distributed``).  The fine levels (N >= ``dist_min_n``) are split into contiguous row slabs,
+boundaries aligned so that fine row 2I and coarse row I live on the same rank; every rank keeps its owned rows plus
+``GHOST`` ghost rows per side, refreshed by a nearest-neighbour exchange (NCCL send/recv over NVLink) after each kernel
+that changes them.  Levels below the threshold are agglomerated: the first replicated right-hand side is all-gathered
+and every rank runs the small coarse cycle redundantly (no scatter on the way up).  The interior residual norm is an
+all-reduce of one double per sample.
+
+The arithmetic is identical to the single-GPU cycle, so results are bit-identical for any number of ranks
+(tests/test_distributed_cpu.py checks that on CPU with gloo, using the oracle as the local operator;
+tests/test_gpu_parity.py::test_slab_* emulates the ranks on one GPU).
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+GHOST = 4  # ghost rows per side: the fused legs read 3 rows above / 2 below their owned range (streaming kernels)
+
+
+class SlabPartition:
+    """Host-side description of which global rows of every level a rank owns / holds."""
+
+    def __init__(self, n, L, world, rank, dist_min_n=2049):
+        self.n, self.L, self.world, self.rank = n, L, world, rank
+        self.levels = []
+        for l in range(L):
+            nl = n // (2 ** l)
+            N = nl + 1
+            distributed = (world > 1) and (N >= dist_min_n) and (nl % (2 * world) == 0) and (nl // world >= 2 * GHOST)
+            if l > 0 and not self.levels[-1]["dist"]:
+                distributed = False
+            if distributed:
+                per = nl // world
+                own0 = rank * per
+                own1 = (rank + 1) * per + (1 if rank == world - 1 else 0)
+                row0 = max(0, own0 - GHOST)
+                row1 = min(N, own1 + GHOST)
+            else:
+                own0, own1, row0, row1 = 0, N, 0, N
+            self.levels.append(dict(N=N, dist=distributed, own0=own0, own1=own1, row0=row0, nrows=row1 - row0))
+        self.ld = next((l for l, v in enumerate(self.levels) if not v["dist"]), L)  # first replicated level
+        if self.ld == L and world > 1:
+            raise ValueError("the coarsest levels must be replicated: lower dist_min_n or use fewer ranks")
+
+    def owned_rows(self, l, rank):
+        nl = self.n // (2 ** l)
+        per = nl // self.world
+        return rank * per, (rank + 1) * per + (1 if rank == self.world - 1 else 0)
+
+
+def _staged(t, group):
+    """gloo has no CUDA point-to-point / all-gather: stage through the host (used by the one-GPU emulation tests)"""
+    return t.is_cuda and dist.get_backend(group) == "gloo"
+
+
+def halo_exchange(arr, lev, rank, world, group=None):
+    """refresh the ghost rows of a local slab array (B=1: [1][nrows][pitch]) from the neighbouring ranks"""
+    if world == 1 or not lev["dist"]:
+        return
+    r0, own0, own1 = lev["row0"], lev["own0"], lev["own1"]
+    a = arr[0]
+    pairs = []  # (send view, recv view, peer)
+    if rank > 0:  # neighbour above (smaller row indices)
+        pairs.append((a[own0 - r0: own0 - r0 + GHOST], a[own0 - r0 - GHOST: own0 - r0], rank - 1))
+    if rank < world - 1:  # neighbour below
+        pairs.append((a[own1 - r0 - GHOST: own1 - r0], a[own1 - r0: own1 - r0 + GHOST], rank + 1))
+    stage = _staged(arr, group)
+    ops, bufs = [], []
+    for send, recv, peer in pairs:
+        sb = send.cpu() if stage else send
+        rb = torch.empty(recv.shape, dtype=recv.dtype) if stage else recv
+        bufs.append((recv, rb))
+        ops += [dist.P2POp(dist.isend, sb, peer, group), dist.P2POp(dist.irecv, rb, peer, group)]
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+    if stage:
+        for recv, rb in bufs:
+            recv.copy_(rb)
+
+
+class CudaSlabOps:
+    """local operators on the GPU: the slab forms of the streaming kernels + the replicated coarse engine"""
+
+    def __init__(self, part, nu1=1, nu2=1):
+        import mgfea
+        from .jacobi import JacobiBlock
+        from .mesh import MeshSquare
+        from .model import KNet
+        from .solver import FULL_WEIGHTING_16, VCycleEngine
+
+        if (nu1, nu2) != (1, 1):
+            raise mgfea.MgfeaError("the row-slab path implements V(1,1)")
+        self.mg = mgfea
+        self.part = part
+        self.dev = mgfea.require_cuda()
+        n, L = part.n, part.L
+        self.jacs = []
+        for l in range(L):  # light-weight levels: no full-size host tensors (a 16385^2 mask alone is 1 GB)
+            mesh = MeshSquare(2, n // 2 ** l + 1)
+            self.jacs.append(JacobiBlock(KNet(mesh), mesh, 2 / 3., None, None))
+        self.rtab = torch.from_numpy(FULL_WEIGHTING_16.reshape(1, 9).copy()).to(self.dev)
+        self.coarse = VCycleEngine(self.jacs[part.ld:], B=1, nu1=nu1, nu2=nu2) if part.ld < L else None
+        self._sumsq = torch.zeros(1, dtype=torch.float64, device=self.dev)
+
+    def alloc(self, l):
+        lev = self.part.levels[l]
+        if l == self.part.ld and self.coarse is not None:
+            return None  # the replicated engine owns these buffers
+        return torch.zeros((1, lev["nrows"], self.mg.pitch_for(lev["N"])), dtype=torch.float32, device=self.dev)
+
+    def coarse_f(self):
+        return self.coarse.f[0].store
+
+    def coarse_u(self):
+        return self.coarse.u[0].store
+
+    def _grid(self, l, arr):
+        lev = self.part.levels[l]
+        fld = self.mg.Field(1, lev["N"], self.dev, store=arr)  # pitch / N carrier; plane = local rows * pitch
+        g = self.jacs[l].grid_struct(fld)
+        g.plane = arr.shape[1] * arr.shape[2]
+        return g
+
+    def _slab(self, l):
+        lev = self.part.levels[l]
+        return self.mg.Slab(lev["row0"], lev["nrows"], lev["own0"], lev["own1"])
+
+    def down(self, l, u_in, u_out, f, fc):
+        mg = self.mg
+        g = self._grid(l, u_out)
+        s, sc = self._slab(l), self._slab(l + 1)
+        mg.check(mg.lib().mgfea_slab_smooth_residual_restrict(
+            ctypes.byref(g), ctypes.byref(s), u_in.data_ptr() if u_in is not None else None, u_out.data_ptr(),
+            f.data_ptr(), fc.data_ptr(), ctypes.byref(sc), fc.shape[2], fc.shape[1] * fc.shape[2], self.rtab.data_ptr(),
+            1, 4.0, None, 1, mg.stream_ptr()))
+
+    def up(self, l, vc, u_in, u_out, f, want_norm):
+        mg = self.mg
+        g = self._grid(l, u_out)
+        s, sc = self._slab(l), self._slab(l + 1)
+        mg.check(mg.lib().mgfea_slab_prolong_correct_smooth(
+            ctypes.byref(g), ctypes.byref(s), vc.data_ptr(), ctypes.byref(sc), vc.shape[2], vc.shape[1] * vc.shape[2],
+            u_in.data_ptr(), u_out.data_ptr(), f.data_ptr(), self._sumsq.data_ptr() if want_norm else None, 1,
+            mg.stream_ptr()))
+        return self._sumsq if want_norm else None
+
+    def coarse_cycle(self):
+        """one V-cycle from a zero guess on the replicated levels; rhs / result live in the engine's level-0 buffers"""
+        self.coarse.u[0].store.zero_()
+        self.coarse.cycle()
+
+    def full_cycle_single(self, u, f):
+        raise NotImplementedError
+
+
+class SlabMultigrid:
+    """V(1,1) solver for the iso Poisson problem on row slabs.  `ops` supplies the local operators."""
+
+    def __init__(self, n, ops_factory=CudaSlabOps, L=None, dist_min_n=2049, group=None):
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.group = group
+        self.n = n
+        self.L = int(math.log2(n)) if L is None else L
+        self.part = SlabPartition(n, self.L, self.world, self.rank, dist_min_n)
+        self.ops = ops_factory(self.part)
+        ld = self.part.ld
+        self.u = [self.ops.alloc(l) for l in range(ld)]
+        self.u_alt = [self.ops.alloc(l) for l in range(ld)]
+        self.f = [self.ops.alloc(l) for l in range(ld)]
+        self.residuals = []
+
+    # ---- problem data: every rank takes its rows (owned + ghost) from the full host arrays
+    def set_problem(self, u0_full, f_full):
+        lev = self.part.levels[0]
+        N = lev["N"]
+        rows = slice(lev["row0"], lev["row0"] + lev["nrows"])
+        if self.part.ld == 0:  # everything replicated (tiny problems / single rank)
+            self.ops.coarse.set_u(u0_full)
+            self.ops.coarse.set_f(f_full)
+            return
+        for dst, src in ((self.u[0], u0_full), (self.f[0], f_full)):
+            src = torch.as_tensor(src, dtype=torch.float32).reshape(N, N)
+            dst[0, :, :N].copy_(src[rows], non_blocking=True)
+
+    def fill_local(self, fn_u, fn_f=None):
+        """set the problem from per-rank generators: fn(row0, nrows, N) -> (nrows, N) float32 tensor of the global rows
+        [row0, row0+nrows) (owned rows only need to be right: ghost rows are refreshed by the first halo exchange)"""
+        lev = self.part.levels[0]
+        N = lev["N"]
+        if self.part.ld == 0:
+            self.ops.coarse.set_u(fn_u(0, N, N))
+            self.ops.coarse.set_f(fn_f(0, N, N) if fn_f else torch.zeros(N, N))
+            return
+        self.u[0][0, :, :N].copy_(fn_u(lev["row0"], lev["nrows"], N))
+        if fn_f is not None:
+            self.f[0][0, :, :N].copy_(fn_f(lev["row0"], lev["nrows"], N))
+        else:
+            self.f[0].zero_()
+
+    def gather_solution(self):
+        """full level-0 solution on every rank (host tensor); for tests / result delivery"""
+        lev = self.part.levels[0]
+        N = lev["N"]
+        if self.part.ld == 0:
+            return self.ops.coarse.solution.cpu().reshape(N, N).clone()
+        own = self.u[0][0, lev["own0"] - lev["row0"]: lev["own1"] - lev["row0"], :N].contiguous()
+        if self.world == 1:
+            return own.cpu()
+        per = self.n // self.world
+        chunk = torch.zeros((per + 1, N), dtype=own.dtype)
+        chunk[: own.shape[0]] = own.cpu()
+        out = [torch.zeros_like(chunk) for _ in range(self.world)]
+        if dist.get_backend(self.group) == "nccl":
+            dev = own.device
+            outd = [o.to(dev) for o in out]
+            dist.all_gather(outd, chunk.to(dev), group=self.group)
+            out = [o.cpu() for o in outd]
+        else:
+            dist.all_gather(out, chunk, group=self.group)
+        full = torch.cat([o[:per] for o in out[:-1]] + [out[-1][: per + 1]], dim=0)
+        return full.cpu()
+
+    def _allgather_coarse_f(self):
+        """first replicated level: every rank wrote its owned coarse rows into the full array; make it complete"""
+        ld = self.part.ld
+        if self.world == 1:
+            return
+        fc = self.ops.coarse_f()  # [1][Nc][pitch]
+        nl = self.n // (2 ** ld)
+        per = nl // self.world
+        body = fc[0, :nl]  # the last row (ring) is zero on every rank
+        mine = body[self.rank * per:(self.rank + 1) * per]
+        if _staged(fc, self.group):
+            outs = [torch.empty(mine.shape, dtype=mine.dtype) for _ in range(self.world)]
+            dist.all_gather(outs, mine.cpu(), group=self.group)
+            for r, o in enumerate(outs):
+                body[r * per:(r + 1) * per].copy_(o)
+        else:
+            dist.all_gather_into_tensor(body.reshape(-1), mine.clone().reshape(-1), group=self.group) \
+                if fc.is_cuda else dist.all_gather([body[r * per:(r + 1) * per] for r in range(self.world)],
+                                                   mine.clone(), group=self.group)
+
+    def cycle(self, want_norm=True):
+        p, ops, ld = self.part, self.ops, self.part.ld
+        if ld == 0:
+            ops.coarse.cycle()
+            return ops.coarse.sumsq.clone()
+        # ---- down leg on the slabs
+        for l in range(ld):
+            fc = self.f[l + 1] if l + 1 < ld else ops.coarse_f()
+            ops.down(l, self.u[l] if l == 0 else None, self.u_alt[l], self.f[l], fc)
+            halo_exchange(self.u_alt[l], p.levels[l], self.rank, self.world, self.group)
+            if l + 1 < ld:
+                halo_exchange(self.f[l + 1], p.levels[l + 1], self.rank, self.world, self.group)
+        # ---- replicated coarse levels
+        self._allgather_coarse_f()
+        ops.coarse_cycle()
+        # ---- up leg
+        ss = None
+        for l in range(ld - 1, -1, -1):
+            vc = self.u[l + 1] if l + 1 < ld else ops.coarse_u()
+            ss = ops.up(l, vc, self.u_alt[l], self.u[l], self.f[l], want_norm and l == 0)
+            halo_exchange(self.u[l], p.levels[l], self.rank, self.world, self.group)
+        if want_norm:
+            tot = ss.clone()
+            if self.world > 1:
+                if _staged(tot, self.group):
+                    t = tot.cpu()
+                    dist.all_reduce(t, group=self.group)
+                    tot.copy_(t)
+                else:
+                    dist.all_reduce(tot, group=self.group)
+            return tot
+        return None
+
+    def Solve(self, n_iter=None, EPS=None, max_cycles=200):
+        """Multigrid.Solve semantics (MM_Model_convergence.ipynb cell 3): cycles while (res > EPS or n < n_iter)"""
+        if n_iter is None:
+            n_iter = 0
+        elif EPS is None:
+            EPS = math.inf
+        res, hist = 1.0, []
+        halo_exchange(self.u[0], self.part.levels[0], self.rank, self.world, self.group) if self.part.ld > 0 else None
+        while (res > EPS or len(hist) < n_iter) and len(hist) < max_cycles:
+            res = float(torch.sqrt(self.cycle().sum()).item())
+            hist.append(res)
+        self.residuals = hist
+        return hist

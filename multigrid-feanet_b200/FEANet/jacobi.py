@@ -34,14 +34,21 @@ class JacobiBlock():
     """
 
     def __init__(self, Knet, mesh, omega, geometry_idx, boundary_value):
-        self.nnode_edge = geometry_idx.shape[2]
-        self.geometry_idx = geometry_idx
-        self.boundary_value = boundary_value
+        if geometry_idx is None:
+            # internal light-weight form (FEANet.distributed at 8193^2 / 16385^2): default square ring with zero boundary
+            # values, mask tensors materialised only if somebody reads the attributes
+            self.nnode_edge = mesh.nnode_edge
+            self._geometry_idx = self._boundary_value = None
+            self._default_bc = True
+        else:
+            self.nnode_edge = geometry_idx.shape[2]
+            self._geometry_idx = geometry_idx
+            self._boundary_value = boundary_value
+            self._default_bc = _is_default_ring(geometry_idx, boundary_value)
         self.omega = omega
         self.mesh = mesh
         self.Knet = Knet
         self._d_mat = None
-        self._default_bc = _is_default_ring(geometry_idx, boundary_value)
         self._bc_fields = None
         # per-pattern omega/d exactly as torch evaluates `self.omega/self.d_mat` (jacobi.py:46): reciprocal, then
         # multiply by fl32(omega)
@@ -50,6 +57,29 @@ class JacobiBlock():
         self._diag = diag
         self._invd_np = ((np.float32(1.0) / diag).astype(np.float32) * np.float32(omega)).astype(np.float32)
         self._invd_dev = None
+
+    @property
+    def geometry_idx(self):
+        if self._geometry_idx is None:
+            from .geo import Geometry
+
+            g = Geometry(self.nnode_edge)
+            self._geometry_idx, self._boundary_value = g.geometry_idx, g.boundary_value
+        return self._geometry_idx
+
+    @geometry_idx.setter
+    def geometry_idx(self, v):
+        self._geometry_idx = v
+
+    @property
+    def boundary_value(self):
+        if self._boundary_value is None:
+            _ = self.geometry_idx
+        return self._boundary_value
+
+    @boundary_value.setter
+    def boundary_value(self, v):
+        self._boundary_value = v
 
     # -- reference attribute: (B or 1,1,N,N) Jacobi diagonal (jacobi.py:31-37); lazy, not used by the kernels
     @property

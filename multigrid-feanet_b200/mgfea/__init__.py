@@ -27,6 +27,7 @@ EXPORTS = [
     "mgfea_stiffness_apply", "mgfea_load_vector", "mgfea_split_x", "mgfea_reset_boundary", "mgfea_smooth",
     "mgfea_residual", "mgfea_restrict", "mgfea_smooth_residual_restrict", "mgfea_prolong_correct_smooth",
     "mgfea_residual_norm", "mgfea_vcycle", "mgfea_restrict_channels", "mgfea_prolong_channels",
+    "mgfea_slab_smooth_residual_restrict", "mgfea_slab_prolong_correct_smooth",
 ]
 
 
@@ -70,6 +71,10 @@ class CycleCfg(ctypes.Structure):
                 ("compute_norm", ctypes.c_int32)]
 
 
+class Slab(ctypes.Structure):
+    _fields_ = [("row0", ctypes.c_int32), ("nrows", ctypes.c_int32), ("own0", ctypes.c_int32), ("own1", ctypes.c_int32)]
+
+
 class LevelBufs(ctypes.Structure):
     _fields_ = [("u", ctypes.c_void_p), ("u_alt", ctypes.c_void_p), ("f", ctypes.c_void_p)]
 
@@ -108,6 +113,9 @@ def lib():
         L.mgfea_restrict_channels.argtypes = [vp, vp, vp, i32, i32, i32, vp]
         L.mgfea_prolong_channels.argtypes = [vp, vp, vp, i32, i32, i32, vp]
         L.mgfea_residual_norm.argtypes = [G, vp, vp, vp, vp, vp, i32, vp]
+        S = ctypes.POINTER(Slab)
+        L.mgfea_slab_smooth_residual_restrict.argtypes = [G, S, vp, vp, vp, vp, S, i32, i64, vp, i32, f32, vp, i32, vp]
+        L.mgfea_slab_prolong_correct_smooth.argtypes = [G, S, vp, S, i32, i64, vp, vp, vp, vp, i32, vp]
         L.mgfea_vcycle.argtypes = [ctypes.POINTER(Grid), ctypes.POINTER(LevelBufs), i32, ctypes.POINTER(CycleCfg), vp,
                                    vp, vp, i32, vp]
         _lib = L

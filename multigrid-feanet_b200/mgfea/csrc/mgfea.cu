@@ -641,6 +641,8 @@ struct Program {
     double *hist = nullptr;
     const float *ktab_override = nullptr;  // load_vector: single table instead of g->ktab
     int ignore_keys = 0;
+    // row-slab partition (mgfea_slab_*): local arrays hold global rows [row0, row0+nrloc); owned rows [own0, own1)
+    int slab = 0, row0 = 0, nrloc = 0, own0 = 0, own1 = 0, crow0 = 0, nrc = 0;
 };
 
 static inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
@@ -721,7 +723,8 @@ static int run_stream(const Program &pr, cudaStream_t st) {
     if (R <= 0) {
         if ((rc = get_scratch(1, &scr))) return rc;
         const double slots = (double)scr->num_sms * 2 * ST_WARPS;
-        R = (int)((double)(g->N - 1) * p.ntx * pr.B / slots + 0.5);
+        const int owned = pr.slab ? (pr.own1 - pr.own0) : (g->N - 1);
+        R = (int)((double)owned * p.ntx * pr.B / slots + 0.5);
         R = (R + 1) & ~1;
         int best = 8;
         for (int c = 8; c <= 256; c *= 2)  // powers of two divide N-1 = 2^k exactly
@@ -731,7 +734,26 @@ static int run_stream(const Program &pr, cudaStream_t st) {
     if (R < 8) R = 8;
     R &= ~1;
     p.R = R;
-    p.nry = (g->N - 1) / R;
+    p.Nc = (g->N - 1) / 2 + 1;
+    if (pr.slab) {
+        if (pr.own0 < 0 || pr.own1 > g->N || pr.own0 >= pr.own1 || (pr.own0 & 1) || pr.nrloc < 1) return MGFEA_EINVAL;
+        if (pr.own0 - pr.row0 < 0 || pr.own1 - pr.row0 > pr.nrloc) return MGFEA_EINVAL;
+        p.row0 = pr.row0;
+        p.nrloc = pr.nrloc;
+        p.own0 = pr.own0;
+        p.own1 = pr.own1;
+        p.crow0 = pr.crow0;
+        p.nrc = pr.nrc;
+        p.nry = (pr.own1 - pr.own0) / R;
+    } else {
+        p.row0 = 0;
+        p.nrloc = g->N;
+        p.own0 = 0;
+        p.own1 = g->N;
+        p.crow0 = 0;
+        p.nrc = p.Nc;
+        p.nry = (g->N - 1) / R;
+    }
     if (p.nry < 1) p.nry = 1;
     p.nstrips = p.ntx * p.nry;
     const long long total = (long long)p.nstrips * pr.B;
@@ -743,7 +765,6 @@ static int run_stream(const Program &pr, cudaStream_t st) {
     p.f = pr.f;
     p.ktab = g->ktab;
     p.invd = g->invd;
-    p.Nc = (g->N - 1) / 2 + 1;
     if (mode == 0) {
         p.fc = pr.fc;
         p.pitch_c = pr.pitch_c;
@@ -754,10 +775,10 @@ static int run_stream(const Program &pr, cudaStream_t st) {
         p.r_scale_dev = pr.r_scale_dev;
         if (!pr.fc || !pr.rtab || (pr.pitch_c & 1) || (reinterpret_cast<uintptr_t>(pr.fc) & 7u)) return MGFEA_EALIGN;
     } else {
-        if (!pr.gc || !pr.vc || pr.gc->N != p.Nc) return MGFEA_EINVAL;
+        if (!pr.vc || (!pr.slab && (!pr.gc || pr.gc->N != p.Nc))) return MGFEA_EINVAL;
         p.vc = pr.vc;
-        p.pitch_c = pr.gc->pitch;
-        p.plane_c = pr.gc->plane;
+        p.pitch_c = pr.slab ? pr.pitch_c : pr.gc->pitch;
+        p.plane_c = pr.slab ? pr.plane_c : pr.gc->plane;
         p.prolong_seq = (g->N <= 33);
         p.want_norm = (pr.out_mode == OUT_NORM);
     }
@@ -1396,6 +1417,69 @@ int mgfea_residual_norm(const mgfea_grid *g, const float *u, const float *f, dou
     pr.ctl = ctl;
     pr.hist = hist;
     return run_program(pr, (cudaStream_t)stream);
+}
+
+/* ---- row-slab (multi-GPU) forms of the two fused legs; see include/mgfea.h ------------------------------ */
+static int slab_common(Program &pr, const mgfea_grid *g, const mgfea_slab *s, const mgfea_slab *sc) {
+    if (!g || !s || !sc) return MGFEA_EINVAL;
+    if (g->keys || g->bc_idx || g->npat != 1) return MGFEA_EUNSUPPORTED;  // single-pattern, default Dirichlet ring
+    pr.g = g;
+    pr.slab = 1;
+    pr.row0 = s->row0;
+    pr.nrloc = s->nrows;
+    pr.own0 = s->own0;
+    pr.own1 = s->own1;
+    pr.crow0 = sc->row0;
+    pr.nrc = sc->nrows;
+    pr.smoother = MGFEA_SMOOTH_JACOBI;
+    pr.nsweeps = 1;
+    return 0;
+}
+
+int mgfea_slab_smooth_residual_restrict(const mgfea_grid *g, const mgfea_slab *s, const float *u_in, float *u_out,
+                                        const float *f, float *fc, const mgfea_slab *sc, int pitch_c, int64_t plane_c,
+                                        const float *rtab, int has_scale, float scale_host, const float *scale_dev,
+                                        int B, void *stream) {
+    Program pr;
+    int rc = slab_common(pr, g, s, sc);
+    if (rc) return rc;
+    if (!u_out || !f || !fc || !rtab || u_in == u_out) return MGFEA_EINVAL;
+    pr.B = B;
+    pr.u_in = u_in;
+    pr.u_out = u_out;
+    pr.f = f;
+    pr.out_mode = OUT_RESTRICT;
+    pr.fc = fc;
+    pr.pitch_c = pitch_c;
+    pr.plane_c = plane_c;
+    pr.rtab = rtab;
+    pr.rtab_n = 1;
+    pr.r_has_scale = has_scale;
+    pr.r_scale = scale_host;
+    pr.r_scale_dev = scale_dev;
+    if ((rc = check_field(u_out, g->pitch, g->plane)) || (rc = check_field(f, g->pitch, g->plane))) return rc;
+    return run_stream(pr, (cudaStream_t)stream);
+}
+
+int mgfea_slab_prolong_correct_smooth(const mgfea_grid *g, const mgfea_slab *s, const float *vc, const mgfea_slab *sc,
+                                      int pitch_c, int64_t plane_c, const float *u_in, float *u_out, const float *f,
+                                      double *sumsq, int B, void *stream) {
+    Program pr;
+    int rc = slab_common(pr, g, s, sc);
+    if (rc) return rc;
+    if (!u_in || !u_out || !f || !vc || u_in == u_out) return MGFEA_EINVAL;
+    pr.B = B;
+    pr.u_in = u_in;
+    pr.u_out = u_out;
+    pr.f = f;
+    pr.prolong_mode = MGFEA_PROLONG_BILINEAR;
+    pr.vc = vc;
+    pr.pitch_c = pitch_c;
+    pr.plane_c = plane_c;
+    pr.out_mode = sumsq ? OUT_NORM : OUT_NONE;
+    pr.sumsq = sumsq;
+    if ((rc = check_field(u_out, g->pitch, g->plane)) || (rc = check_field(f, g->pitch, g->plane))) return rc;
+    return run_stream(pr, (cudaStream_t)stream);
 }
 
 int mgfea_vcycle(const mgfea_grid *grids, const mgfea_level_bufs *bufs, int nlevels, const mgfea_cycle_cfg *cfg,

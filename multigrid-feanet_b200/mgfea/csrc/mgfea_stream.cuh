@@ -29,6 +29,10 @@ struct StreamParams {
     int N, B, pitch;
     long long plane;
     int R, ntx, nry, nstrips;  // rows per strip, strips per row of strips, strip rows, strips per sample
+    // row-slab partition (multi-GPU): the arrays hold local rows [row0, row0+nrloc) of the global N x N level (owned rows
+    // plus ghost rows filled by the halo exchange); this rank computes / stores the owned global rows [own0, own1).
+    // Coarse arrays hold global coarse rows [crow0, crow0+nrc).  Single GPU: row0=0, nrloc=N, own=[0,N), crow0=0, nrc=Nc.
+    int row0, nrloc, own0, own1, crow0, nrc;
     float inv_nstrips, inv_ntx;
     const float *u_in;   // NULL: zero initial guess (down leg of coarse levels)
     float *u_out;
@@ -219,8 +223,8 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream_kernel(const Strea
             ++ry;
             tx -= p.ntx;
         }
-        const int y0 = ry * p.R;
-        const int y1 = (ry == p.nry - 1) ? N : y0 + p.R;  // exclusive
+        const int y0 = p.own0 + ry * p.R;                       // global rows
+        const int y1 = (ry == p.nry - 1) ? p.own1 : y0 + p.R;  // exclusive
         const int gx = tx * ST_TWI - 4 + 4 * lane;         // first global column of this lane
         const bool lane_int = (lane >= 1 && lane <= 30);
         // column masks of this lane's 4 columns
@@ -248,15 +252,17 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream_kernel(const Strea
         const int K = ((MODE == 0 && y1 == N) ? y1 + 2 : y1 + 1) - a0 + 1;
         auto prefetch = [&](int k) {
             const int a = a0 + k;
-            const bool ok = col_ok && (a >= 0) && (a < N) && (k < K);
-            const long long off = ok ? (long long)a * p.pitch : 0;
+            const int la = a - p.row0;  // local row
+            const bool ok = col_ok && (a >= 0) && (a < N) && (la >= 0) && (la < p.nrloc) && (k < K);
+            const long long off = ok ? (long long)la * p.pitch : 0;
             const int slot = (k % ST_DEPTH) * 32 + lane;
             if (!ZERO_INIT) st_cp16(&ring_u[slot], ok ? (const void *)(ub + off) : (const void *)p.f, ok);
             st_cp16(&ring_f[slot], ok ? (const void *)(fb + off) : (const void *)p.f, ok);
             if (MODE == 1) {  // coarse row ceil(a/2): the row an even fine row copies / an odd row's lower partner
                 const int I = (a + 1) >> 1;
-                const bool okc = ccol_ok && (I >= 0) && (I < p.Nc) && (k < K);
-                const void *src = okc ? (const void *)(cbp + (long long)I * p.pitch_c) : (const void *)p.f;
+                const int lI = I - p.crow0;
+                const bool okc = ccol_ok && (I >= 0) && (I < p.Nc) && (lI >= 0) && (lI < p.nrc) && (k < K);
+                const void *src = okc ? (const void *)(cbp + (long long)lI * p.pitch_c) : (const void *)p.f;
                 const uint32_t sz = okc ? 8u : 0u;
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(&ring_c[slot])), "l"(src),
                              "r"(sz)
@@ -275,11 +281,12 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream_kernel(const Strea
         float vt[3] = {0.f, 0.f, 0.f};  // coarse row floor(a/2) at coarse columns cxl, cxl+1, cxl+2 (up leg)
         double part = 0.0;
         if (MODE == 1 && (a0 & 1) && a0 >= 1) {  // the strip starts on an odd row: fetch its upper coarse row directly
-            const float *row = p.vc + (long long)b * p.plane_c + (long long)(a0 >> 1) * p.pitch_c;
+            const int lI = (a0 >> 1) - p.crow0;
+            const float *row = p.vc + (long long)b * p.plane_c + (long long)lI * p.pitch_c;
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
                 const int c = cxl + q;
-                vt[q] = (c >= 0 && c < p.Nc) ? __ldg(row + c) : 0.0f;
+                vt[q] = (c >= 0 && c < p.Nc && lI >= 0 && lI < p.nrc) ? __ldg(row + c) : 0.0f;
             }
         }
 
@@ -357,7 +364,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream_kernel(const Strea
                     o.w = __fadd_rn(__fmul_rn(inv, __fsub_rn(ff.w, ku.w)), m.a[4]);
                     if (EDGE) o = mask4(o, (y >= 1 && y <= N - 2) ? cin : 0u);
                     const bool st_ok = lane_int && (!GUARD || (y >= y0 && y < y1)) && (!EDGE || (cdom & 1u));
-                    if (st_ok) st_global_v4(uo + (long long)y * p.pitch, o);
+                    if (st_ok) st_global_v4(uo + (long long)(y - p.row0) * p.pitch, o);
                     Bw[(ph + 2) % 3] = widen(o);
                     // ---- residual row a-2
                     if (!GUARD || k >= 4) {
@@ -412,7 +419,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream_kernel(const Strea
                                         o2[1] = (Iin && cxl + 1 >= 1 && cxl + 1 <= p.Nc - 2) ? o2[1] : 0.0f;
                                     }
                                     if (fc_ok)
-                                        *reinterpret_cast<float2 *>(fco + (long long)I * p.pitch_c) =
+                                        *reinterpret_cast<float2 *>(fco + (long long)(I - p.crow0) * p.pitch_c) =
                                             make_float2(o2[0], o2[1]);
                                 }
                             }
@@ -545,8 +552,8 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
             ++ry;
             tx -= p.ntx;
         }
-        const int y0 = ry * p.R;
-        const int y1 = (ry == p.nry - 1) ? N : y0 + p.R;  // exclusive
+        const int y0 = p.own0 + ry * p.R;                       // global rows
+        const int y1 = (ry == p.nry - 1) ? p.own1 : y0 + p.R;  // exclusive
         const int gx = tx * ST_TWI - 4 + 4 * lane;         // first global column of this lane
         const bool lane_int = (lane >= 1 && lane <= 30);
         // column masks of this lane's 4 columns
@@ -574,15 +581,17 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
         const int K = ((MODE == 0 && y1 == N) ? y1 + 2 : y1 + 1) - a0 + 1;
         auto prefetch = [&](int k) {
             const int a = a0 + k;
-            const bool ok = col_ok && (a >= 0) && (a < N) && (k < K);
-            const long long off = ok ? (long long)a * p.pitch : 0;
+            const int la = a - p.row0;  // local row
+            const bool ok = col_ok && (a >= 0) && (a < N) && (la >= 0) && (la < p.nrloc) && (k < K);
+            const long long off = ok ? (long long)la * p.pitch : 0;
             const int slot = (k % ST_DEPTH) * 32 + lane;
             if (!ZERO_INIT) st_cp16(&ring_u[slot], ok ? (const void *)(ub + off) : (const void *)p.f, ok);
             st_cp16(&ring_f[slot], ok ? (const void *)(fb + off) : (const void *)p.f, ok);
             if (MODE == 1) {  // coarse row ceil(a/2): the row an even fine row copies / an odd row's lower partner
                 const int I = (a + 1) >> 1;
-                const bool okc = ccol_ok && (I >= 0) && (I < p.Nc) && (k < K);
-                const void *src = okc ? (const void *)(cbp + (long long)I * p.pitch_c) : (const void *)p.f;
+                const int lI = I - p.crow0;
+                const bool okc = ccol_ok && (I >= 0) && (I < p.Nc) && (lI >= 0) && (lI < p.nrc) && (k < K);
+                const void *src = okc ? (const void *)(cbp + (long long)lI * p.pitch_c) : (const void *)p.f;
                 const uint32_t sz = okc ? 8u : 0u;
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(&ring_c[slot])), "l"(src),
                              "r"(sz)
@@ -600,11 +609,12 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
         float vt[3] = {0.f, 0.f, 0.f};  // coarse row floor(a/2) at coarse columns cxl, cxl+1, cxl+2 (up leg)
         double part = 0.0;
         if (MODE == 1 && (a0 & 1) && a0 >= 1) {  // the strip starts on an odd row: fetch its upper coarse row directly
-            const float *row = p.vc + (long long)b * p.plane_c + (long long)(a0 >> 1) * p.pitch_c;
+            const int lI = (a0 >> 1) - p.crow0;
+            const float *row = p.vc + (long long)b * p.plane_c + (long long)lI * p.pitch_c;
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
                 const int c = cxl + q;
-                vt[q] = (c >= 0 && c < p.Nc) ? __ldg(row + c) : 0.0f;
+                vt[q] = (c >= 0 && c < p.Nc && lI >= 0 && lI < p.nrc) ? __ldg(row + c) : 0.0f;
             }
         }
 
@@ -687,7 +697,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
                         o3 = om.w;
                     }
                     const bool st_ok = lane_int && (!GUARD || (y >= y0 && y < y1)) && (!EDGE || (cdom & 1u));
-                    if (st_ok) st_global_v4(uo + (long long)y * p.pitch, make_float4(o0, o1, o2, o3));
+                    if (st_ok) st_global_v4(uo + (long long)(y - p.row0) * p.pitch, make_float4(o0, o1, o2, o3));
                     Bw[(ph + 2) % 3] = widen2(o0, o1, o2, o3);
                     // ---- residual row a-2
                     if (!GUARD || k >= 4) {
@@ -743,7 +753,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
                                         o2[1] = (Iin && cxl + 1 >= 1 && cxl + 1 <= p.Nc - 2) ? o2[1] : 0.0f;
                                     }
                                     if (fc_ok)
-                                        *reinterpret_cast<float2 *>(fco + (long long)I * p.pitch_c) =
+                                        *reinterpret_cast<float2 *>(fco + (long long)(I - p.crow0) * p.pitch_c) =
                                             make_float2(o2[0], o2[1]);
                                 }
                             }

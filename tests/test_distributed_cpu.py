@@ -1,0 +1,137 @@
+"""Multi-rank logic of the row-slab V-cycle on CPU: world_size 2 (and 4) with the gloo backend, the ORACLE as the local
+operator.  Checks that partition + halo exchange + coarse agglomeration reproduce the single-process oracle bit for bit."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleSlabOps:
+    """local slab operators emulated with the oracle: embed the local rows (owned + ghost) in a zero full-size array,
+    apply the full-domain operator, keep the owned rows (valid because every operator has a 3-row dependency cone)"""
+
+    def __init__(self, part):
+        from oracle import oracle as O
+
+        self.O, self.part = O, part
+        self.levels = O.make_levels(part.n, part.L)
+        Nc = part.levels[part.ld]["N"] if part.ld < part.L else 0
+        self.fc_full = torch.zeros((1, Nc, Nc), dtype=torch.float32)
+        self.uc_full = torch.zeros((1, Nc, Nc), dtype=torch.float32)
+
+    def alloc(self, l):
+        lev = self.part.levels[l]
+        return torch.zeros((1, lev["nrows"], lev["N"]), dtype=torch.float32)
+
+    def coarse_f(self):
+        return self.fc_full
+
+    def coarse_u(self):
+        return self.uc_full
+
+    def _full(self, l, arr):
+        lev = self.part.levels[l]
+        full = np.zeros((1, lev["N"], lev["N"]), np.float32)
+        if arr is not None:
+            full[0, lev["row0"]:lev["row0"] + lev["nrows"]] = arr[0].numpy()
+        return full
+
+    def down(self, l, u_in, u_out, f, fc):
+        O, lv = self.O, self.levels[l]
+        lev, levc = self.part.levels[l], self.part.levels[l + 1]
+        ff = self._full(l, f)
+        u1 = O.jacobi(self._full(l, u_in), ff, lv.keys, lv.ktab, lv.invd)
+        fcg = O.restrict(O.residual(u1, ff, lv.keys, lv.ktab), None, O.FW16, 4.0)
+        o0, o1, r0 = lev["own0"], lev["own1"], lev["row0"]
+        u_out[0, o0 - r0:o1 - r0] = torch.from_numpy(u1[0, o0:o1])
+        c0, c1 = o0 // 2, (o1 + 1) // 2 if o1 == lev["N"] else o1 // 2
+        fc[0, c0 - levc["row0"]:c1 - levc["row0"]] = torch.from_numpy(fcg[0, c0:c1])
+
+    def up(self, l, vc, u_in, u_out, f, want_norm):
+        O, lv = self.O, self.levels[l]
+        lev = self.part.levels[l]
+        ff = self._full(l, f)
+        ucorr = O.prolong_bilinear(self._full(l + 1, vc), self._full(l, u_in))
+        u2 = O.jacobi(ucorr, ff, lv.keys, lv.ktab, lv.invd)
+        o0, o1, r0 = lev["own0"], lev["own1"], lev["row0"]
+        u_out[0, o0 - r0:o1 - r0] = torch.from_numpy(u2[0, o0:o1])
+        if not want_norm:
+            return None
+        r = O.residual(u2, ff, lv.keys, lv.ktab)[0]
+        rows = r[max(o0, 1):min(o1, lev["N"] - 1), 1:-1].astype(np.float64)
+        return torch.tensor([float((rows * rows).sum())], dtype=torch.float64)
+
+    def coarse_cycle(self):
+        O, ld = self.O, self.part.ld
+        u = O.vcycle(self.levels[ld:], O.CycleCfg(), np.zeros_like(self.fc_full.numpy()), self.fc_full.numpy())
+        self.uc_full.copy_(torch.from_numpy(u))
+
+
+def _worker(rank, world, n, dist_min_n, port, ret):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "multigrid-feanet_b200"), os.path.join(ROOT, "tests")]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from FEANet.distributed import SlabMultigrid
+        from test_distributed_cpu import OracleSlabOps as Ops
+
+        rs = np.random.RandomState(3)
+        u0 = rs.standard_normal((n + 1, n + 1)).astype(np.float32)
+        f = 0.01 * rs.standard_normal((n + 1, n + 1)).astype(np.float32)
+        mg = SlabMultigrid(n, ops_factory=Ops, dist_min_n=dist_min_n)
+        mg.set_problem(torch.from_numpy(u0), torch.from_numpy(f))
+        hist = mg.Solve(n_iter=3)
+        sol = mg.gather_solution()
+        if rank == 0:
+            ret["hist"], ret["sol"], ret["ld"] = hist, sol.numpy(), mg.part.ld
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,dist_min_n", [(2, 64, 17), (4, 128, 33), (2, 32, 33)])
+def test_row_slab_vcycle_matches_single_process(world, n, dist_min_n):
+    from oracle import oracle as O
+
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29500 + (os.getpid() % 2000) + world
+    mp.spawn(_worker, args=(world, n, dist_min_n, port, ret), nprocs=world, join=True)
+    rs = np.random.RandomState(3)
+    u0 = rs.standard_normal((n + 1, n + 1)).astype(np.float32)
+    f = 0.01 * rs.standard_normal((n + 1, n + 1)).astype(np.float32)
+    levels = O.make_levels(n)
+    u, hist = O.solve(levels, O.CycleCfg(), u0, f[None], n_iter=3)
+    assert ret["ld"] >= 1, "test must exercise distributed levels"
+    assert np.array_equal(ret["sol"], u[0]), "slab-partitioned V-cycle differs from the single-process cycle"
+    assert np.allclose(ret["hist"], hist, rtol=1e-12)
+
+
+def test_partition_properties():
+    sys.path[:0] = [os.path.join(ROOT, "multigrid-feanet_b200")]
+    from FEANet.distributed import GHOST, SlabPartition
+
+    for world in (2, 4, 8):
+        for n in (8192, 16384):
+            L = int(np.log2(n))
+            parts = [SlabPartition(n, L, world, r) for r in range(world)]
+            ld = parts[0].ld
+            assert 1 <= ld < L
+            for l in range(ld):
+                N = n // 2 ** l + 1
+                rows = []
+                for p in parts:
+                    lev = p.levels[l]
+                    assert lev["dist"] and lev["own0"] % 2 == 0
+                    assert lev["row0"] <= max(0, lev["own0"] - 3) and lev["row0"] + lev["nrows"] >= min(N, lev["own1"] + 3)
+                    rows += list(range(lev["own0"], lev["own1"]))
+                    if l + 1 < ld:  # fine row 2I and coarse row I on the same rank
+                        assert p.levels[l + 1]["own0"] * 2 == lev["own0"]
+                assert rows == list(range(N)), "owned rows must tile the level exactly once"
+            assert all(not p.levels[ld]["dist"] for p in parts)
+    assert GHOST >= 3
