@@ -408,26 +408,43 @@ def run_multi(args):
         dist.barrier()
         torch.cuda.synchronize()
 
+    graphed = mg.enable_graph() if not args.no_graph else False
+    gflag = torch.tensor([1.0 if graphed else 0.0], device="cuda")
+    dist.all_reduce(gflag, op=dist.ReduceOp.MIN)
+    if float(gflag.item()) < 0.5 and graphed:  # all ranks or none
+        mg._graph = None
+        graphed = False
     sampler = ClockSampler(local) if rank == 0 else None
-    t_end = time.time() + 1.0
-    while time.time() < t_end:
+    # every rank must issue the SAME sequence of collectives: agree on the number of load-phase cycles first
+    for _ in range(3):
+        mg.cycle()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        mg.cycle()
+    torch.cuda.synchronize()
+    tc = torch.tensor([(time.perf_counter() - t0) / 5], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+    n_load = int(max(5, min(2000, 1.0 / max(float(tc.item()), 1e-5))))
+    for _ in range(n_load):
         mg.cycle()
     for _ in range(warm):
         mg.cycle()
     barrier()
-    c0 = mgfea.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(steps):
         ss = mg.cycle()
     ev1.record()
     barrier()
-    launches = mgfea.launch_count() - c0
+    c0 = mgfea.launch_count()  # graph replays bypass the host-side counter: count one eager cycle on every rank
+    mg._cycle_eager()
+    barrier()
+    launches = (mgfea.launch_count() - c0) * steps
     t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    t_end = time.time() + 0.3
-    while time.time() < t_end:
+    for _ in range(max(5, n_load // 3)):
         mg.cycle()
     torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
@@ -488,6 +505,7 @@ def run_multi(args):
                                        f"row slabs (NCCL halo exchange, levels N<2049 replicated), f=0 model problem; "
                                        f"{dof / world / 1e6:.1f} MDOF per GPU (N=1 runs 16.8 MDOF)",
                            "n": n, "levels": L, "nu": [1, 1], "batch": 1, "first_replicated_level": mg.part.ld,
+                           "cuda_graph": bool(graphed), "graph_error": mg._graph_err,
                            "l2": "inputs larger than L2 per GPU at level 0; no explicit flush"},
                 "clocks": clocks,
                 "e2e": {"value": args.e2e_cycles * dof / e2e_dt / 1e9, "unit": "GDOF/s",
@@ -503,7 +521,14 @@ def run_multi(args):
                                        "achieved": balg / (ms / steps * 1e-3) / 1e9,
                                        "frac": balg / (ms / steps * 1e-3) / 1e9 / (peak * world)}}}
         print(json.dumps(line), flush=True)
-    dist.destroy_process_group()
+    # teardown: captured graphs reference the NCCL communicator; drop them first, then leave without running the
+    # process-group destructor (it can block on graph-captured communicators)
+    mg._graph = None
+    mg.ops.coarse._graph = None if mg.ops.coarse is not None else None
+    barrier()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def main():
@@ -516,6 +541,7 @@ def main():
     ap.add_argument("--e2e-cycles", type=int, default=13)
     ap.add_argument("--loader", default="tma", choices=["tma", "cpasync"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--n-multi", type=int, default=0, help="grid intervals for the row-slab run at N > 1 (default by N)")
     args = ap.parse_args()
     if args.impl == "reference":

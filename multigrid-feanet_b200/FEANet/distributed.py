@@ -173,6 +173,15 @@ class SlabMultigrid:
         self.u_alt = [self.ops.alloc(l) for l in range(ld)]
         self.f = [self.ops.alloc(l) for l in range(ld)]
         self.residuals = []
+        self._graph = None
+        self._graph_out = None
+        self._graph_err = None
+        # the exchange of the pre-smoothed u is only needed by the up leg of the same level: it runs on a side stream
+        # with its own communicator so that it overlaps the coarser levels instead of delaying the next restriction
+        self._side_group, self._side_stream = None, None
+        if self.world > 1 and torch.cuda.is_available() and dist.get_backend(group) == "nccl":
+            self._side_group = dist.new_group(ranks=list(range(self.world)), backend="nccl")
+            self._side_stream = torch.cuda.Stream()
 
     # ---- problem data: every rank takes its rows (owned + ghost) from the full host arrays
     def set_problem(self, u0_full, f_full):
@@ -245,16 +254,51 @@ class SlabMultigrid:
                 if fc.is_cuda else dist.all_gather([body[r * per:(r + 1) * per] for r in range(self.world)],
                                                    mine.clone(), group=self.group)
 
+    def enable_graph(self, warm=3):
+        """capture one whole cycle -- kernels AND the NCCL halo exchanges / all-gather / all-reduce -- in a CUDA graph
+        (removes ~25 host-side launches per cycle); falls back to eager launches if capture is not possible"""
+        if self._graph is not None or not torch.cuda.is_available():
+            return self._graph is not None
+        try:
+            for _ in range(warm):  # communicators, function attributes and scratch must exist before capture
+                self._cycle_eager()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._graph_out = self._cycle_eager()
+            self._graph = g
+        except Exception as e:  # noqa: BLE001
+            self._graph = None
+            self._graph_err = repr(e)
+            torch.cuda.synchronize()
+        return self._graph is not None
+
     def cycle(self, want_norm=True):
+        if self._graph is not None:
+            self._graph.replay()
+            return self._graph_out
+        return self._cycle_eager(want_norm)
+
+    def _cycle_eager(self, want_norm=True):
         p, ops, ld = self.part, self.ops, self.part.ld
         if ld == 0:
             ops.coarse.cycle()
             return ops.coarse.sumsq.clone()
         # ---- down leg on the slabs
+        side_done = [None] * ld
         for l in range(ld):
             fc = self.f[l + 1] if l + 1 < ld else ops.coarse_f()
             ops.down(l, self.u[l] if l == 0 else None, self.u_alt[l], self.f[l], fc)
-            halo_exchange(self.u_alt[l], p.levels[l], self.rank, self.world, self.group)
+            if self._side_stream is not None:
+                ev = torch.cuda.Event()
+                ev.record()
+                with torch.cuda.stream(self._side_stream):
+                    self._side_stream.wait_event(ev)
+                    halo_exchange(self.u_alt[l], p.levels[l], self.rank, self.world, self._side_group)
+                    side_done[l] = torch.cuda.Event()
+                    side_done[l].record()
+            else:
+                halo_exchange(self.u_alt[l], p.levels[l], self.rank, self.world, self.group)
             if l + 1 < ld:
                 halo_exchange(self.f[l + 1], p.levels[l + 1], self.rank, self.world, self.group)
         # ---- replicated coarse levels
@@ -264,6 +308,8 @@ class SlabMultigrid:
         ss = None
         for l in range(ld - 1, -1, -1):
             vc = self.u[l + 1] if l + 1 < ld else ops.coarse_u()
+            if side_done[l] is not None:
+                torch.cuda.current_stream().wait_event(side_done[l])
             ss = ops.up(l, vc, self.u_alt[l], self.u[l], self.f[l], want_norm and l == 0)
             halo_exchange(self.u[l], p.levels[l], self.rank, self.world, self.group)
         if want_norm:
