@@ -238,8 +238,7 @@ __global__ void __launch_bounds__(NTHREADS, MGFEA_MINBLOCKS) mg_tile_kernel(cons
     extern __shared__ __align__(1024) unsigned char smem[];
     Tables &T = *reinterpret_cast<Tables *>(smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    if (p.ctl != nullptr && ld_volatile_s32(&reinterpret_cast<const Ctl *>(p.ctl)->done) != 0) return;
+    pdl_launch_dependents();
 
     // ---- tables (live weights are read from device memory at every launch) and barriers
     for (int i = tid; i < MAXPAT * 9; i += NTHREADS) {
@@ -260,6 +259,8 @@ __global__ void __launch_bounds__(NTHREADS, MGFEA_MINBLOCKS) mg_tile_kernel(cons
             tma_prefetch_desc(&maps.f);
         }
     }
+    pdl_wait();  // from here on the previous kernel's global writes are visible (and its reads are finished)
+    if (p.ctl != nullptr && ld_volatile_s32(&reinterpret_cast<const Ctl *>(p.ctl)->done) != 0) return;
     __syncthreads();
 
     float *W1 = reinterpret_cast<float *>(smem + p.off_w1);
@@ -647,10 +648,35 @@ struct Program {
 
 static inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
 
+static int pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("MGFEA_PDL");
+        v = e ? (atoi(e) != 0) : 1;
+    }
+    return v;
+}
+// launch with the programmatic-stream-serialization attribute (PDL): see mgfea_ptx.cuh
+template <class K, class... Args>
+static cudaError_t launch_pdl(K kernel, int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled();
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 // tuning knobs (defaults chosen from the measurements in profiles/); overridable through the environment for sweeps
 struct Knobs {
     int th = 32, stages = 1, ctas = 0, threads = 256;
-    int stream_min_n = 2049;  // levels with N >= this use the register-chained streaming kernels (0 disables)
+    int stream_min_n = 129;   // levels with N >= this use the register-chained streaming kernels (0 disables)
     int stream_r = 0;         // rows per strip (0 = auto)
     int stream_packed = 1;    // 1: FFMA2 (fma.rn.f32x2) streaming kernels, 0: scalar FFMA
     Knobs() {
@@ -682,7 +708,8 @@ static cudaError_t launch_tile(const TileMaps &maps, const TileParams &p, int gr
         configured = 232448;
     }
     (void)threads;
-    mg_tile_kernel<KEYS, GBC><<<grid, NTHREADS, smem, st>>>(maps, p);
+    cudaError_t le = launch_pdl(mg_tile_kernel<KEYS, GBC>, grid, NTHREADS, smem, st, maps, p);
+    if (le != cudaSuccess) return le;
     g_launches.fetch_add(1);
     return cudaGetLastError();
 }
@@ -726,12 +753,12 @@ static int run_stream(const Program &pr, cudaStream_t st) {
         const int owned = pr.slab ? (pr.own1 - pr.own0) : (g->N - 1);
         R = (int)((double)owned * p.ntx * pr.B / slots + 0.5);
         R = (R + 1) & ~1;
-        int best = 8;
-        for (int c = 8; c <= 256; c *= 2)  // powers of two divide N-1 = 2^k exactly
+        int best = 2;
+        for (int c = 2; c <= 256; c *= 2)  // powers of two divide N-1 = 2^k exactly
             if (abs(c - R) < abs(best - R)) best = c;
         R = best;
     }
-    if (R < 8) R = 8;
+    if (R < 2) R = 2;
     R &= ~1;
     p.R = R;
     p.Nc = (g->N - 1) / 2 + 1;
@@ -805,15 +832,15 @@ static int run_stream(const Program &pr, cudaStream_t st) {
     const bool pk = knobs().stream_packed != 0;
     if (mode == 0) {
         if (pr.u_in) {
-            if (pk) mg_stream2_kernel<0, false><<<grid, ST_WARPS * 32, smem, st>>>(p);
-            else mg_stream_kernel<0, false><<<grid, ST_WARPS * 32, smem, st>>>(p);
+            if (pk) launch_pdl(mg_stream2_kernel<0, false>, grid, ST_WARPS * 32, smem, st, p);
+            else launch_pdl(mg_stream_kernel<0, false>, grid, ST_WARPS * 32, smem, st, p);
         } else {
-            if (pk) mg_stream2_kernel<0, true><<<grid, ST_WARPS * 32, smem, st>>>(p);
-            else mg_stream_kernel<0, true><<<grid, ST_WARPS * 32, smem, st>>>(p);
+            if (pk) launch_pdl(mg_stream2_kernel<0, true>, grid, ST_WARPS * 32, smem, st, p);
+            else launch_pdl(mg_stream_kernel<0, true>, grid, ST_WARPS * 32, smem, st, p);
         }
     } else {
-        if (pk) mg_stream2_kernel<1, false><<<grid, ST_WARPS * 32, smem, st>>>(p);
-        else mg_stream_kernel<1, false><<<grid, ST_WARPS * 32, smem, st>>>(p);
+        if (pk) launch_pdl(mg_stream2_kernel<1, false>, grid, ST_WARPS * 32, smem, st, p);
+        else launch_pdl(mg_stream_kernel<1, false>, grid, ST_WARPS * 32, smem, st, p);
     }
     g_launches.fetch_add(1);
     return (int)cudaGetLastError();
@@ -1168,14 +1195,14 @@ static int run_tail(const mgfea_grid *grids, const mgfea_level_bufs *bufs, int l
             if (e != cudaSuccess) return (int)e;
             configured[1] = true;
         }
-        mg_tail_kernel<true><<<B, TAIL_THREADS, bytes, st>>>(p);
+        launch_pdl(mg_tail_kernel<true>, B, TAIL_THREADS, (size_t)bytes, st, p);
     } else {
         if (!configured[0]) {
             e = cudaFuncSetAttribute(mg_tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 2048);
             if (e != cudaSuccess) return (int)e;
             configured[0] = true;
         }
-        mg_tail_kernel<false><<<B, TAIL_THREADS, bytes, st>>>(p);
+        launch_pdl(mg_tail_kernel<false>, B, TAIL_THREADS, (size_t)bytes, st, p);
     }
     g_launches.fetch_add(1);
     return (int)cudaGetLastError();

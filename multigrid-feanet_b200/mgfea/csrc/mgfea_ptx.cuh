@@ -83,6 +83,12 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// ---- programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor drains; everything before pdl_wait() (smem carve-up, barrier init, weight tables, which no
+// kernel writes) overlaps the predecessor's tail, everything after sees all of its global writes.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- global stores / loads ---------------------------------------------------------------------------
 __device__ __forceinline__ void st_global_v4(float *p, float4 v) {
     asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)

@@ -21,7 +21,7 @@
 namespace mgfea {
 
 constexpr int ST_WARPS = 8;    // warps per CTA
-constexpr int ST_DEPTH = 8;    // prefetch ring depth (rows); the packed kernel keeps rows k-2..k for f re-reads
+constexpr int ST_DEPTH = 6;    // prefetch ring depth (rows) == unroll factor of the row loop: ring slots are compile-time
 constexpr int ST_TWI = BW - 8; // interior columns per strip (HX = 4)
 constexpr int ST_RING_F4 = 2 * ST_DEPTH + ST_DEPTH / 2;  // float4 units per lane: u ring, f ring, coarse float2 ring
 
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream_kernel(const Strea
     extern __shared__ __align__(16) unsigned char st_smem[];
     __shared__ double red[ST_WARPS];
     __shared__ int lastflag;
-    if (p.ctl != nullptr && ld_volatile_s32(&reinterpret_cast<const Ctl *>(p.ctl)->done) != 0) return;
+    pdl_launch_dependents();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int N = p.N;
 
@@ -192,6 +192,8 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream_kernel(const Strea
     }
     const float inv = p.invd[0];
     const float rscale = (MODE == 0 && p.r_has_scale) ? (p.r_scale_dev ? *p.r_scale_dev : p.r_scale) : 1.0f;
+    pdl_wait();  // weights above are never written by a kernel; all field data is touched only after this point
+    if (p.ctl != nullptr && ld_volatile_s32(&reinterpret_cast<const Ctl *>(p.ctl)->done) != 0) return;
 
     // ---- per-lane prefetch ring: [slot][lane] float4 for u and for f, float2 for the coarse row (up leg)
     float4 *ring_u = reinterpret_cast<float4 *>(st_smem) + warp * (ST_RING_F4 * 32);
@@ -250,18 +252,23 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream_kernel(const Strea
         // last streamed row: y1+1 (u1 row y1 for the residual row y1-1); the last strip of the down leg goes one
         // further so that the coarse ring row (N-1)/2 is produced (as zeros) too
         const int K = ((MODE == 0 && y1 == N) ? y1 + 2 : y1 + 1) - a0 + 1;
-        auto prefetch = [&](int k) {
-            const int a = a0 + k;
-            const int la = a - p.row0;  // local row
-            const bool ok = col_ok && (a >= 0) && (a < N) && (la >= 0) && (la < p.nrloc) && (k < K);
-            const long long off = ok ? (long long)la * p.pitch : 0;
-            const int slot = (k % ST_DEPTH) * 32 + lane;
-            if (!ZERO_INIT) st_cp16(&ring_u[slot], ok ? (const void *)(ub + off) : (const void *)p.f, ok);
-            st_cp16(&ring_f[slot], ok ? (const void *)(fb + off) : (const void *)p.f, ok);
+        // prefetch of streamed row k (rows are requested in increasing k): running global pointers, compile-time ring
+        // slot, and no validity test in steady-state blocks (CHECK = false)
+        const int klo = max(0, p.row0) - a0;                    // first k whose row exists locally / in the domain
+        const int khi = min(min(N, p.row0 + p.nrloc) - a0, K);  // one past the last such k
+        const float *pf_u = ZERO_INIT ? nullptr : ub + (long long)(a0 - p.row0) * p.pitch;
+        const float *pf_f = fb + (long long)(a0 - p.row0) * p.pitch;
+        int kpf = 0;
+        auto prefetch = [&](auto check_tag, int slot_row) {
+            constexpr bool CHECK = decltype(check_tag)::value;
+            const bool ok = !CHECK || (col_ok && kpf >= klo && kpf < khi);
+            const int slot = slot_row * 32 + lane;
+            if (!ZERO_INIT) st_cp16(&ring_u[slot], ok ? (const void *)pf_u : (const void *)p.f, ok);
+            st_cp16(&ring_f[slot], ok ? (const void *)pf_f : (const void *)p.f, ok);
             if (MODE == 1) {  // coarse row ceil(a/2): the row an even fine row copies / an odd row's lower partner
-                const int I = (a + 1) >> 1;
+                const int I = (a0 + kpf + 1) >> 1;
                 const int lI = I - p.crow0;
-                const bool okc = ccol_ok && (I >= 0) && (I < p.Nc) && (lI >= 0) && (lI < p.nrc) && (k < K);
+                const bool okc = !CHECK || (ccol_ok && (I >= 0) && (I < p.Nc) && (lI >= 0) && (lI < p.nrc) && kpf < K);
                 const void *src = okc ? (const void *)(cbp + (long long)lI * p.pitch_c) : (const void *)p.f;
                 const uint32_t sz = okc ? 8u : 0u;
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(&ring_c[slot])), "l"(src),
@@ -269,9 +276,12 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream_kernel(const Strea
                              : "memory");
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
+            if (!ZERO_INIT) pf_u += p.pitch;
+            pf_f += p.pitch;
+            ++kpf;
         };
 #pragma unroll
-        for (int k = 0; k < ST_DEPTH - 1; ++k) prefetch(k);
+        for (int k = 0; k < ST_DEPTH - 1; ++k) prefetch(std::true_type{}, k);
 
         // rotating windows (indices are compile-time after unrolling by 6)
         R6 A[3];      // input rows (u0, or corrected u for the up leg): a-2, a-1, a
@@ -291,7 +301,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream_kernel(const Strea
         }
 
         // one block of 6 row steps.  GUARD: start-up / drain steps (pipeline fill, store ranges); EDGE: masks needed.
-        auto block6 = [&](auto guard_tag, auto edge_tag, int k0) {
+        auto block6 = [&](auto guard_tag, auto edge_tag, auto pf_tag, int k0) {
             constexpr bool GUARD = decltype(guard_tag)::value;
             constexpr bool EDGE = decltype(edge_tag)::value;
 #pragma unroll
@@ -299,9 +309,9 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream_kernel(const Strea
                 const int k = k0 + ph;
                 if (GUARD && k >= K) break;
                 const int a = a0 + k;
-                prefetch(k + ST_DEPTH - 1);
+                prefetch(pf_tag, (ph + ST_DEPTH - 1) % ST_DEPTH);  // k0 is a multiple of ST_DEPTH: slot == phase
                 asm volatile("cp.async.wait_group %0;" ::"n"(ST_DEPTH - 1) : "memory");
-                const int slot = (k % ST_DEPTH) * 32 + lane;
+                const int slot = ph * 32 + lane;
                 float4 uv = ZERO_INIT ? make_float4(0.f, 0.f, 0.f, 0.f) : ring_u[slot];
                 const float4 fv = ring_f[slot];
                 const bool arow_in = !EDGE || (a >= 1 && a <= N - 2);
@@ -433,11 +443,13 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream_kernel(const Strea
         // steady state: k0 >= 6 (pipeline full, all store rows >= y0) and k0 + 5 <= K - 4 (all store rows < y1)
         int k0 = 0;
         if (edge) {
-            for (; k0 < K; k0 += 6) block6(T_{}, T_{}, k0);
+            for (; k0 < K; k0 += 6) block6(T_{}, T_{}, T_{}, k0);
         } else {
-            block6(T_{}, F_{}, 0);
-            for (k0 = 6; k0 + 5 <= K - 4; k0 += 6) block6(F_{}, F_{}, k0);
-            for (; k0 < K; k0 += 6) block6(T_{}, F_{}, k0);
+            block6(T_{}, F_{}, T_{}, 0);
+            // steady state: no pipeline / store-range guards; prefetches unchecked while every prefetched row exists
+            for (k0 = 6; k0 + 5 <= K - 4 && k0 + 5 + ST_DEPTH - 1 < khi; k0 += 6) block6(F_{}, F_{}, F_{}, k0);
+            for (; k0 + 5 <= K - 4; k0 += 6) block6(F_{}, F_{}, T_{}, k0);
+            for (; k0 < K; k0 += 6) block6(T_{}, F_{}, T_{}, k0);
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (MODE == 1 && p.want_norm) {
@@ -504,7 +516,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
     extern __shared__ __align__(16) unsigned char st_smem[];
     __shared__ double red[ST_WARPS];
     __shared__ int lastflag;
-    if (p.ctl != nullptr && ld_volatile_s32(&reinterpret_cast<const Ctl *>(p.ctl)->done) != 0) return;
+    pdl_launch_dependents();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int N = p.N;
 
@@ -521,6 +533,8 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
     for (int q = 0; q < 9; ++q) kw2[q] = pack2(kw[q], kw[q]);
     const u64 inv2 = pack2(inv, inv);
     const float rscale = (MODE == 0 && p.r_has_scale) ? (p.r_scale_dev ? *p.r_scale_dev : p.r_scale) : 1.0f;
+    pdl_wait();  // weights above are never written by a kernel; all field data is touched only after this point
+    if (p.ctl != nullptr && ld_volatile_s32(&reinterpret_cast<const Ctl *>(p.ctl)->done) != 0) return;
 
     // ---- per-lane prefetch ring: [slot][lane] float4 for u and for f, float2 for the coarse row (up leg)
     float4 *ring_u = reinterpret_cast<float4 *>(st_smem) + warp * (ST_RING_F4 * 32);
@@ -579,18 +593,23 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
         // last streamed row: y1+1 (u1 row y1 for the residual row y1-1); the last strip of the down leg goes one
         // further so that the coarse ring row (N-1)/2 is produced (as zeros) too
         const int K = ((MODE == 0 && y1 == N) ? y1 + 2 : y1 + 1) - a0 + 1;
-        auto prefetch = [&](int k) {
-            const int a = a0 + k;
-            const int la = a - p.row0;  // local row
-            const bool ok = col_ok && (a >= 0) && (a < N) && (la >= 0) && (la < p.nrloc) && (k < K);
-            const long long off = ok ? (long long)la * p.pitch : 0;
-            const int slot = (k % ST_DEPTH) * 32 + lane;
-            if (!ZERO_INIT) st_cp16(&ring_u[slot], ok ? (const void *)(ub + off) : (const void *)p.f, ok);
-            st_cp16(&ring_f[slot], ok ? (const void *)(fb + off) : (const void *)p.f, ok);
+        // prefetch of streamed row k (rows are requested in increasing k): running global pointers, compile-time ring
+        // slot, and no validity test in steady-state blocks (CHECK = false)
+        const int klo = max(0, p.row0) - a0;                    // first k whose row exists locally / in the domain
+        const int khi = min(min(N, p.row0 + p.nrloc) - a0, K);  // one past the last such k
+        const float *pf_u = ZERO_INIT ? nullptr : ub + (long long)(a0 - p.row0) * p.pitch;
+        const float *pf_f = fb + (long long)(a0 - p.row0) * p.pitch;
+        int kpf = 0;
+        auto prefetch = [&](auto check_tag, int slot_row) {
+            constexpr bool CHECK = decltype(check_tag)::value;
+            const bool ok = !CHECK || (col_ok && kpf >= klo && kpf < khi);
+            const int slot = slot_row * 32 + lane;
+            if (!ZERO_INIT) st_cp16(&ring_u[slot], ok ? (const void *)pf_u : (const void *)p.f, ok);
+            st_cp16(&ring_f[slot], ok ? (const void *)pf_f : (const void *)p.f, ok);
             if (MODE == 1) {  // coarse row ceil(a/2): the row an even fine row copies / an odd row's lower partner
-                const int I = (a + 1) >> 1;
+                const int I = (a0 + kpf + 1) >> 1;
                 const int lI = I - p.crow0;
-                const bool okc = ccol_ok && (I >= 0) && (I < p.Nc) && (lI >= 0) && (lI < p.nrc) && (k < K);
+                const bool okc = !CHECK || (ccol_ok && (I >= 0) && (I < p.Nc) && (lI >= 0) && (lI < p.nrc) && kpf < K);
                 const void *src = okc ? (const void *)(cbp + (long long)lI * p.pitch_c) : (const void *)p.f;
                 const uint32_t sz = okc ? 8u : 0u;
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(&ring_c[slot])), "l"(src),
@@ -598,9 +617,12 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
                              : "memory");
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
+            if (!ZERO_INIT) pf_u += p.pitch;
+            pf_f += p.pitch;
+            ++kpf;
         };
 #pragma unroll
-        for (int k = 0; k < ST_DEPTH - 3; ++k) prefetch(k);
+        for (int k = 0; k < ST_DEPTH - 3; ++k) prefetch(std::true_type{}, k);
 
         // rotating windows (indices are compile-time after unrolling by 6)
         RP A[3];   // input rows (u0, or corrected u for the up leg): a-2, a-1, a
@@ -619,7 +641,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
         }
 
         // one block of 6 row steps.  GUARD: start-up / drain steps (pipeline fill, store ranges); EDGE: masks needed.
-        auto block6 = [&](auto guard_tag, auto edge_tag, int k0) {
+        auto block6 = [&](auto guard_tag, auto edge_tag, auto pf_tag, int k0) {
             constexpr bool GUARD = decltype(guard_tag)::value;
             constexpr bool EDGE = decltype(edge_tag)::value;
 #pragma unroll
@@ -627,9 +649,9 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
                 const int k = k0 + ph;
                 if (GUARD && k >= K) break;
                 const int a = a0 + k;
-                prefetch(k + ST_DEPTH - 3);  // rows k-2..k stay in the ring: f rows are re-read from it
+                prefetch(pf_tag, (ph + ST_DEPTH - 3) % ST_DEPTH);  // rows k-2..k stay in the ring (f is re-read)
                 asm volatile("cp.async.wait_group %0;" ::"n"(ST_DEPTH - 3) : "memory");
-                const int slot = (k % ST_DEPTH) * 32 + lane;
+                const int slot = ph * 32 + lane;
                 float4 uv = ZERO_INIT ? make_float4(0.f, 0.f, 0.f, 0.f) : ring_u[slot];
                 const bool arow_in = !EDGE || (a >= 1 && a <= N - 2);
                 if (MODE == 1) {
@@ -683,7 +705,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
                     const RP &t = A[(ph + 0) % 3], &m = A[(ph + 1) % 3], &bq = A[(ph + 2) % 3];
                     u64 klo, khi;
                     stencil_rows2(kw2, t, m, bq, klo, khi);
-                    const ulonglong2 ff = *reinterpret_cast<const ulonglong2 *>(&ring_f[((k + ST_DEPTH - 1) % ST_DEPTH) * 32 + lane]);
+                    const ulonglong2 ff = *reinterpret_cast<const ulonglong2 *>(&ring_f[((ph + ST_DEPTH - 1) % ST_DEPTH) * 32 + lane]);
                     u64 olo = add2(mul2(inv2, sub2(ff.x, klo)), m.q[1]);
                     u64 ohi = add2(mul2(inv2, sub2(ff.y, khi)), m.q[3]);
                     float o0, o1, o2, o3;
@@ -704,7 +726,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
                         const int yr = a - 2;
                         u64 rlo, rhi;
                         stencil_rows2(kw2, Bw[(ph + 0) % 3], Bw[(ph + 1) % 3], Bw[(ph + 2) % 3], rlo, rhi);
-                        const ulonglong2 f2 = *reinterpret_cast<const ulonglong2 *>(&ring_f[((k + ST_DEPTH - 2) % ST_DEPTH) * 32 + lane]);
+                        const ulonglong2 f2 = *reinterpret_cast<const ulonglong2 *>(&ring_f[((ph + ST_DEPTH - 2) % ST_DEPTH) * 32 + lane]);
                         rlo = sub2(f2.x, rlo);
                         rhi = sub2(f2.y, rhi);
                         float4 r;
@@ -767,11 +789,13 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
         // steady state: k0 >= 6 (pipeline full, all store rows >= y0) and k0 + 5 <= K - 4 (all store rows < y1)
         int k0 = 0;
         if (edge) {
-            for (; k0 < K; k0 += 6) block6(T_{}, T_{}, k0);
+            for (; k0 < K; k0 += 6) block6(T_{}, T_{}, T_{}, k0);
         } else {
-            block6(T_{}, F_{}, 0);
-            for (k0 = 6; k0 + 5 <= K - 4; k0 += 6) block6(F_{}, F_{}, k0);
-            for (; k0 < K; k0 += 6) block6(T_{}, F_{}, k0);
+            block6(T_{}, F_{}, T_{}, 0);
+            // steady state: no pipeline / store-range guards; prefetches unchecked while every prefetched row exists
+            for (k0 = 6; k0 + 5 <= K - 4 && k0 + 5 + ST_DEPTH - 1 < khi; k0 += 6) block6(F_{}, F_{}, F_{}, k0);
+            for (; k0 + 5 <= K - 4; k0 += 6) block6(F_{}, F_{}, T_{}, k0);
+            for (; k0 < K; k0 += 6) block6(T_{}, F_{}, T_{}, k0);
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (MODE == 1 && p.want_norm) {

@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail_kernel(const TailPara
     extern __shared__ __align__(16) unsigned char smraw[];
     float *sm = reinterpret_cast<float *>(smraw);
     __shared__ TailTabs T;
-    if (p.ctl != nullptr && ld_volatile_s32(&reinterpret_cast<const Ctl *>(p.ctl)->done) != 0) return;
+    pdl_launch_dependents();
     const int tid = threadIdx.x, b = blockIdx.x;
     // ---- zero all fields (ghost cells / pads / zero initial guesses), load tables and keys
     for (int i = tid; i < p.total_floats / 4; i += blockDim.x)
@@ -306,6 +306,8 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail_kernel(const TailPara
             }
         }
     }
+    pdl_wait();  // tables / keys above are never written by a kernel; the restricted rhs below is
+    if (p.ctl != nullptr && ld_volatile_s32(&reinterpret_cast<const Ctl *>(p.ctl)->done) != 0) return;
     {
         const TailLevel &L = p.lv[0];
         const float *fin = p.f_in + (long long)b * p.plane;
