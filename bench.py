@@ -400,9 +400,7 @@ def run_multi(args):
         return (1.2e5 * torch.rand((nrows, NN), generator=g, device="cuda") + 1.3e5)
 
     mg.fill_local(u_rows)
-    from FEANet.distributed import halo_exchange
-
-    halo_exchange(mg.u[0], lev, mg.rank, mg.world)
+    mg.exchange_initial()
 
     def barrier():
         dist.barrier()
@@ -449,6 +447,8 @@ def run_multi(args):
     torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
     cycles_per_s = steps / (ms * 1e-3)
+    if mg.peer is not None:
+        mg.peer.check()  # a timed-out peer wait invalidates the run: fail loudly
 
     # dominant kernel on this rank: level-0 slab down leg
     peak, peak_src = hbm_peak()
@@ -497,15 +497,19 @@ def run_multi(args):
     te = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
     dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_dt = float(te.item())
+    xname = ("halo rows stored straight into the neighbours' ghost rows over NVLink peer memory, one exchange kernel "
+             "per step, no NCCL on the data path") if mg.peer is not None else "NCCL send/recv halo exchange"
     if rank == 0:
         line = {"metric": METRIC, "value": cycles_per_s * dof / 1e9, "unit": "GDOF/s", "n_gpus": world, "steps": steps,
                 "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "v_cycles_per_s": cycles_per_s,
                 "config": {"workload": f"iso Poisson {N}x{N}, V(1,1), {L} levels, single RHS partitioned into {world} "
-                                       f"row slabs (NCCL halo exchange, levels N<2049 replicated), f=0 model problem; "
+                                       f"row slabs ({xname}, levels N<2049 replicated), f=0 model problem; "
                                        f"{dof / world / 1e6:.1f} MDOF per GPU (N=1 runs 16.8 MDOF)",
                            "n": n, "levels": L, "nu": [1, 1], "batch": 1, "first_replicated_level": mg.part.ld,
                            "cuda_graph": bool(graphed), "graph_error": mg._graph_err,
+                           "exchange": "peer" if mg.peer is not None else "nccl",
+                           "peer_error": getattr(mg, "peer_error", None),
                            "l2": "inputs larger than L2 per GPU at level 0; no explicit flush"},
                 "clocks": clocks,
                 "e2e": {"value": args.e2e_cycles * dof / e2e_dt / 1e9, "unit": "GDOF/s",

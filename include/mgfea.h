@@ -156,6 +156,37 @@ int mgfea_slab_prolong_correct_smooth(const mgfea_grid *g, const mgfea_slab *s, 
                                       int pitch_c, int64_t plane_c, const float *u_in, float *u_out, const float *f,
                                       double *sumsq, int B, void *stream);
 
+/* ---- peer memory: halo exchange over NVLink without a collective library ----------- */
+/* The reference has no distributed code; these entries carry the row-slab exchange of FEANet/distributed.py.  Slab
+ * arrays and one mailbox per rank are allocated with mgfea_peer_alloc, exported as 64-byte handles that the host side
+ * passes to the other ranks of the node (any byte transport), and mapped there with mgfea_peer_open. */
+#define MGFEA_IPC_HANDLE_BYTES 64
+int mgfea_peer_alloc(void **ptr, uint64_t bytes);      /* cudaMalloc + zero fill (synchronises once, at setup) */
+int mgfea_peer_free(void *ptr);
+int mgfea_peer_export(const void *ptr, void *handle);  /* handle[MGFEA_IPC_HANDLE_BYTES] of an mgfea_peer_alloc block */
+int mgfea_peer_open(const void *handle, void **ptr);   /* map another rank's block (enables peer access lazily) */
+int mgfea_peer_close(void *ptr);
+
+#define MGFEA_XCHG_MAX_JOBS 16
+#define MGFEA_XCHG_MAX_PEERS 8
+#define MGFEA_XCHG_PUSH 1 /* run the copy jobs, then increment every `signal` flag (release, system scope) */
+#define MGFEA_XCHG_WAIT 2 /* wait until every `wait` flag has reached *seq + 1, then advance *seq */
+/* One exchange step of one rank (a single kernel, graph-capturable).  All addresses and sizes are multiples of 16 B. */
+typedef struct mgfea_xchg {
+    int32_t njobs, nsignal, nwait, mode;
+    const void *src[MGFEA_XCHG_MAX_JOBS]; /* local rows */
+    void *dst[MGFEA_XCHG_MAX_JOBS];       /* the same rows in a peer's array (ghost rows / gathered rows / slots) */
+    uint64_t bytes[MGFEA_XCHG_MAX_JOBS];
+    uint32_t *signal[MGFEA_XCHG_MAX_PEERS];     /* flags in the TARGET ranks' mailboxes */
+    const uint32_t *wait[MGFEA_XCHG_MAX_PEERS]; /* flags in THIS rank's mailbox, incremented by the ranks pushing to it */
+    uint32_t *seq;   /* this rank's count of completed steps on this flag set (device memory, advanced by the kernel) */
+    int32_t *err;    /* device word set to 1 + index of the flag whose wait timed out (dead peer); may be NULL */
+    const double *red_src; /* optional: after the wait, *red_dst = sum of nred doubles spaced red_stride bytes apart */
+    double *red_dst;
+    int32_t nred, red_stride;
+} mgfea_xchg;
+int mgfea_p2p_exchange(const mgfea_xchg *x, void *stream);
+
 /* ---- whole V-cycle ----------------------------------------------------------------------------------- */
 typedef struct mgfea_cycle_cfg {
     int32_t nu1, nu2;      /* pre / post sweeps (coarsest level gets nu1 + nu2) */

@@ -13,6 +13,7 @@ tests/test_gpu_parity.py::test_slab_* emulates the ranks on one GPU).
 """
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -25,7 +26,7 @@ class SlabPartition:
     """Host-side description of which global rows of every level a rank owns / holds."""
 
     def __init__(self, n, L, world, rank, dist_min_n=2049):
-        self.n, self.L, self.world, self.rank = n, L, world, rank
+        self.n, self.L, self.world, self.rank, self.dist_min_n = n, L, world, rank, dist_min_n
         self.levels = []
         for l in range(L):
             nl = n // (2 ** l)
@@ -82,10 +83,115 @@ def halo_exchange(arr, lev, rank, world, group=None):
             recv.copy_(rb)
 
 
+class PeerSlabMemory:
+    """Slab arrays + exchange mailbox of one rank in a block the other ranks of the node map through cudaIpc
+    (mgfea.PeerBlock), and the exchange steps over it (mgfea_p2p_exchange): the ranks store their boundary rows straight
+    into the neighbours' ghost rows over NVLink, one kernel per step, no collective library on the data path.
+
+    The layout is identical on every rank (arrays sized for the largest slab), so a peer's address of any row is
+    base[q] + offset(array) + (global row - row0 of rank q) * pitch.
+    """
+    # mailbox (bytes): flags written by the neighbours / by every rank, partial-sum slots, this rank's step counters
+    FLAG_UP, FLAG_DOWN, ALL_FLAGS, SLOTS, SEQ_NB, SEQ_ALL, ERR, PARTIAL, TOTAL, MAILBOX = 0, 16, 64, 256, 512, 528, 544, 576, 592, 4096
+
+    def __init__(self, part, group=None):
+        import mgfea
+
+        self.mg, self.part, self.group = mgfea, part, group
+        world, rank, ld = part.world, part.rank, part.ld
+        if world > mgfea.XCHG_MAX_PEERS:
+            raise mgfea.MgfeaError(f"peer exchange supports up to {mgfea.XCHG_MAX_PEERS} ranks")
+        self.parts = [part if q == rank else SlabPartition(part.n, part.L, world, q, part.dist_min_n) for q in range(world)]
+        off, self.off, self.pitch = self.MAILBOX, {}, {}
+        for l in range(ld + 1):
+            N = part.levels[l]["N"]
+            self.pitch[l] = mgfea.pitch_for(N)
+            rows = max(p.levels[l]["nrows"] for p in self.parts)
+            size = (rows * self.pitch[l] * 4 + 255) // 256 * 256
+            for name in (("u", "u_alt", "f") if l < ld else ("f",)):
+                self.off[(name, l)] = off
+                off += size
+        self.block = mgfea.PeerBlock(off)
+        self.bases = None
+        self.partial = self.block.tensor(self.PARTIAL, (2,), torch.float64)  # [0]: this rank's interior sum of squares
+        self.total = self.block.tensor(self.TOTAL, (1,), torch.float64)      # all-rank sum (same bits on every rank)
+        self.err = self.block.tensor(self.ERR, (1,), torch.int32)
+        self._steps = {}
+
+    def connect(self, handles):
+        """map the blocks of the other ranks (handles[q] = their PeerBlock.handle(), any transport)"""
+        rank = self.part.rank
+        self.bases = [self.block.base if q == rank else self.block.open_peer(handles[q]) for q in range(len(handles))]
+
+    def array(self, name, l):
+        lev = self.part.levels[l]
+        return self.block.tensor(self.off[(name, l)], (1, lev["nrows"], self.pitch[l]), torch.float32)
+
+    def _build(self, halos, gather, reduce):
+        mg, part, rank, world = self.mg, self.part, self.part.rank, self.part.world
+        x, j = mg.Xchg(), 0
+
+        def job(src, dst, nbytes):
+            nonlocal j
+            x.src[j], x.dst[j], x.bytes[j] = src, dst, nbytes
+            j += 1
+
+        me = self.bases[rank]
+        for name, l in halos:  # GHOST boundary rows of my owned range -> the neighbours' ghost rows
+            lev, rowb, off = part.levels[l], self.pitch[l] * 4, self.off[(name, l)]
+            for q, first in ((rank - 1, lev["own0"]), (rank + 1, lev["own1"] - GHOST)):
+                if 0 <= q < world:
+                    job(me + off + (first - lev["row0"]) * rowb,
+                        self.bases[q] + off + (first - self.parts[q].levels[l]["row0"]) * rowb, GHOST * rowb)
+        all_step = gather or reduce
+        if gather:  # my owned rows of the first replicated level's right-hand side -> every peer
+            ld = part.ld
+            per, rowb, off = (part.n // 2 ** ld) // world, self.pitch[ld] * 4, self.off[("f", ld)]
+            for q in range(world):
+                if q != rank:
+                    job(me + off + rank * per * rowb, self.bases[q] + off + rank * per * rowb, per * rowb)
+        if reduce:  # my partial sum -> slot [rank] of every mailbox (mine included); summed in rank order after the wait
+            for q in range(world):
+                job(me + self.PARTIAL, self.bases[q] + self.SLOTS + 16 * rank, 16)
+            x.red_src, x.red_dst, x.nred, x.red_stride = me + self.SLOTS, me + self.TOTAL, world, 16
+        ns = nw = 0
+        if all_step:
+            for q in range(world):
+                if q != rank:
+                    x.signal[ns], x.wait[nw] = self.bases[q] + self.ALL_FLAGS + 16 * rank, me + self.ALL_FLAGS + 16 * q
+                    ns, nw = ns + 1, nw + 1
+            x.seq = me + self.SEQ_ALL
+        else:
+            if rank > 0:
+                x.signal[ns], x.wait[nw] = self.bases[rank - 1] + self.FLAG_DOWN, me + self.FLAG_UP
+                ns, nw = ns + 1, nw + 1
+            if rank < world - 1:
+                x.signal[ns], x.wait[nw] = self.bases[rank + 1] + self.FLAG_UP, me + self.FLAG_DOWN
+                ns, nw = ns + 1, nw + 1
+            x.seq = me + self.SEQ_NB
+        x.njobs, x.nsignal, x.nwait, x.err = j, ns, nw, me + self.ERR
+        x.mode = mg.XCHG_PUSH | mg.XCHG_WAIT
+        return x
+
+    def step(self, halos, gather=False, reduce=False):
+        """one exchange step (a single kernel on the current stream); every rank must issue the same sequence"""
+        key = (tuple(halos), gather, reduce)
+        x = self._steps.get(key)
+        if x is None:
+            x = self._steps[key] = self._build(halos, gather, reduce)
+        self.mg.check(self.mg.lib().mgfea_p2p_exchange(ctypes.byref(x), self.mg.stream_ptr()))
+
+    def check(self):
+        """raises if a wait timed out (a peer died or fell out of step); synchronises"""
+        e = int(self.err.item())
+        if e:
+            raise self.mg.MgfeaError(f"peer exchange: wait on flag {e - 1} timed out on rank {self.part.rank}")
+
+
 class CudaSlabOps:
     """local operators on the GPU: the slab forms of the streaming kernels + the replicated coarse engine"""
 
-    def __init__(self, part, nu1=1, nu2=1):
+    def __init__(self, part, nu1=1, nu2=1, coarse_f_store=None):
         import mgfea
         from .jacobi import JacobiBlock
         from .mesh import MeshSquare
@@ -103,7 +209,8 @@ class CudaSlabOps:
             mesh = MeshSquare(2, n // 2 ** l + 1)
             self.jacs.append(JacobiBlock(KNet(mesh), mesh, 2 / 3., None, None))
         self.rtab = torch.from_numpy(FULL_WEIGHTING_16.reshape(1, 9).copy()).to(self.dev)
-        self.coarse = VCycleEngine(self.jacs[part.ld:], B=1, nu1=nu1, nu2=nu2) if part.ld < L else None
+        self.coarse = VCycleEngine(self.jacs[part.ld:], B=1, nu1=nu1, nu2=nu2, f0_store=coarse_f_store) \
+            if part.ld < L else None
         self._sumsq = torch.zeros(1, dtype=torch.float64, device=self.dev)
 
     def alloc(self, l):
@@ -160,18 +267,31 @@ class CudaSlabOps:
 class SlabMultigrid:
     """V(1,1) solver for the iso Poisson problem on row slabs.  `ops` supplies the local operators."""
 
-    def __init__(self, n, ops_factory=CudaSlabOps, L=None, dist_min_n=2049, group=None):
+    def __init__(self, n, ops_factory=CudaSlabOps, L=None, dist_min_n=2049, group=None, p2p=None):
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.group = group
         self.n = n
         self.L = int(math.log2(n)) if L is None else L
         self.part = SlabPartition(n, self.L, self.world, self.rank, dist_min_n)
-        self.ops = ops_factory(self.part)
         ld = self.part.ld
-        self.u = [self.ops.alloc(l) for l in range(ld)]
-        self.u_alt = [self.ops.alloc(l) for l in range(ld)]
-        self.f = [self.ops.alloc(l) for l in range(ld)]
+        # peer-memory exchange (NVLink P2P, no NCCL on the data path) whenever the CUDA operators run on > 1 rank
+        self.peer = None
+        if p2p is None:
+            p2p = os.environ.get("MGFEA_P2P", "1") != "0"
+        if p2p and self.world > 1 and 0 < ld < self.L and ops_factory is CudaSlabOps and torch.cuda.is_available():
+            self.peer = self._try_peer_memory()
+        if self.peer is not None:
+            self.ops = ops_factory(self.part, coarse_f_store=self.peer.array("f", ld))
+            self.ops._sumsq = self.peer.partial
+            self.u = [self.peer.array("u", l) for l in range(ld)]
+            self.u_alt = [self.peer.array("u_alt", l) for l in range(ld)]
+            self.f = [self.peer.array("f", l) for l in range(ld)]
+        else:
+            self.ops = ops_factory(self.part)
+            self.u = [self.ops.alloc(l) for l in range(ld)]
+            self.u_alt = [self.ops.alloc(l) for l in range(ld)]
+            self.f = [self.ops.alloc(l) for l in range(ld)]
         self.residuals = []
         self._graph = None
         self._graph_out = None
@@ -179,9 +299,32 @@ class SlabMultigrid:
         # the exchange of the pre-smoothed u is only needed by the up leg of the same level: it runs on a side stream
         # with its own communicator so that it overlaps the coarser levels instead of delaying the next restriction
         self._side_group, self._side_stream = None, None
-        if self.world > 1 and torch.cuda.is_available() and dist.get_backend(group) == "nccl":
+        if self.peer is None and self.world > 1 and torch.cuda.is_available() and dist.get_backend(group) == "nccl":
             self._side_group = dist.new_group(ranks=list(range(self.world)), backend="nccl")
             self._side_stream = torch.cuda.Stream()
+
+    def _try_peer_memory(self):
+        """collective: all ranks map each other's block, or all fall back to the NCCL exchange"""
+        mem, handle, why = None, None, None
+        try:
+            mem = PeerSlabMemory(self.part, self.group)
+            handle = mem.block.handle()
+        except Exception as e:  # noqa: BLE001  (allocation / cudaIpc export unavailable)
+            why = repr(e)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle, group=self.group)
+        if why is None and all(h is not None for h in handles):
+            try:
+                mem.connect(handles)
+            except Exception as e:  # noqa: BLE001  (peers without P2P access, IPC blocked by the container, ...)
+                why = repr(e)
+        elif why is None:
+            why = "a peer could not export its block"
+        ok = [None] * self.world
+        dist.all_gather_object(ok, why, group=self.group)
+        bad = [w for w in ok if w is not None]
+        self.peer_error = bad[0] if bad else None
+        return mem if not bad else None
 
     # ---- problem data: every rank takes its rows (owned + ghost) from the full host arrays
     def set_problem(self, u0_full, f_full):
@@ -284,6 +427,8 @@ class SlabMultigrid:
         if ld == 0:
             ops.coarse.cycle()
             return ops.coarse.sumsq.clone()
+        if self.peer is not None:
+            return self._cycle_peer(want_norm)
         # ---- down leg on the slabs
         side_done = [None] * ld
         for l in range(ld):
@@ -324,6 +469,33 @@ class SlabMultigrid:
             return tot
         return None
 
+    def _cycle_peer(self, want_norm=True):
+        """the same cycle with every exchange done by peer stores (PeerSlabMemory.step): 2 * ld kernels, no NCCL.
+        Buffer discipline (what makes overwriting a neighbour's ghost rows safe without a second handshake): the step
+        after down(l) pushes u_alt[l] / f[l+1], the step after up(l) pushes u[l] -- never an array that the kernel
+        running between two consecutive steps reads."""
+        ops, ld, peer = self.ops, self.part.ld, self.peer
+        for l in range(ld):
+            last = l == ld - 1
+            ops.down(l, self.u[l] if l == 0 else None, self.u_alt[l], self.f[l], ops.coarse_f() if last else self.f[l + 1])
+            peer.step((("u_alt", l),) if last else (("u_alt", l), ("f", l + 1)), gather=last)
+        ops.coarse_cycle()
+        for l in range(ld - 1, -1, -1):
+            vc = self.u[l + 1] if l + 1 < ld else ops.coarse_u()
+            ops.up(l, vc, self.u_alt[l], self.u[l], self.f[l], want_norm and l == 0)
+            peer.step((("u", l),), reduce=(want_norm and l == 0))
+        return peer.total if want_norm else None
+
+    def exchange_initial(self):
+        """ghost rows of the level-0 iterate and right-hand side (after set_problem / fill_local)"""
+        if self.part.ld == 0:
+            return
+        if self.peer is not None:
+            self.peer.step((("u", 0), ("f", 0)))
+        else:
+            halo_exchange(self.u[0], self.part.levels[0], self.rank, self.world, self.group)
+            halo_exchange(self.f[0], self.part.levels[0], self.rank, self.world, self.group)
+
     def Solve(self, n_iter=None, EPS=None, max_cycles=200):
         """Multigrid.Solve semantics (MM_Model_convergence.ipynb cell 3): cycles while (res > EPS or n < n_iter)"""
         if n_iter is None:
@@ -331,9 +503,11 @@ class SlabMultigrid:
         elif EPS is None:
             EPS = math.inf
         res, hist = 1.0, []
-        halo_exchange(self.u[0], self.part.levels[0], self.rank, self.world, self.group) if self.part.ld > 0 else None
+        self.exchange_initial()
         while (res > EPS or len(hist) < n_iter) and len(hist) < max_cycles:
             res = float(torch.sqrt(self.cycle().sum()).item())
             hist.append(res)
+        if self.peer is not None:
+            self.peer.check()
         self.residuals = hist
         return hist

@@ -24,7 +24,7 @@ class VCycleEngine:
 
     def __init__(self, jacs, B=1, nu1=1, nu2=1, smoother="jac", hnet=None, prolong="bilinear", rtab=None, r_scale=4.0,
                  ptab=None, p_scale=None, w_param=None, quirk_level0=False, conv_rule=mgfea.CONV_SUM,
-                 max_cycles=256):
+                 max_cycles=256, f0_store=None):
         self.dev = mgfea.require_cuda()
         self.jacs = list(jacs)
         self.L = len(self.jacs)
@@ -44,6 +44,8 @@ class VCycleEngine:
         self.u = [Field(B, j.nnode_edge, self.dev) for j in self.jacs]
         self.u_alt = [Field(B, j.nnode_edge, self.dev) for j in self.jacs]
         self.f = [Field(B, j.nnode_edge, self.dev) for j in self.jacs]
+        if f0_store is not None:  # caller-owned level-0 right-hand side (peer-mapped memory of the row-slab path)
+            self.f[0] = Field(B, self.jacs[0].nnode_edge, self.dev, store=f0_store)
         self.sumsq = torch.zeros(B, dtype=torch.float64, device=self.dev)
         self.hist = torch.zeros((max_cycles, B), dtype=torch.float64, device=self.dev)
         self.ctl = torch.zeros(8, dtype=torch.int32, device=self.dev)  # mgfea_ctl (32 bytes)

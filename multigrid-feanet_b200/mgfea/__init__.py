@@ -28,6 +28,8 @@ EXPORTS = [
     "mgfea_residual", "mgfea_restrict", "mgfea_smooth_residual_restrict", "mgfea_prolong_correct_smooth",
     "mgfea_residual_norm", "mgfea_vcycle", "mgfea_restrict_channels", "mgfea_prolong_channels",
     "mgfea_slab_smooth_residual_restrict", "mgfea_slab_prolong_correct_smooth",
+    "mgfea_peer_alloc", "mgfea_peer_free", "mgfea_peer_export", "mgfea_peer_open", "mgfea_peer_close",
+    "mgfea_p2p_exchange",
 ]
 
 
@@ -75,6 +77,19 @@ class Slab(ctypes.Structure):
     _fields_ = [("row0", ctypes.c_int32), ("nrows", ctypes.c_int32), ("own0", ctypes.c_int32), ("own1", ctypes.c_int32)]
 
 
+XCHG_MAX_JOBS, XCHG_MAX_PEERS, XCHG_PUSH, XCHG_WAIT, IPC_HANDLE_BYTES = 16, 8, 1, 2, 64
+
+
+class Xchg(ctypes.Structure):
+    """mgfea_xchg: one exchange step of one rank (include/mgfea.h)"""
+    _fields_ = [("njobs", ctypes.c_int32), ("nsignal", ctypes.c_int32), ("nwait", ctypes.c_int32),
+                ("mode", ctypes.c_int32), ("src", ctypes.c_void_p * XCHG_MAX_JOBS),
+                ("dst", ctypes.c_void_p * XCHG_MAX_JOBS), ("bytes", ctypes.c_uint64 * XCHG_MAX_JOBS),
+                ("signal", ctypes.c_void_p * XCHG_MAX_PEERS), ("wait", ctypes.c_void_p * XCHG_MAX_PEERS),
+                ("seq", ctypes.c_void_p), ("err", ctypes.c_void_p), ("red_src", ctypes.c_void_p),
+                ("red_dst", ctypes.c_void_p), ("nred", ctypes.c_int32), ("red_stride", ctypes.c_int32)]
+
+
 class LevelBufs(ctypes.Structure):
     _fields_ = [("u", ctypes.c_void_p), ("u_alt", ctypes.c_void_p), ("f", ctypes.c_void_p)]
 
@@ -116,6 +131,12 @@ def lib():
         S = ctypes.POINTER(Slab)
         L.mgfea_slab_smooth_residual_restrict.argtypes = [G, S, vp, vp, vp, vp, S, i32, i64, vp, i32, f32, vp, i32, vp]
         L.mgfea_slab_prolong_correct_smooth.argtypes = [G, S, vp, S, i32, i64, vp, vp, vp, vp, i32, vp]
+        L.mgfea_peer_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_uint64]
+        L.mgfea_peer_free.argtypes = [vp]
+        L.mgfea_peer_export.argtypes = [vp, vp]
+        L.mgfea_peer_open.argtypes = [vp, ctypes.POINTER(vp)]
+        L.mgfea_peer_close.argtypes = [vp]
+        L.mgfea_p2p_exchange.argtypes = [ctypes.POINTER(Xchg), vp]
         L.mgfea_vcycle.argtypes = [ctypes.POINTER(Grid), ctypes.POINTER(LevelBufs), i32, ctypes.POINTER(CycleCfg), vp,
                                    vp, vp, i32, vp]
         _lib = L
@@ -222,6 +243,57 @@ def pack_keys(keys_u8) -> torch.Tensor:
     out = torch.zeros((N, kp), dtype=torch.uint8, device=dev)
     out[:, :N] = k.to(dev)
     return out
+
+
+class _RawCuda:
+    """__cuda_array_interface__ carrier: lets torch view memory owned by the C library (mgfea_peer_alloc) without a copy"""
+
+    def __init__(self, ptr, shape, typestr, owner):
+        self.owner = owner  # keeps the block alive while a tensor built on it exists
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class PeerBlock:
+    """A device block that the other ranks of the node can map (cudaIpc): slab arrays + the exchange mailbox live here.
+    `base` is the local address; `tensor()` carves torch views out of it; `handle()` is what travels to the peers."""
+
+    def __init__(self, nbytes: int):
+        self.dev = require_cuda()
+        self.nbytes = int(nbytes)
+        p = ctypes.c_void_p()
+        check(lib().mgfea_peer_alloc(ctypes.byref(p), self.nbytes))
+        self.base = int(p.value)
+        self._opened = []
+
+    def handle(self) -> bytes:
+        buf = ctypes.create_string_buffer(IPC_HANDLE_BYTES)
+        check(lib().mgfea_peer_export(self.base, buf))
+        return bytes(buf.raw)
+
+    def open_peer(self, handle: bytes) -> int:
+        """map another rank's block into this process; returns its base address here"""
+        p = ctypes.c_void_p()
+        check(lib().mgfea_peer_open(ctypes.create_string_buffer(handle, IPC_HANDLE_BYTES), ctypes.byref(p)))
+        self._opened.append(int(p.value))
+        return int(p.value)
+
+    def tensor(self, offset: int, shape, dtype=torch.float32) -> torch.Tensor:
+        typestr = {torch.float32: "<f4", torch.float64: "<f8", torch.int32: "<i4", torch.uint8: "|u1"}[dtype]
+        nbytes = int(torch.empty((), dtype=dtype).element_size())
+        for d in shape:
+            nbytes *= int(d)
+        if offset < 0 or offset + nbytes > self.nbytes:
+            raise MgfeaError("PeerBlock.tensor: region outside the block")
+        return torch.as_tensor(_RawCuda(self.base + offset, shape, typestr, self), device=self.dev)
+
+    def close(self):
+        for p in self._opened:
+            lib().mgfea_peer_close(p)
+        self._opened = []
+        if self.base:
+            lib().mgfea_peer_free(self.base)
+            self.base = 0
 
 
 class DeviceTable:

@@ -14,6 +14,7 @@
 #include "mgfea_tile.cuh"
 #include "mgfea_tail.cuh"
 #include "mgfea_stream.cuh"
+#include "mgfea_p2p.cuh"
 
 #ifndef MGFEA_MINBLOCKS
 #define MGFEA_MINBLOCKS 3
@@ -1507,6 +1508,83 @@ int mgfea_slab_prolong_correct_smooth(const mgfea_grid *g, const mgfea_slab *s, 
     pr.sumsq = sumsq;
     if ((rc = check_field(u_out, g->pitch, g->plane)) || (rc = check_field(f, g->pitch, g->plane))) return rc;
     return run_stream(pr, (cudaStream_t)stream);
+}
+
+/* ---- peer memory + exchange (mgfea_p2p.cuh) -------------------------------------------------------------- */
+int mgfea_peer_alloc(void **ptr, uint64_t bytes) {
+    if (!ptr || bytes == 0) return MGFEA_EINVAL;
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemset(p, 0, (size_t)bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return (int)e;
+    }
+    *ptr = p;
+    return 0;
+}
+int mgfea_peer_free(void *ptr) { return ptr ? (int)cudaFree(ptr) : MGFEA_EINVAL; }
+int mgfea_peer_export(const void *ptr, void *handle) {
+    if (!ptr || !handle) return MGFEA_EINVAL;
+    static_assert(sizeof(cudaIpcMemHandle_t) == MGFEA_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, const_cast<void *>(ptr));
+    if (e != cudaSuccess) return (int)e;
+    memcpy(handle, &h, sizeof(h));
+    return 0;
+}
+int mgfea_peer_open(const void *handle, void **ptr) {
+    if (!ptr || !handle) return MGFEA_EINVAL;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void *p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return (int)e;
+    *ptr = p;
+    return 0;
+}
+int mgfea_peer_close(void *ptr) { return ptr ? (int)cudaIpcCloseMemHandle(ptr) : MGFEA_EINVAL; }
+
+int mgfea_p2p_exchange(const mgfea_xchg *x, void *stream) {
+    if (!x || x->njobs < 0 || x->njobs > MGFEA_XCHG_MAX_JOBS || x->nsignal < 0 || x->nsignal > MGFEA_XCHG_MAX_PEERS ||
+        x->nwait < 0 || x->nwait > MGFEA_XCHG_MAX_PEERS || !(x->mode & (MGFEA_XCHG_PUSH | MGFEA_XCHG_WAIT)))
+        return MGFEA_EINVAL;
+    if ((x->mode & MGFEA_XCHG_WAIT) && !x->seq) return MGFEA_EINVAL;
+    unsigned long long total = 0;
+    for (int j = 0; j < x->njobs; ++j) {
+        if (!x->src[j] || !x->dst[j]) return MGFEA_EINVAL;
+        if ((reinterpret_cast<uintptr_t>(x->src[j]) | reinterpret_cast<uintptr_t>(x->dst[j]) | x->bytes[j]) & 15u)
+            return MGFEA_EALIGN;
+        total += x->bytes[j];
+    }
+    DeviceScratch *scr = nullptr;
+    int rc = get_scratch(1, &scr);
+    if (rc) return rc;
+    XchgParams p;
+    p.x = *x;
+    p.ticket = scr->counter + 8;  // separate word from the residual-norm ticket
+    int khz = 0;
+    static long long clocks_per_s = 0;
+    if (clocks_per_s == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev);
+        clocks_per_s = khz > 0 ? (long long)khz * 1000 : 2000000000LL;
+    }
+    const char *te = getenv("MGFEA_P2P_TIMEOUT_S");
+    p.timeout_clocks = clocks_per_s * (te ? atoll(te) : 5);
+    int grid = 1;
+    if (x->mode & MGFEA_XCHG_PUSH) {
+        const unsigned long long chunks = total >> 4;
+        grid = (int)((chunks + XCHG_THREADS * 4 - 1) / (XCHG_THREADS * 4));  // about 4 chunks per thread
+        if (grid < 1) grid = 1;
+        if (grid > 64) grid = 64;
+    }
+    p2p_exchange_kernel<<<grid, XCHG_THREADS, 0, (cudaStream_t)stream>>>(p);
+    g_launches.fetch_add(1);
+    return (int)cudaGetLastError();
 }
 
 int mgfea_vcycle(const mgfea_grid *grids, const mgfea_level_bufs *bufs, int nlevels, const mgfea_cycle_cfg *cfg,

@@ -1,0 +1,96 @@
+// Halo exchange / gather / all-reduce of the row-slab V-cycle over NVLink peer memory (no NCCL on the data path).
+//
+// Every rank's slab arrays and a small "mailbox" live in memory that the other ranks of the node have mapped
+// (cudaIpc).  One exchange step is ONE kernel per rank:
+//
+//   push    the copy jobs store this rank's boundary rows straight into the neighbours' ghost rows (or its coarse rows /
+//           partial sums into every peer) with 16-byte peer stores over NVLink;
+//   signal  when the last CTA has finished its stores (ticket counter), it makes them visible at system scope and
+//           increments one flag in each target's mailbox (red.release.sys);
+//   wait    the same thread then spins (ld.acquire.sys) until the flags in ITS mailbox, written by the ranks that push to
+//           it, have reached this rank's exchange count + 1.  The count lives in device memory and is advanced by the
+//           kernel itself, so the whole step is CUDA-graph replayable.
+//
+// The kernel that follows on the stream therefore sees complete ghost rows.  Overwriting a neighbour's ghost rows is safe
+// without a second handshake because of the ping-pong buffers: the array pushed in step s+1 is never the one a kernel
+// between steps s and s+1 reads (see FEANet/distributed.py), and a rank cannot be more than one step ahead of a
+// neighbour.  Waits are bounded (a dead peer must not hang the GPU box): on timeout the error word is set and the host
+// raises.
+#pragma once
+#include <stdint.h>
+
+#include "../../../include/mgfea.h"
+
+namespace mgfea {
+
+struct XchgParams {
+    mgfea_xchg x;
+    unsigned int *ticket;  // per-device CTA ticket counter (zero between launches)
+    long long timeout_clocks;
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_sys_add_u32(unsigned int *p, unsigned int v) {
+    asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+constexpr int XCHG_THREADS = 256;
+
+__global__ void __launch_bounds__(XCHG_THREADS) p2p_exchange_kernel(const XchgParams p) {
+    __shared__ int is_waiter;
+    const mgfea_xchg &x = p.x;
+    const bool push = (x.mode & MGFEA_XCHG_PUSH) != 0;
+    if (push) {
+        // ---- copy jobs: 16-byte chunks, grid-stride within each job (coalesced peer stores)
+        const long long gtid = (long long)blockIdx.x * XCHG_THREADS + threadIdx.x;
+        const long long gstride = (long long)gridDim.x * XCHG_THREADS;
+        for (int j = 0; j < x.njobs; ++j) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(x.src[j]);
+            uint4 *dst = reinterpret_cast<uint4 *>(x.dst[j]);
+            const long long nchunk = (long long)(x.bytes[j] >> 4);
+            for (long long i = gtid; i < nchunk; i += gstride) dst[i] = __ldcg(src + i);
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int t = atomicAdd(p.ticket, 1u);
+            const int last = (t == gridDim.x - 1);
+            if (last) {
+                *p.ticket = 0u;
+                __threadfence_system();
+                for (int s = 0; s < x.nsignal; ++s) red_release_sys_add_u32(x.signal[s], 1u);
+            }
+            is_waiter = last;
+        }
+    } else if (threadIdx.x == 0) {
+        is_waiter = (blockIdx.x == 0);
+    }
+    __syncthreads();
+    if (!(x.mode & MGFEA_XCHG_WAIT) || !is_waiter || threadIdx.x != 0) return;
+    // ---- wait for the ranks that push to this one
+    const unsigned int expect = *x.seq + 1u;
+    const long long t0 = clock64();
+    for (int w = 0; w < x.nwait; ++w) {
+        while ((int)(ld_acquire_sys_u32(x.wait[w]) - expect) < 0) {
+            if (clock64() - t0 > p.timeout_clocks) {
+                if (x.err) *x.err = 1 + w;
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+    *x.seq = expect;
+    // ---- optional reduction of the slots the peers filled (fixed rank order: identical result on every rank)
+    if (x.nred > 0 && x.red_dst != nullptr) {
+        double s = 0.0;
+        for (int i = 0; i < x.nred; ++i) s += __ldcg(reinterpret_cast<const double *>(
+                                               reinterpret_cast<const unsigned char *>(x.red_src) + (size_t)i * x.red_stride));
+        *x.red_dst = s;
+    }
+}
+
+}  // namespace mgfea

@@ -492,7 +492,7 @@ def test_full_size_properties_4097():
 
 
 # ------------------------------------------------------------------------------------------ row slabs (multi-GPU path)
-def _slab_worker(rank, world, n, dist_min_n, port, ret):
+def _slab_worker(rank, world, n, dist_min_n, port, p2p, ret):
     import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -508,28 +508,32 @@ def _slab_worker(rank, world, n, dist_min_n, port, ret):
         rs = np.random.RandomState(3)
         u0 = rs.standard_normal((n + 1, n + 1)).astype(np.float32)
         f = 0.01 * rs.standard_normal((n + 1, n + 1)).astype(np.float32)
-        mg = SlabMultigrid(n, dist_min_n=dist_min_n)
+        mg = SlabMultigrid(n, dist_min_n=dist_min_n, p2p=p2p)
         mg.set_problem(torch.from_numpy(u0), torch.from_numpy(f))
         hist = mg.Solve(n_iter=3)
         sol = mg.gather_solution()
         if rank == 0:
             ret["hist"], ret["sol"], ret["ld"] = hist, sol.numpy(), mg.part.ld
+            ret["peer"], ret["peer_error"] = mg.peer is not None, getattr(mg, "peer_error", None)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n,dist_min_n", [(2, 512, 129), (4, 1024, 257)])
-def test_slab_kernels_match_single_gpu(world, n, dist_min_n):
+@pytest.mark.parametrize("world,n,dist_min_n,p2p", [(2, 512, 129, False), (4, 1024, 257, False), (2, 512, 129, True),
+                                                     (4, 1024, 257, True), (8, 2048, 257, True)])
+def test_slab_kernels_match_single_gpu(world, n, dist_min_n, p2p):
     """the CUDA slab operators (mgfea_slab_*) + halo exchange + coarse agglomeration, ranks emulated as processes on one
-    GPU, against the single-GPU cycle: bit-identical solution, same residuals"""
+    GPU, against the single-GPU cycle: bit-identical solution, same residuals.  p2p=False: exchanges staged through the
+    host (gloo); p2p=True: the peer-memory exchange kernels (mgfea_p2p_exchange) over cudaIpc-mapped blocks"""
     import torch.multiprocessing as mp
 
     from FEANet.drivers import Multigrid
 
     mgr = mp.Manager()
     ret = mgr.dict()
-    port = 29700 + (os.getpid() % 1000) + world
-    mp.spawn(_slab_worker, args=(world, n, dist_min_n, port, ret), nprocs=world, join=True)
+    port = 29700 + (os.getpid() % 1000) + world + (10 if p2p else 0)
+    mp.spawn(_slab_worker, args=(world, n, dist_min_n, port, p2p, ret), nprocs=world, join=True)
+    assert ret["peer"] == p2p, ret["peer_error"]
     rs = np.random.RandomState(3)
     u0 = rs.standard_normal((n + 1, n + 1)).astype(np.float32)
     f = 0.01 * rs.standard_normal((n + 1, n + 1)).astype(np.float32)
