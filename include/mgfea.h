@@ -81,6 +81,9 @@ const char *mgfea_version(void);
 const char *mgfea_error_string(int code);
 /* 0 = cp.async tile loader, 1 = TMA (cp.async.bulk.tensor) tile loader [default]; returns previous value */
 int mgfea_set_loader(int use_tma);
+/* profiling aid: while buf != NULL a one-thread kernel stores %globaltimer (ns) into buf[i++] before and after every
+ * fused-leg launch of mgfea_vcycle (i restarts at 0 on every call of mgfea_trace); buf = NULL switches it off */
+int mgfea_trace(unsigned long long *buf, int capacity);
 /* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
 uint64_t mgfea_launch_count(void);
 

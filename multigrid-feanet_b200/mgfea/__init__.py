@@ -29,7 +29,7 @@ EXPORTS = [
     "mgfea_residual_norm", "mgfea_vcycle", "mgfea_restrict_channels", "mgfea_prolong_channels",
     "mgfea_slab_smooth_residual_restrict", "mgfea_slab_prolong_correct_smooth",
     "mgfea_peer_alloc", "mgfea_peer_free", "mgfea_peer_export", "mgfea_peer_open", "mgfea_peer_close",
-    "mgfea_p2p_exchange",
+    "mgfea_p2p_exchange", "mgfea_trace",
 ]
 
 
@@ -112,6 +112,7 @@ def lib():
         vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
         G = ctypes.POINTER(Grid)
         L.mgfea_set_loader.argtypes = [i32]
+        L.mgfea_trace.argtypes = [vp, i32]
         L.mgfea_pack.argtypes = [vp, vp, i32, i32, i64, i32, vp]
         L.mgfea_unpack.argtypes = [vp, vp, i32, i32, i64, i32, vp]
         L.mgfea_stiffness_apply.argtypes = [G, vp, vp, i32, vp]

@@ -15,6 +15,7 @@
 #include "mgfea_tail.cuh"
 #include "mgfea_stream.cuh"
 #include "mgfea_p2p.cuh"
+#include "mgfea_mid.cuh"
 
 #ifndef MGFEA_MINBLOCKS
 #define MGFEA_MINBLOCKS 3
@@ -501,6 +502,19 @@ __global__ void prolong_channels_kernel(const float *__restrict__ eFC, float *__
 // host side
 // =========================================================================================================
 static std::atomic<uint64_t> g_launches{0};
+
+// ---- optional timeline trace (tools/cycle_trace.py): a one-thread kernel writes %globaltimer before / after every
+// program launch into a caller-provided buffer; slots are handed out in launch order (graph capture freezes them)
+static unsigned long long *g_trace_buf = nullptr;
+static int g_trace_cap = 0, g_trace_idx = 0;
+__global__ void trace_stamp_kernel(unsigned long long *slot) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    *slot = t;
+}
+static void trace_stamp(cudaStream_t st) {
+    if (g_trace_buf && g_trace_idx < g_trace_cap) trace_stamp_kernel<<<1, 1, 0, st>>>(g_trace_buf + g_trace_idx++);
+}
 static std::atomic<int> g_use_tma{1};
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -680,7 +694,11 @@ struct Knobs {
     int stream_min_n = 129;   // levels with N >= this use the register-chained streaming kernels (0 disables)
     int stream_r = 0;         // rows per strip (0 = auto)
     int stream_packed = 1;    // 1: FFMA2 (fma.rn.f32x2) streaming kernels, 0: scalar FFMA
+    int mid_min_n = 66;       // coarse levels with mid_min_n <= N <= mid_max_n use the latency-oriented mid kernels
+    int mid_max_n = 513;      // (mid_max_n = 0 disables them; at 1025 the streaming kernels win: profiles/)
     Knobs() {
+        if (const char *e = getenv("MGFEA_MID_MIN_N")) mid_min_n = atoi(e);
+        if (const char *e = getenv("MGFEA_MID_MAX_N")) mid_max_n = atoi(e);
         if (const char *e = getenv("MGFEA_TH")) th = atoi(e);
         if (const char *e = getenv("MGFEA_STAGES")) stages = atoi(e);
         if (const char *e = getenv("MGFEA_CTAS")) ctas = atoi(e);
@@ -847,7 +865,70 @@ static int run_stream(const Program &pr, cudaStream_t st) {
     return (int)cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// mid-level kernels (mgfea_mid.cuh): eligibility + launch
+static int mid_mode(const Program &pr, bool keys, bool gbc) {
+    const Knobs &k = knobs();
+    if (k.mid_max_n <= 0 || pr.g->N < k.mid_min_n || pr.g->N > k.mid_max_n) return -1;
+    if (keys || gbc || pr.reset_only || pr.ktab_override || pr.slab) return -1;
+    if (pr.smoother != MGFEA_SMOOTH_JACOBI || pr.nsweeps != 1 || !pr.u_out || !pr.f) return -1;
+    if (pr.out_mode == OUT_RESTRICT && pr.prolong_mode == 0 && pr.rtab_n == 1 && pr.u_in == nullptr) return 0;
+    if (pr.prolong_mode == MGFEA_PROLONG_BILINEAR && pr.out_mode == OUT_NONE && pr.u_in != nullptr) return 1;
+    return -1;
+}
+
+static int run_mid(const Program &pr, int mode, cudaStream_t st) {
+    const mgfea_grid *g = pr.g;
+    MidParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = g->N;
+    p.B = pr.B;
+    p.pitch = g->pitch;
+    p.plane = g->plane;
+    p.nt = (g->N + MID_T - 1) / MID_T;
+    const long long total = (long long)p.nt * p.nt * pr.B;
+    if (total >= (1 << 24)) return MGFEA_EUNSUPPORTED;
+    p.inv_per = 1.0f / (float)(p.nt * p.nt);
+    p.inv_nt = 1.0f / (float)p.nt;
+    p.u_in = pr.u_in;
+    p.u_out = pr.u_out;
+    p.f = pr.f;
+    p.ktab = g->ktab;
+    p.invd = g->invd;
+    p.Nc = (g->N - 1) / 2 + 1;
+    p.ctl = pr.ctl;
+    if (mode == 0) {
+        if (!pr.fc || !pr.rtab) return MGFEA_EINVAL;
+        p.fc = pr.fc;
+        p.pitch_c = pr.pitch_c;
+        p.plane_c = pr.plane_c;
+        p.rtab = pr.rtab;
+        p.r_has_scale = pr.r_has_scale;
+        p.r_scale = pr.r_scale;
+        p.r_scale_dev = pr.r_scale_dev;
+        launch_pdl(mg_mid_kernel<0>, (int)total, MID_THREADS, 0, st, p);
+    } else {
+        if (!pr.vc || !pr.gc || pr.gc->N != p.Nc) return MGFEA_EINVAL;
+        int rc = check_field(pr.vc, pr.gc->pitch, pr.gc->plane);
+        if (rc) return rc;
+        p.vc = pr.vc;
+        p.pitch_c = pr.gc->pitch;
+        p.plane_c = pr.gc->plane;
+        p.prolong_seq = (g->N <= 33);
+        launch_pdl(mg_mid_kernel<1>, (int)total, MID_THREADS, 0, st, p);
+    }
+    g_launches.fetch_add(1);
+    return (int)cudaGetLastError();
+}
+
+static int run_program_(const Program &pr, cudaStream_t st);
 static int run_program(const Program &pr, cudaStream_t st) {
+    trace_stamp(st);
+    const int rc = run_program_(pr, st);
+    trace_stamp(st);
+    return rc;
+}
+static int run_program_(const Program &pr, cudaStream_t st) {
     const mgfea_grid *g = pr.g;
     if (!g || g->N < 3 || pr.B < 1) return MGFEA_EINVAL;
     if (g->pitch < g->N || (g->pitch & 3)) return MGFEA_EALIGN;
@@ -856,6 +937,13 @@ static int run_program(const Program &pr, cudaStream_t st) {
     const bool gbc = (g->bc_idx != nullptr) && (pr.nsweeps > 0 || pr.reset_only || pr.prolong_mode == 1);
     if (keys && (g->key_pitch & 15)) return MGFEA_EALIGN;
     int rc;
+    const int mmode = mid_mode(pr, keys, gbc);
+    if (mmode >= 0) {
+        if (pr.u_in && (rc = check_field(pr.u_in, g->pitch, g->plane))) return rc;
+        if ((rc = check_field(pr.u_out, g->pitch, g->plane))) return rc;
+        if ((rc = check_field(pr.f, g->pitch, g->plane))) return rc;
+        return run_mid(pr, mmode, st);
+    }
     if (stream_eligible(pr, keys, gbc)) {
         if (pr.u_in && (rc = check_field(pr.u_in, g->pitch, g->plane))) return rc;
         if ((rc = check_field(pr.u_out, g->pitch, g->plane))) return rc;
@@ -1187,6 +1275,7 @@ static int run_tail(const mgfea_grid *grids, const mgfea_level_bufs *bufs, int l
     p.p_scale = cfg->p_scale_host;
     p.p_scale_dev = cfg->p_scale_dev;
     p.ctl = ctl;
+    p.trace = (g_trace_buf && g_trace_cap >= 192) ? reinterpret_cast<long long *>(g_trace_buf + 128) : nullptr;
     if (hj && (!cfg->hw || cfg->nlayers < 1 || cfg->nlayers > MAXLAYERS)) return MGFEA_EINVAL;
     static bool configured[2] = {false, false};
     cudaError_t e;
@@ -1237,6 +1326,12 @@ const char *mgfea_error_string(int code) {
     }
 }
 
+int mgfea_trace(unsigned long long *buf, int capacity) {
+    g_trace_buf = buf;
+    g_trace_cap = buf ? capacity : 0;
+    g_trace_idx = 0;
+    return 0;
+}
 int mgfea_set_loader(int use_tma) { return g_use_tma.exchange(use_tma ? 1 : 0); }
 uint64_t mgfea_launch_count(void) { return g_launches.load(); }
 
@@ -1677,7 +1772,10 @@ int mgfea_vcycle(const mgfea_grid *grids, const mgfea_level_bufs *bufs, int nlev
             if ((rc = run_chain(pr, cur[0], bufs[0].u, bufs[0].u_alt, cfg->nu1 * (L - lt), &res, st))) return rc;
             cur[0] = res;
         }
-        if ((rc = run_tail(grids, bufs, lt, L, cfg, ctl, B, st))) return rc;
+        trace_stamp(st);
+        rc = run_tail(grids, bufs, lt, L, cfg, ctl, B, st);
+        trace_stamp(st);
+        if (rc) return rc;
         cur[lt] = bufs[lt].u;
     }
     // ---- up leg

@@ -193,7 +193,9 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream_kernel(const Strea
     const float inv = p.invd[0];
     const float rscale = (MODE == 0 && p.r_has_scale) ? (p.r_scale_dev ? *p.r_scale_dev : p.r_scale) : 1.0f;
     pdl_wait();  // weights above are never written by a kernel; all field data is touched only after this point
-    if (p.ctl != nullptr && ld_volatile_s32(&reinterpret_cast<const Ctl *>(p.ctl)->done) != 0) return;
+    // the solve-control word is requested here but tested only after the first prefetches are in flight, so the two
+    // memory round trips overlap (a finished solve returns before anything is stored)
+    const int solve_done = (p.ctl != nullptr) ? ld_volatile_s32(&reinterpret_cast<const Ctl *>(p.ctl)->done) : 0;
 
     // ---- per-lane prefetch ring: [slot][lane] float4 for u and for f, float2 for the coarse row (up leg)
     float4 *ring_u = reinterpret_cast<float4 *>(st_smem) + warp * (ST_RING_F4 * 32);
@@ -282,6 +284,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream_kernel(const Strea
         };
 #pragma unroll
         for (int k = 0; k < ST_DEPTH - 1; ++k) prefetch(std::true_type{}, k);
+        if (solve_done) break;
 
         // rotating windows (indices are compile-time after unrolling by 6)
         R6 A[3];      // input rows (u0, or corrected u for the up leg): a-2, a-1, a
@@ -389,9 +392,14 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream_kernel(const Strea
                         if (MODE == 1) {
                             if (p.want_norm && lane_int && (!GUARD || (yr >= y0 && yr < y1)) &&
                                 (!EDGE || (yr >= 1 && yr <= N - 2))) {
+                                // squares of the lane's 4 columns summed in fp32 (fixed order), rows in fp64: one
+                                // F2F + DADD per row instead of eight FP64-pipe instructions
                                 const float4 q = EDGE ? mask4(r, cin) : r;
-                                part += (double)q.x * (double)q.x + (double)q.y * (double)q.y;
-                                part += (double)q.z * (double)q.z + (double)q.w * (double)q.w;
+                                float s4 = __fmul_rn(q.x, q.x);
+                                s4 = __fmaf_rn(q.y, q.y, s4);
+                                s4 = __fmaf_rn(q.z, q.z, s4);
+                                s4 = __fmaf_rn(q.w, q.w, s4);
+                                part += (double)s4;
                             }
                         } else {
                             R6 rr;
@@ -458,6 +466,10 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream_kernel(const Strea
         }
     }
 
+    if (solve_done) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        return;
+    }
     // ---- deterministic final reduction of the per-strip partial sums by the last CTA to finish
     if (MODE == 1 && p.want_norm) {
         __threadfence();
@@ -534,7 +546,9 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
     const u64 inv2 = pack2(inv, inv);
     const float rscale = (MODE == 0 && p.r_has_scale) ? (p.r_scale_dev ? *p.r_scale_dev : p.r_scale) : 1.0f;
     pdl_wait();  // weights above are never written by a kernel; all field data is touched only after this point
-    if (p.ctl != nullptr && ld_volatile_s32(&reinterpret_cast<const Ctl *>(p.ctl)->done) != 0) return;
+    // the solve-control word is requested here but tested only after the first prefetches are in flight, so the two
+    // memory round trips overlap (a finished solve returns before anything is stored)
+    const int solve_done = (p.ctl != nullptr) ? ld_volatile_s32(&reinterpret_cast<const Ctl *>(p.ctl)->done) : 0;
 
     // ---- per-lane prefetch ring: [slot][lane] float4 for u and for f, float2 for the coarse row (up leg)
     float4 *ring_u = reinterpret_cast<float4 *>(st_smem) + warp * (ST_RING_F4 * 32);
@@ -623,6 +637,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
         };
 #pragma unroll
         for (int k = 0; k < ST_DEPTH - 3; ++k) prefetch(std::true_type{}, k);
+        if (solve_done) break;
 
         // rotating windows (indices are compile-time after unrolling by 6)
         RP A[3];   // input rows (u0, or corrected u for the up leg): a-2, a-1, a
@@ -735,9 +750,14 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
                         if (MODE == 1) {
                             if (p.want_norm && lane_int && (!GUARD || (yr >= y0 && yr < y1)) &&
                                 (!EDGE || (yr >= 1 && yr <= N - 2))) {
+                                // squares of the lane's 4 columns summed in fp32 (fixed order), rows in fp64: one
+                                // F2F + DADD per row instead of eight FP64-pipe instructions
                                 const float4 q = EDGE ? mask4(r, cin) : r;
-                                part += (double)q.x * (double)q.x + (double)q.y * (double)q.y;
-                                part += (double)q.z * (double)q.z + (double)q.w * (double)q.w;
+                                float s4 = __fmul_rn(q.x, q.x);
+                                s4 = __fmaf_rn(q.y, q.y, s4);
+                                s4 = __fmaf_rn(q.z, q.z, s4);
+                                s4 = __fmaf_rn(q.w, q.w, s4);
+                                part += (double)s4;
                             }
                         } else {
                             R6 rr;
@@ -804,6 +824,10 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
         }
     }
 
+    if (solve_done) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        return;
+    }
     // ---- deterministic final reduction of the per-strip partial sums by the last CTA to finish
     if (MODE == 1 && p.want_norm) {
         __threadfence();

@@ -47,6 +47,7 @@ struct TailParams {
     float p_scale;
     const float *p_scale_dev;
     void *ctl;
+    long long *trace;  // optional: thread 0 appends clock64() after every stage (profiling aid, see mgfea_trace)
 };
 
 struct TailTabs {  // shared by all levels
@@ -278,6 +279,11 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail_kernel(const TailPara
     __shared__ TailTabs T;
     pdl_launch_dependents();
     const int tid = threadIdx.x, b = blockIdx.x;
+    int ntrace = 0;
+    auto stamp = [&]() {
+        if (p.trace != nullptr && tid == 0 && b == 0 && ntrace < 64) p.trace[ntrace++] = clock64();
+    };
+    stamp();
     // ---- zero all fields (ghost cells / pads / zero initial guesses), load tables and keys
     for (int i = tid; i < p.total_floats / 4; i += blockDim.x)
         reinterpret_cast<float4 *>(sm)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -291,6 +297,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail_kernel(const TailPara
         T.p_scale = p.p_scale_dev ? *p.p_scale_dev : p.p_scale;
     }
     __syncthreads();
+    stamp();
     float *tabs = sm + p.off_tab;
     for (int l = 0; l < p.nlev; ++l) {
         const TailLevel &L = p.lv[l];
@@ -306,8 +313,10 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail_kernel(const TailPara
             }
         }
     }
+    stamp();
     pdl_wait();  // tables / keys above are never written by a kernel; the restricted rhs below is
-    if (p.ctl != nullptr && ld_volatile_s32(&reinterpret_cast<const Ctl *>(p.ctl)->done) != 0) return;
+    stamp();
+    const int solve_done = (p.ctl != nullptr) ? ld_volatile_s32(&reinterpret_cast<const Ctl *>(p.ctl)->done) : 0;
     {
         const TailLevel &L = p.lv[0];
         const float *fin = p.f_in + (long long)b * p.plane;
@@ -317,7 +326,9 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail_kernel(const TailPara
             f[t_node(L, y, x)] = fin[(long long)y * p.pitch + x];
         }
     }
+    if (solve_done) return;
     __syncthreads();
+    stamp();
 
     // current solution buffer per level (ping-pong between off_u / off_v)
     int cur[TAIL_MAXLEV];
@@ -333,15 +344,18 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail_kernel(const TailPara
             if (p.smoother == 0) {
                 t_jacobi<KEYS>(sm, smraw, L, tb, tb + MAXPAT * 9, src, dst, nullptr);
                 __syncthreads();
+                stamp();
             } else {
                 // J -> tmp0, x -> tmp1, layers ping-pong tmp1/tmp2, last layer adds J into dst
                 t_jacobi<KEYS>(sm, smraw, L, tb, tb + MAXPAT * 9, src, tmp0, tmp1);
                 __syncthreads();
+                stamp();
                 float *a = tmp1, *bb = tmp2;
                 for (int q = 0; q < p.nlayers; ++q) {
                     const bool last = (q == p.nlayers - 1);
                     t_hlayer(L, T.hw + 9 * q, a, last ? dst : bb, last ? tmp0 : nullptr);
                     __syncthreads();
+                    stamp();
                     float *sw = a;
                     a = bb;
                     bb = sw;
@@ -360,8 +374,10 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail_kernel(const TailPara
             const float *u = sm + (cur[l] ? L.off_v : L.off_u);
             t_residual<KEYS>(sm, smraw, L, tb, u, sm + L.off_t0);
             __syncthreads();
+            stamp();
             t_restrict<KEYS>(sm, smraw, L, p.lv[l + 1], T, p, sm + L.off_t0);
             __syncthreads();
+            stamp();
         }
     }
     // ---- up leg
@@ -372,6 +388,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail_kernel(const TailPara
             const float *vc = sm + (cur[l + 1] ? C.off_v : C.off_u);
             t_prolong<KEYS>(sm, smraw, L, C, T, p, vc, u);
             __syncthreads();
+            stamp();
         }
         relax(l, p.nu2);
     }
@@ -387,6 +404,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail_kernel(const TailPara
             *reinterpret_cast<float4 *>(uo + (long long)y * p.pitch + 4 * g) = v;
         }
     }
+    stamp();
 }
 
 }  // namespace mgfea

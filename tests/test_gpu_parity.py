@@ -239,7 +239,9 @@ def engine_vs_oracle(O, jacs, levels, cfg, eng_kw, u0, f, ncyc=3, name=""):
         exact(host(eng.solution)[:, 0], uo, f"{name} u after cycle {c + 1}")
         ss = host(eng.sumsq)
         ref = O.sumsq_interior(O.residual(uo, f, levels[0].keys, levels[0].ktab))
-        assert np.allclose(ss, ref, rtol=1e-12, atol=0), (name, ss, ref)
+        # streaming kernels: the 4 squares of a lane's column group are summed in fp32 before the fp64 accumulation
+        # (<= 2e-7 relative, far inside the 1e-5 the north star asks for; the reference itself sums in fp32)
+        assert np.allclose(ss, ref, rtol=2e-7, atol=0), (name, ss, ref)
     return eng
 
 
