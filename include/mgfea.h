@@ -172,8 +172,8 @@ int mgfea_peer_close(void *ptr);
 
 #define MGFEA_XCHG_MAX_JOBS 16
 #define MGFEA_XCHG_MAX_PEERS 8
-#define MGFEA_XCHG_PUSH 1 /* run the copy jobs, then increment every `signal` flag (release, system scope) */
-#define MGFEA_XCHG_WAIT 2 /* wait until every `wait` flag has reached *seq + 1, then advance *seq */
+#define MGFEA_XCHG_PUSH 1 /* run the copy jobs; every CTA then increments every `signal` flag once (system scope) */
+#define MGFEA_XCHG_WAIT 2 /* wait until every `wait` flag has reached *seq + grid, then advance *seq by grid */
 /* One exchange step of one rank (a single kernel, graph-capturable).  All addresses and sizes are multiples of 16 B. */
 typedef struct mgfea_xchg {
     int32_t njobs, nsignal, nwait, mode;
@@ -182,11 +182,13 @@ typedef struct mgfea_xchg {
     uint64_t bytes[MGFEA_XCHG_MAX_JOBS];
     uint32_t *signal[MGFEA_XCHG_MAX_PEERS];     /* flags in the TARGET ranks' mailboxes */
     const uint32_t *wait[MGFEA_XCHG_MAX_PEERS]; /* flags in THIS rank's mailbox, incremented by the ranks pushing to it */
-    uint32_t *seq;   /* this rank's count of completed steps on this flag set (device memory, advanced by the kernel) */
+    uint32_t *seq;   /* this rank's expected flag value for this flag set (device memory, advanced by the kernel) */
     int32_t *err;    /* device word set to 1 + index of the flag whose wait timed out (dead peer); may be NULL */
     const double *red_src; /* optional: after the wait, *red_dst = sum of nred doubles spaced red_stride bytes apart */
     double *red_dst;
     int32_t nred, red_stride;
+    int32_t grid;    /* CTAs of this step, 1..64: MUST be the same on every rank (a flag counts the pushing CTAs) */
+    int32_t pad_;
 } mgfea_xchg;
 int mgfea_p2p_exchange(const mgfea_xchg *x, void *stream);
 
@@ -210,6 +212,9 @@ typedef struct mgfea_cycle_cfg {
     int32_t quirk_level0;  /* MM_Interface_error.ipynb cell 2: pre-smooth is always applied to level 0 */
     int32_t tail_max_n;    /* levels with N <= tail_max_n run inside the single coarse-tail kernel (0: default) */
     int32_t compute_norm;  /* 1: fuse the interior residual norm of level 0 into the last kernel */
+    int32_t zero_guess;    /* 1: level 0 starts from u = 0 (bufs[0].u is output only): the replicated coarse cycle of the
+                              row-slab path, i.e. the `v = zeros` of every coarse level (multigrid.py:171) */
+    int32_t pad_;
 } mgfea_cycle_cfg;
 
 /* Per-level buffers of one V-cycle: u ping-pong pair and f.  After the call the result is in u[0] again. */

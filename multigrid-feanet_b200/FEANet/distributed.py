@@ -171,6 +171,11 @@ class PeerSlabMemory:
             x.seq = me + self.SEQ_NB
         x.njobs, x.nsignal, x.nwait, x.err = j, ns, nw, me + self.ERR
         x.mode = mg.XCHG_PUSH | mg.XCHG_WAIT
+        # CTAs of the step: a function of the step alone (NOT of the rank): the flags count the pushing CTAs.  About one
+        # 16-byte chunk per thread for the halo rows, more CTAs when whole coarse slabs travel
+        halo_chunks = sum(GHOST * self.pitch[l] * 4 // 16 for _, l in halos) * 2
+        gather_chunks = ((part.n // 2 ** part.ld) // world) * self.pitch[part.ld] * 4 // 16 * (world - 1) if gather else 0
+        x.grid = int(min(64, max(1, (halo_chunks + gather_chunks // 4 + 255) // 256)))
         return x
 
     def step(self, halos, gather=False, reduce=False):
@@ -209,8 +214,11 @@ class CudaSlabOps:
             mesh = MeshSquare(2, n // 2 ** l + 1)
             self.jacs.append(JacobiBlock(KNet(mesh), mesh, 2 / 3., None, None))
         self.rtab = torch.from_numpy(FULL_WEIGHTING_16.reshape(1, 9).copy()).to(self.dev)
-        self.coarse = VCycleEngine(self.jacs[part.ld:], B=1, nu1=nu1, nu2=nu2, f0_store=coarse_f_store) \
-            if part.ld < L else None
+        # the replicated coarse cycle always starts from a zero guess and nobody reads its residual norm -- unless it IS
+        # the whole problem (ld == 0: single rank / tiny grids)
+        sub = part.ld > 0
+        self.coarse = VCycleEngine(self.jacs[part.ld:], B=1, nu1=nu1, nu2=nu2, f0_store=coarse_f_store,
+                                   compute_norm=not sub, zero_guess=sub) if part.ld < L else None
         self._sumsq = torch.zeros(1, dtype=torch.float64, device=self.dev)
 
     def alloc(self, l):
@@ -257,7 +265,6 @@ class CudaSlabOps:
 
     def coarse_cycle(self):
         """one V-cycle from a zero guess on the replicated levels; rhs / result live in the engine's level-0 buffers"""
-        self.coarse.u[0].store.zero_()
         self.coarse.cycle()
 
     def full_cycle_single(self, u, f):

@@ -24,7 +24,7 @@ class VCycleEngine:
 
     def __init__(self, jacs, B=1, nu1=1, nu2=1, smoother="jac", hnet=None, prolong="bilinear", rtab=None, r_scale=4.0,
                  ptab=None, p_scale=None, w_param=None, quirk_level0=False, conv_rule=mgfea.CONV_SUM,
-                 max_cycles=256, f0_store=None):
+                 max_cycles=256, f0_store=None, compute_norm=True, zero_guess=False):
         self.dev = mgfea.require_cuda()
         self.jacs = list(jacs)
         self.L = len(self.jacs)
@@ -36,6 +36,7 @@ class VCycleEngine:
         self.quirk_level0 = quirk_level0
         self.conv_rule = conv_rule
         self.max_cycles = max_cycles
+        self.compute_norm, self.zero_guess = bool(compute_norm), bool(zero_guess)
         self._rtab_src = rtab  # numpy array, torch tensor / Parameter (live) or None (full weighting /16)
         self._ptab_src = ptab
         self.r_scale, self.p_scale = r_scale, p_scale
@@ -106,7 +107,8 @@ class VCycleEngine:
             cfg.p_has_scale = int(self.p_scale is not None)
             cfg.p_scale_host = float(self.p_scale or 0.0)
         cfg.quirk_level0 = int(self.quirk_level0)
-        cfg.compute_norm = 1
+        cfg.compute_norm = int(self.compute_norm)
+        cfg.zero_guess = int(self.zero_guess)
         self._cfg = cfg
         self._keep = keep
         sig = (cfg.hw, cfg.rtab, cfg.ptab, cfg.r_scale_dev, tuple(g.ktab for g in grids), tuple(g.bc_idx for g in grids),

@@ -70,7 +70,7 @@ class CycleCfg(ctypes.Structure):
                 ("r_has_scale", ctypes.c_int32), ("ptab", ctypes.c_void_p), ("r_scale_host", ctypes.c_float),
                 ("p_scale_host", ctypes.c_float), ("r_scale_dev", ctypes.c_void_p), ("p_scale_dev", ctypes.c_void_p),
                 ("p_has_scale", ctypes.c_int32), ("quirk_level0", ctypes.c_int32), ("tail_max_n", ctypes.c_int32),
-                ("compute_norm", ctypes.c_int32)]
+                ("compute_norm", ctypes.c_int32), ("zero_guess", ctypes.c_int32), ("pad_", ctypes.c_int32)]
 
 
 class Slab(ctypes.Structure):
@@ -87,7 +87,8 @@ class Xchg(ctypes.Structure):
                 ("dst", ctypes.c_void_p * XCHG_MAX_JOBS), ("bytes", ctypes.c_uint64 * XCHG_MAX_JOBS),
                 ("signal", ctypes.c_void_p * XCHG_MAX_PEERS), ("wait", ctypes.c_void_p * XCHG_MAX_PEERS),
                 ("seq", ctypes.c_void_p), ("err", ctypes.c_void_p), ("red_src", ctypes.c_void_p),
-                ("red_dst", ctypes.c_void_p), ("nred", ctypes.c_int32), ("red_stride", ctypes.c_int32)]
+                ("red_dst", ctypes.c_void_p), ("nred", ctypes.c_int32), ("red_stride", ctypes.c_int32),
+                ("grid", ctypes.c_int32), ("pad_", ctypes.c_int32)]
 
 
 class LevelBufs(ctypes.Structure):

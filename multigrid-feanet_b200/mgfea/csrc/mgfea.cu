@@ -695,10 +695,12 @@ struct Knobs {
     int stream_r = 0;         // rows per strip (0 = auto)
     int stream_packed = 1;    // 1: FFMA2 (fma.rn.f32x2) streaming kernels, 0: scalar FFMA
     int mid_min_n = 66;       // coarse levels with mid_min_n <= N <= mid_max_n use the latency-oriented mid kernels
-    int mid_max_n = 513;      // (mid_max_n = 0 disables them; at 1025 the streaming kernels win: profiles/)
+    int mid_max_n = 513;      // (mid_max_n = 0 disables them; at 1025 the streaming DOWN kernel wins: profiles/)
+    int mid_max_n_up = 1025;  // the up leg stays ahead one level longer
     Knobs() {
         if (const char *e = getenv("MGFEA_MID_MIN_N")) mid_min_n = atoi(e);
-        if (const char *e = getenv("MGFEA_MID_MAX_N")) mid_max_n = atoi(e);
+        if (const char *e = getenv("MGFEA_MID_MAX_N")) mid_max_n = mid_max_n_up = atoi(e);
+        if (const char *e = getenv("MGFEA_MID_MAX_N_UP")) mid_max_n_up = atoi(e);
         if (const char *e = getenv("MGFEA_TH")) th = atoi(e);
         if (const char *e = getenv("MGFEA_STAGES")) stages = atoi(e);
         if (const char *e = getenv("MGFEA_CTAS")) ctas = atoi(e);
@@ -869,11 +871,14 @@ static int run_stream(const Program &pr, cudaStream_t st) {
 // mid-level kernels (mgfea_mid.cuh): eligibility + launch
 static int mid_mode(const Program &pr, bool keys, bool gbc) {
     const Knobs &k = knobs();
-    if (k.mid_max_n <= 0 || pr.g->N < k.mid_min_n || pr.g->N > k.mid_max_n) return -1;
+    const int mmax = k.mid_max_n > k.mid_max_n_up ? k.mid_max_n : k.mid_max_n_up;
+    if (mmax <= 0 || pr.g->N < k.mid_min_n || pr.g->N > mmax) return -1;
     if (keys || gbc || pr.reset_only || pr.ktab_override || pr.slab) return -1;
     if (pr.smoother != MGFEA_SMOOTH_JACOBI || pr.nsweeps != 1 || !pr.u_out || !pr.f) return -1;
-    if (pr.out_mode == OUT_RESTRICT && pr.prolong_mode == 0 && pr.rtab_n == 1 && pr.u_in == nullptr) return 0;
-    if (pr.prolong_mode == MGFEA_PROLONG_BILINEAR && pr.out_mode == OUT_NONE && pr.u_in != nullptr) return 1;
+    if (pr.out_mode == OUT_RESTRICT && pr.prolong_mode == 0 && pr.rtab_n == 1 && pr.u_in == nullptr)
+        return pr.g->N <= k.mid_max_n ? 0 : -1;
+    if (pr.prolong_mode == MGFEA_PROLONG_BILINEAR && pr.out_mode == OUT_NONE && pr.u_in != nullptr)
+        return pr.g->N <= k.mid_max_n_up ? 1 : -1;
     return -1;
 }
 
@@ -1581,7 +1586,10 @@ int mgfea_slab_smooth_residual_restrict(const mgfea_grid *g, const mgfea_slab *s
     pr.r_scale = scale_host;
     pr.r_scale_dev = scale_dev;
     if ((rc = check_field(u_out, g->pitch, g->plane)) || (rc = check_field(f, g->pitch, g->plane))) return rc;
-    return run_stream(pr, (cudaStream_t)stream);
+    trace_stamp((cudaStream_t)stream);
+    rc = run_stream(pr, (cudaStream_t)stream);
+    trace_stamp((cudaStream_t)stream);
+    return rc;
 }
 
 int mgfea_slab_prolong_correct_smooth(const mgfea_grid *g, const mgfea_slab *s, const float *vc, const mgfea_slab *sc,
@@ -1602,7 +1610,10 @@ int mgfea_slab_prolong_correct_smooth(const mgfea_grid *g, const mgfea_slab *s, 
     pr.out_mode = sumsq ? OUT_NORM : OUT_NONE;
     pr.sumsq = sumsq;
     if ((rc = check_field(u_out, g->pitch, g->plane)) || (rc = check_field(f, g->pitch, g->plane))) return rc;
-    return run_stream(pr, (cudaStream_t)stream);
+    trace_stamp((cudaStream_t)stream);
+    rc = run_stream(pr, (cudaStream_t)stream);
+    trace_stamp((cudaStream_t)stream);
+    return rc;
 }
 
 /* ---- peer memory + exchange (mgfea_p2p.cuh) -------------------------------------------------------------- */
@@ -1654,30 +1665,23 @@ int mgfea_p2p_exchange(const mgfea_xchg *x, void *stream) {
             return MGFEA_EALIGN;
         total += x->bytes[j];
     }
-    DeviceScratch *scr = nullptr;
-    int rc = get_scratch(1, &scr);
-    if (rc) return rc;
+    if (x->grid < 1 || x->grid > 64) return MGFEA_EINVAL;
     XchgParams p;
     p.x = *x;
-    p.ticket = scr->counter + 8;  // separate word from the residual-norm ticket
-    int khz = 0;
     static long long clocks_per_s = 0;
     if (clocks_per_s == 0) {
-        int dev = 0;
+        int dev = 0, khz = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev);
         clocks_per_s = khz > 0 ? (long long)khz * 1000 : 2000000000LL;
     }
     const char *te = getenv("MGFEA_P2P_TIMEOUT_S");
     p.timeout_clocks = clocks_per_s * (te ? atoll(te) : 5);
-    int grid = 1;
-    if (x->mode & MGFEA_XCHG_PUSH) {
-        const unsigned long long chunks = total >> 4;
-        grid = (int)((chunks + XCHG_THREADS * 4 - 1) / (XCHG_THREADS * 4));  // about 4 chunks per thread
-        if (grid < 1) grid = 1;
-        if (grid > 64) grid = 64;
-    }
+    const int grid = (x->mode & MGFEA_XCHG_PUSH) ? x->grid : 1;
+    (void)total;
+    trace_stamp((cudaStream_t)stream);
     p2p_exchange_kernel<<<grid, XCHG_THREADS, 0, (cudaStream_t)stream>>>(p);
+    trace_stamp((cudaStream_t)stream);
     g_launches.fetch_add(1);
     return (int)cudaGetLastError();
 }
@@ -1688,7 +1692,10 @@ int mgfea_vcycle(const mgfea_grid *grids, const mgfea_level_bufs *bufs, int nlev
     cudaStream_t st = (cudaStream_t)stream;
     const int L = nlevels;
     float *cur[32];   // buffer holding the current iterate of each level (NULL = zero)
-    for (int l = 0; l < L; ++l) cur[l] = (l == 0) ? bufs[0].u : nullptr;
+    for (int l = 0; l < L; ++l) cur[l] = (l == 0 && !cfg->zero_guess) ? bufs[0].u : nullptr;
+    // zero guess on level 0: the first launch writes u_alt so that the up leg lands the result in u
+    float *const a0 = cfg->zero_guess ? bufs[0].u_alt : bufs[0].u;
+    float *const b0 = cfg->zero_guess ? bufs[0].u : bufs[0].u_alt;
     int rc;
 
     auto base_prog = [&](int l) {
@@ -1752,7 +1759,8 @@ int mgfea_vcycle(const mgfea_grid *grids, const mgfea_level_bufs *bufs, int nlev
             Program pr = base_prog(l);
             set_restrict(pr, l);
             float *res = nullptr;
-            if ((rc = run_chain(pr, cur[l], bufs[l].u, bufs[l].u_alt, cfg->nu1, &res, st))) return rc;
+            if ((rc = run_chain(pr, cur[l], l == 0 ? a0 : bufs[l].u, l == 0 ? b0 : bufs[l].u_alt, cfg->nu1, &res, st)))
+                return rc;
             cur[l] = res;
         } else {
             // coarsest: nu1 pre-sweeps here; the nu2 post-sweeps follow in the up leg (same chain when L > 1)

@@ -5,10 +5,10 @@
 //
 //   push    the copy jobs store this rank's boundary rows straight into the neighbours' ghost rows (or its coarse rows /
 //           partial sums into every peer) with 16-byte peer stores over NVLink;
-//   signal  when the last CTA has finished its stores (ticket counter), it makes them visible at system scope and
-//           increments one flag in each target's mailbox (red.release.sys);
-//   wait    the same thread then spins (ld.acquire.sys) until the flags in ITS mailbox, written by the ranks that push to
-//           it, have reached this rank's exchange count + 1.  The count lives in device memory and is advanced by the
+//   signal  every CTA, once its own stores are done (barrier + one system-scope fence), increments one flag in each
+//           target's mailbox; all ranks launch a step with the same number of CTAs (mgfea_xchg.grid);
+//   wait    one thread spins (ld.acquire.sys) until the flags in ITS mailbox, written by the ranks that push to it,
+//           have advanced by that number of CTAs.  The expected count lives in device memory and is advanced by the
 //           kernel itself, so the whole step is CUDA-graph replayable.
 //
 // The kernel that follows on the stream therefore sees complete ghost rows.  Overwriting a neighbour's ghost rows is safe
@@ -25,7 +25,6 @@ namespace mgfea {
 
 struct XchgParams {
     mgfea_xchg x;
-    unsigned int *ticket;  // per-device CTA ticket counter (zero between launches)
     long long timeout_clocks;
 };
 
@@ -34,17 +33,15 @@ __device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int *p
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void red_release_sys_add_u32(unsigned int *p, unsigned int v) {
-    asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void red_relaxed_sys_add_u32(unsigned int *p, unsigned int v) {
+    asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 constexpr int XCHG_THREADS = 256;
 
 __global__ void __launch_bounds__(XCHG_THREADS) p2p_exchange_kernel(const XchgParams p) {
-    __shared__ int is_waiter;
     const mgfea_xchg &x = p.x;
-    const bool push = (x.mode & MGFEA_XCHG_PUSH) != 0;
-    if (push) {
+    if (x.mode & MGFEA_XCHG_PUSH) {
         // ---- copy jobs: 16-byte chunks, grid-stride within each job (coalesced peer stores)
         const long long gtid = (long long)blockIdx.x * XCHG_THREADS + threadIdx.x;
         const long long gstride = (long long)gridDim.x * XCHG_THREADS;
@@ -52,35 +49,36 @@ __global__ void __launch_bounds__(XCHG_THREADS) p2p_exchange_kernel(const XchgPa
             const uint4 *src = reinterpret_cast<const uint4 *>(x.src[j]);
             uint4 *dst = reinterpret_cast<uint4 *>(x.dst[j]);
             const long long nchunk = (long long)(x.bytes[j] >> 4);
-            for (long long i = gtid; i < nchunk; i += gstride) dst[i] = __ldcg(src + i);
+            long long i = gtid;
+            for (; i + 3 * gstride < nchunk; i += 4 * gstride) {  // 4 independent loads in flight per thread
+                const uint4 a = __ldcg(src + i), b = __ldcg(src + i + gstride), c = __ldcg(src + i + 2 * gstride),
+                            d = __ldcg(src + i + 3 * gstride);
+                dst[i] = a;
+                dst[i + gstride] = b;
+                dst[i + 2 * gstride] = c;
+                dst[i + 3 * gstride] = d;
+            }
+            for (; i < nchunk; i += gstride) dst[i] = __ldcg(src + i);
         }
-        __threadfence_system();
+        // ---- every CTA signals for itself: the barrier makes the CTA's stores precede thread 0's system-scope fence,
+        // the fence makes them visible before the flag increment (no grid-wide ticket, one fence per CTA)
         __syncthreads();
         if (threadIdx.x == 0) {
-            const unsigned int t = atomicAdd(p.ticket, 1u);
-            const int last = (t == gridDim.x - 1);
-            if (last) {
-                *p.ticket = 0u;
-                __threadfence_system();
-                for (int s = 0; s < x.nsignal; ++s) red_release_sys_add_u32(x.signal[s], 1u);
-            }
-            is_waiter = last;
+            __threadfence_system();
+            for (int s = 0; s < x.nsignal; ++s) red_relaxed_sys_add_u32(x.signal[s], 1u);
         }
-    } else if (threadIdx.x == 0) {
-        is_waiter = (blockIdx.x == 0);
     }
-    __syncthreads();
-    if (!(x.mode & MGFEA_XCHG_WAIT) || !is_waiter || threadIdx.x != 0) return;
-    // ---- wait for the ranks that push to this one
-    const unsigned int expect = *x.seq + 1u;
+    if (!(x.mode & MGFEA_XCHG_WAIT) || blockIdx.x != 0 || threadIdx.x != 0) return;
+    // ---- CTA 0 waits for the ranks that push to this one: each of their `x.grid` CTAs increments the flag once
+    const unsigned int expect = *x.seq + (unsigned int)x.grid;
+    const bool dead = (x.err != nullptr) && (*x.err != 0);  // after one timeout do not wait again (fail fast on the host)
     const long long t0 = clock64();
-    for (int w = 0; w < x.nwait; ++w) {
+    for (int w = 0; w < x.nwait && !dead; ++w) {
         while ((int)(ld_acquire_sys_u32(x.wait[w]) - expect) < 0) {
             if (clock64() - t0 > p.timeout_clocks) {
                 if (x.err) *x.err = 1 + w;
                 break;
             }
-            __nanosleep(64);
         }
     }
     *x.seq = expect;

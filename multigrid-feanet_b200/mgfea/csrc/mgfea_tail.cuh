@@ -272,6 +272,99 @@ __device__ __forceinline__ void t_prolong(float *sm, const unsigned char *smb, c
     }
 }
 
+// bilinear variant of t_prolong with one work item per (row, group of 4 columns): three coarse values per coarse row
+// serve four fine nodes (same expressions as the streaming / mid kernels)
+__device__ __forceinline__ void t_prolong_bilinear4(const TailLevel &L, const TailLevel &C, const float *vc, float *u) {
+    const int N = L.N, G = (N + 3) / 4, ntask = N * G;
+    const bool seq = (N <= 33);
+    for (int t = threadIdx.x; t < ntask; t += blockDim.x) {
+        const int y = t / G, g = t - y * G, x = 4 * g;
+        if (y == 0 || y == N - 1) continue;  // ring rows: correction masked to zero
+        const float *c0 = vc + t_node(C, y >> 1, x >> 1);
+        const float t0 = c0[0], t1 = c0[1], t2 = c0[2];  // columns beyond the coarse grid are zero pads
+        float e[4];
+        if ((y & 1) == 0) {
+            e[0] = t0;
+            e[1] = __fadd_rn(__fmul_rn(0.5f, t0), __fmul_rn(0.5f, t1));
+            e[2] = t1;
+            e[3] = __fadd_rn(__fmul_rn(0.5f, t1), __fmul_rn(0.5f, t2));
+        } else {
+            const float *c1 = c0 + C.S;
+            const float b0 = c1[0], b1 = c1[1], b2 = c1[2];
+            e[0] = __fadd_rn(__fmul_rn(0.5f, t0), __fmul_rn(0.5f, b0));
+            e[2] = __fadd_rn(__fmul_rn(0.5f, t1), __fmul_rn(0.5f, b1));
+            if (seq) {
+                float v = __fadd_rn(__fmul_rn(0.25f, t0), __fmul_rn(0.25f, t1));
+                v = __fadd_rn(v, __fmul_rn(0.25f, b0));
+                e[1] = __fadd_rn(v, __fmul_rn(0.25f, b1));
+                v = __fadd_rn(__fmul_rn(0.25f, t1), __fmul_rn(0.25f, t2));
+                v = __fadd_rn(v, __fmul_rn(0.25f, b1));
+                e[3] = __fadd_rn(v, __fmul_rn(0.25f, b2));
+            } else {
+                const float ta = __fadd_rn(__fmul_rn(0.5f, t0), __fmul_rn(0.5f, t1));
+                const float ba = __fadd_rn(__fmul_rn(0.5f, b0), __fmul_rn(0.5f, b1));
+                e[1] = __fadd_rn(__fmul_rn(0.5f, ta), __fmul_rn(0.5f, ba));
+                const float tb = __fadd_rn(__fmul_rn(0.5f, t1), __fmul_rn(0.5f, t2));
+                const float bb = __fadd_rn(__fmul_rn(0.5f, b1), __fmul_rn(0.5f, b2));
+                e[3] = __fadd_rn(__fmul_rn(0.5f, tb), __fmul_rn(0.5f, bb));
+            }
+        }
+        float4 *cell = reinterpret_cast<float4 *>(u + t_node(L, y, x));
+        float4 uv = *cell;
+        float *up = reinterpret_cast<float *>(&uv);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int xx = x + q;
+            if (xx >= 1 && xx <= N - 2) up[q] = __fadd_rn(up[q], e[q]);
+        }
+        *cell = uv;
+    }
+}
+
+// Down leg of one level from a ZERO guess, single pattern, one Jacobi pre-sweep: u1 = mask(inv * f) is pointwise, so
+// u1 (-> dst) and r = f - K u1 (-> rdst) come out of ONE pass over the f window (one barrier less per level).
+__device__ __forceinline__ void t_down_fused(float *sm, const TailLevel &L, const float *tab, const float *invd,
+                                             float *dst, float *rdst) {
+    const int G = (L.N - 1 + 3) / 4, ntask = (L.N - 2) * G;
+    const float *f = sm + L.off_f;
+    const float inv = invd[0];
+    float kw[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) kw[q] = tab[q];
+    for (int t = threadIdx.x; t < ntask; t += blockDim.x) {
+        const int i = 1 + t / G, g = t - (i - 1) * G;
+        const Win w = t_window(f, L, i, g);
+        float u1[3][6];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const int yy = i - 1 + d;
+            const bool rin = (yy >= 1 && yy <= L.N - 2);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                const int xx = 4 * g - 1 + q;
+                u1[d][q] = (rin && xx >= 1 && xx <= L.N - 2) ? __fadd_rn(__fmul_rn(inv, w.a[d][q]), 0.0f) : 0.0f;
+            }
+        }
+        float r[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float s = __fmul_rn(kw[0], u1[0][e]);
+            s = __fmaf_rn(kw[1], u1[0][e + 1], s);
+            s = __fmaf_rn(kw[2], u1[0][e + 2], s);
+            s = __fmaf_rn(kw[3], u1[1][e], s);
+            s = __fmaf_rn(kw[4], u1[1][e + 1], s);
+            s = __fmaf_rn(kw[5], u1[1][e + 2], s);
+            s = __fmaf_rn(kw[6], u1[2][e], s);
+            s = __fmaf_rn(kw[7], u1[2][e + 1], s);
+            s = __fmaf_rn(kw[8], u1[2][e + 2], s);
+            r[e] = __fsub_rn(w.a[1][e + 1], s);
+        }
+        const int o = t_node(L, i, 4 * g);
+        *reinterpret_cast<float4 *>(dst + o) = make_float4(u1[1][1], u1[1][2], u1[1][3], u1[1][4]);
+        *reinterpret_cast<float4 *>(rdst + o) = make_float4(r[0], r[1], r[2], r[3]);
+    }
+}
+
 template <bool KEYS>
 __global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail_kernel(const TailParams p) {
     extern __shared__ __align__(16) unsigned char smraw[];
@@ -299,12 +392,20 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail_kernel(const TailPara
     __syncthreads();
     stamp();
     float *tabs = sm + p.off_tab;
-    for (int l = 0; l < p.nlev; ++l) {
+    // all levels' stencil tables in one flat pass (independent loads: one memory round trip, not one per level)
+    constexpr int TABW = MAXPAT * 9 + MAXPAT;
+    for (int idx = tid; idx < p.nlev * TABW; idx += blockDim.x) {
+        const int l = idx / TABW, i = idx - l * TABW;
         const TailLevel &L = p.lv[l];
-        float *tb = tabs + l * (MAXPAT * 9 + MAXPAT);
-        for (int i = tid; i < L.npat * 9; i += blockDim.x) tb[i] = L.ktab[i];
-        for (int i = tid; i < L.npat; i += blockDim.x) tb[MAXPAT * 9 + i] = L.invd[i];
-        if (KEYS && L.off_k >= 0) {
+        float v = 0.0f;
+        if (i < L.npat * 9) v = L.ktab[i];
+        else if (i >= MAXPAT * 9 && i - MAXPAT * 9 < L.npat) v = L.invd[i - MAXPAT * 9];
+        tabs[idx] = v;
+    }
+    if (KEYS) {
+        for (int l = 0; l < p.nlev; ++l) {
+            const TailLevel &L = p.lv[l];
+            if (L.off_k < 0) continue;
             unsigned char *kb = smraw + L.off_k;  // whole layout: ghost rows / pad columns get key 0
             for (int i = tid; i < (L.N + 2) * L.S; i += blockDim.x) {
                 const int y = i / L.S - 1, x = i - (y + 1) * L.S - 4;
@@ -321,9 +422,12 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail_kernel(const TailPara
         const TailLevel &L = p.lv[0];
         const float *fin = p.f_in + (long long)b * p.plane;
         float *f = sm + L.off_f;
-        for (int i = tid; i < L.N * L.N; i += blockDim.x) {
-            const int y = i / L.N, x = i - y * L.N;
-            f[t_node(L, y, x)] = fin[(long long)y * p.pitch + x];
+        // rows are 16-byte aligned in HBM (pitch % 4 == 0) and in the layout; columns [N, roundup4(N)) are zero in both
+        const int G = (L.N + 3) / 4;
+        for (int i = tid; i < L.N * G; i += blockDim.x) {
+            const int y = i / G, g = i - y * G;
+            *reinterpret_cast<float4 *>(f + t_node(L, y, 4 * g)) =
+                __ldcg(reinterpret_cast<const float4 *>(fin + (long long)y * p.pitch + 4 * g));
         }
     }
     if (solve_done) return;
@@ -367,6 +471,19 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail_kernel(const TailPara
 
     // ---- down leg
     for (int l = 0; l < p.nlev; ++l) {
+        if (!KEYS && !p.quirk && p.nu1 == 1 && p.smoother == 0 && l < p.nlev - 1) {
+            // every tail level starts from a zero guess: pre-sweep and residual in one pass
+            const TailLevel &L = p.lv[l];
+            const float *tb = tabs + l * (MAXPAT * 9 + MAXPAT);
+            t_down_fused(sm, L, tb, tb + MAXPAT * 9, sm + (cur[l] ? L.off_u : L.off_v), sm + L.off_t0);
+            cur[l] ^= 1;
+            __syncthreads();
+            stamp();
+            t_restrict<KEYS>(sm, smraw, L, p.lv[l + 1], T, p, sm + L.off_t0);
+            __syncthreads();
+            stamp();
+            continue;
+        }
         if (!p.quirk) relax(l, p.nu1);
         if (l < p.nlev - 1) {
             const TailLevel &L = p.lv[l];
@@ -386,7 +503,10 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail_kernel(const TailPara
             const TailLevel &L = p.lv[l], &C = p.lv[l + 1];
             float *u = sm + (cur[l] ? L.off_v : L.off_u);
             const float *vc = sm + (cur[l + 1] ? C.off_v : C.off_u);
-            t_prolong<KEYS>(sm, smraw, L, C, T, p, vc, u);
+            if (p.prolong_mode != 3)
+                t_prolong_bilinear4(L, C, vc, u);
+            else
+                t_prolong<KEYS>(sm, smraw, L, C, T, p, vc, u);
             __syncthreads();
             stamp();
         }
