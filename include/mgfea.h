@@ -130,6 +130,12 @@ int mgfea_prolong_correct_smooth(const mgfea_grid *g, const mgfea_grid *gc, cons
                                  float *u_out, const float *f, int mode, const float *ptab, int ptab_n,
                                  int has_scale, float scale_host, const float *scale_dev, int nsweeps, int smoother,
                                  const float *hw, int nlayers, int B, void *stream);
+/* the same with the interior residual sum of squares of the result fused into the last launch (what the finest level
+ * of mgfea_vcycle runs when compute_norm is set): sumsq[b] = sum over interior nodes of (f - K u_out)^2 */
+int mgfea_prolong_correct_smooth_norm(const mgfea_grid *g, const mgfea_grid *gc, const float *vc, const float *u_in,
+                                      float *u_out, const float *f, int mode, const float *ptab, int ptab_n,
+                                      int has_scale, float scale_host, const float *scale_dev, int nsweeps,
+                                      int smoother, const float *hw, int nlayers, double *sumsq, int B, void *stream);
 /* sumsq[b] = sum over interior nodes of (f - K u)^2, accumulated in fp64, deterministic order.
  * If ctl != NULL the value is also appended to hist[ctl->cycle*B + b] and the convergence rule is evaluated. */
 int mgfea_residual_norm(const mgfea_grid *g, const float *u, const float *f, double *sumsq, mgfea_ctl *ctl,

@@ -29,7 +29,7 @@ EXPORTS = [
     "mgfea_residual_norm", "mgfea_vcycle", "mgfea_restrict_channels", "mgfea_prolong_channels",
     "mgfea_slab_smooth_residual_restrict", "mgfea_slab_prolong_correct_smooth",
     "mgfea_peer_alloc", "mgfea_peer_free", "mgfea_peer_export", "mgfea_peer_open", "mgfea_peer_close",
-    "mgfea_p2p_exchange", "mgfea_trace",
+    "mgfea_p2p_exchange", "mgfea_trace", "mgfea_prolong_correct_smooth_norm",
 ]
 
 
@@ -127,6 +127,8 @@ def lib():
                                                      vp, i32, vp]
         L.mgfea_prolong_correct_smooth.argtypes = [G, G, vp, vp, vp, vp, i32, vp, i32, i32, f32, vp, i32, i32, vp, i32,
                                                    i32, vp]
+        L.mgfea_prolong_correct_smooth_norm.argtypes = [G, G, vp, vp, vp, vp, i32, vp, i32, i32, f32, vp, i32, i32, vp,
+                                                        i32, vp, i32, vp]
         L.mgfea_restrict_channels.argtypes = [vp, vp, vp, i32, i32, i32, vp]
         L.mgfea_prolong_channels.argtypes = [vp, vp, vp, i32, i32, i32, vp]
         L.mgfea_residual_norm.argtypes = [G, vp, vp, vp, vp, vp, i32, vp]

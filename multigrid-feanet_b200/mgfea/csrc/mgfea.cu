@@ -1532,6 +1532,38 @@ int mgfea_prolong_correct_smooth(const mgfea_grid *g, const mgfea_grid *gc, cons
     return run_program(pr, (cudaStream_t)stream);
 }
 
+int mgfea_prolong_correct_smooth_norm(const mgfea_grid *g, const mgfea_grid *gc, const float *vc, const float *u_in,
+                                      float *u_out, const float *f, int mode, const float *ptab, int ptab_n,
+                                      int has_scale, float scale_host, const float *scale_dev, int nsweeps,
+                                      int smoother, const float *hw, int nlayers, double *sumsq, int B, void *stream) {
+    if (!u_in || !u_out || !vc || !sumsq || u_in == u_out) return MGFEA_EINVAL;
+    if (mode != MGFEA_PROLONG_BILINEAR && mode != MGFEA_PROLONG_TABLE) return MGFEA_EINVAL;
+    Program pr;
+    pr.g = g;
+    pr.B = B;
+    pr.u_in = u_in;
+    pr.f = f;
+    pr.smoother = smoother;
+    pr.hw = hw;
+    pr.nlayers = nlayers;
+    pr.prolong_mode = mode;
+    pr.gc = gc;
+    pr.vc = vc;
+    pr.ptab = ptab;
+    pr.ptab_n = ptab_n;
+    pr.p_has_scale = has_scale;
+    pr.p_scale = scale_host;
+    pr.p_scale_dev = scale_dev;
+    pr.out_mode = OUT_NORM;
+    pr.sumsq = sumsq;
+    // same launch sequence as the last level-0 step of mgfea_vcycle
+    float *res = nullptr;
+    float *other = const_cast<float *>(u_in);
+    const int rc = run_chain(pr, u_in, other, u_out, nsweeps, &res, (cudaStream_t)stream);
+    if (rc) return rc;
+    return res == u_out ? 0 : MGFEA_EUNSUPPORTED;  // an even number of split launches would land in u_in
+}
+
 int mgfea_residual_norm(const mgfea_grid *g, const float *u, const float *f, double *sumsq, mgfea_ctl *ctl,
                         double *hist, int B, void *stream) {
     if (!u || !f) return MGFEA_EINVAL;
