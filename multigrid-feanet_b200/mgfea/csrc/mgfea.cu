@@ -192,9 +192,14 @@ __device__ __forceinline__ void run_tile(TileCtx &c, Tables &T, const RegW &W, c
             cur = dst;
             d += 1;
         } else {
-            stage_reset<GBC>(c, cur, W3, d, p.BH - d);
-            __syncthreads();
-            stage_jacobi<KEYS, GBC, true, EDGE>(c, T, W, W3, W1, cur, W2, d + 1, p.BH - d - 1);
+            // reset_boundary of the sweep's input; with the default ring it is the identity on interior tiles
+            const float *jin = cur;
+            if (GBC || EDGE) {
+                stage_reset<GBC>(c, cur, W3, d, p.BH - d);
+                __syncthreads();
+                jin = W3;
+            }
+            stage_jacobi<KEYS, GBC, true, EDGE>(c, T, W, jin, W1, cur, W2, d + 1, p.BH - d - 1);
             __syncthreads();
             float *src = W2, *dst = W3;
             for (int l = 0; l < p.nlayers; ++l) {
@@ -697,10 +702,12 @@ struct Knobs {
     int mid_min_n = 66;       // coarse levels with mid_min_n <= N <= mid_max_n use the latency-oriented mid kernels
     int mid_max_n = 513;      // (mid_max_n = 0 disables them; at 1025 the streaming DOWN kernel wins: profiles/)
     int mid_max_n_up = 1025;  // the up leg stays ahead one level longer
+    int mid_max_tiles = 1200; // ... and only while tiles x samples stay within about two waves
     Knobs() {
         if (const char *e = getenv("MGFEA_MID_MIN_N")) mid_min_n = atoi(e);
         if (const char *e = getenv("MGFEA_MID_MAX_N")) mid_max_n = mid_max_n_up = atoi(e);
         if (const char *e = getenv("MGFEA_MID_MAX_N_UP")) mid_max_n_up = atoi(e);
+        if (const char *e = getenv("MGFEA_MID_MAX_TILES")) mid_max_tiles = atoi(e);
         if (const char *e = getenv("MGFEA_TH")) th = atoi(e);
         if (const char *e = getenv("MGFEA_STAGES")) stages = atoi(e);
         if (const char *e = getenv("MGFEA_CTAS")) ctas = atoi(e);
@@ -875,6 +882,10 @@ static int mid_mode(const Program &pr, bool keys, bool gbc) {
     if (mmax <= 0 || pr.g->N < k.mid_min_n || pr.g->N > mmax) return -1;
     if (keys || gbc || pr.reset_only || pr.ktab_override || pr.slab) return -1;
     if (pr.smoother != MGFEA_SMOOTH_JACOBI || pr.nsweeps != 1 || !pr.u_out || !pr.f) return -1;
+    // latency-oriented kernels: only while the whole launch is a wave or two of tiles (a batch of 64 samples turns
+    // the same level into a throughput problem, where the streaming kernels execute fewer instructions per node)
+    const long long nt = (pr.g->N + MID_T - 1) / MID_T;
+    if (nt * nt * pr.B > k.mid_max_tiles) return -1;
     if (pr.out_mode == OUT_RESTRICT && pr.prolong_mode == 0 && pr.rtab_n == 1 && pr.u_in == nullptr)
         return pr.g->N <= k.mid_max_n ? 0 : -1;
     if (pr.prolong_mode == MGFEA_PROLONG_BILINEAR && pr.out_mode == OUT_NONE && pr.u_in != nullptr)
@@ -1050,11 +1061,32 @@ static int run_program_(const Program &pr, cudaStream_t st) {
         p.p_scale_dev = pr.p_scale_dev;
     }
 
-    // ---- pick TH so that the carve-up fits 227 KB
+    // ---- pick TH so that the carve-up fits 227 KB; for the staged-heavy programs (pattern keys, HNet temporaries) a
+    // slightly lower tile that lets one more CTA share the SM wins (TH 32 -> 28: 0.915 -> 0.695 ms/cycle on config 3,
+    // profiles/r01_th_sweep_cfg3.log), so among TH in {knob, knob-4, knob-8} take the one with the most resident CTAs
     const bool hj = (pr.nsweeps > 0 && pr.smoother == MGFEA_SMOOTH_HJACOBI);
     int TH = knobs().th;
     p.nstages = knobs().stages;
     size_t smem = 0;
+    if ((keys || hj) && getenv("MGFEA_TH") == nullptr) {
+        int best_th = TH, best_ctas = 0;
+        for (int cand = TH; cand >= TH - 8 && cand >= 8; cand -= 4) {
+            const int bh = cand + (D + (restr ? 1 : 0)) + D;
+            const int box = bh * BW * 4, ch = bh / 2 + 2;
+            long long st = (long long)box * (1 + (need_f ? 1 : 0) + (gbc ? 2 : 0)) + (keys ? round_up(bh * KBW, 128) : 0) +
+                           (pr.prolong_mode ? round_up(ch * CW * 4, 128) : 0) +
+                           (p.keys_c ? round_up(ch * KCW, 128) : 0);
+            long long tot = TABLES_BYTES + p.nstages * st + (long long)box * ((pr.nsweeps > 0 ? 1 : 0) + (hj ? 2 : 0));
+            if (tot > 232448) continue;
+            int ctas = (int)(232448 / tot);
+            if (ctas > MGFEA_MINBLOCKS) ctas = MGFEA_MINBLOCKS;  // the register budget (launch bounds) allows no more
+            if (ctas > best_ctas) {
+                best_ctas = ctas;
+                best_th = cand;
+            }
+        }
+        TH = best_th;
+    }
     for (;; TH -= 4) {
         if (TH < 8) return MGFEA_EUNSUPPORTED;
         p.TH = TH;

@@ -1,6 +1,6 @@
 """Timeline of one replayed V-cycle: %globaltimer stamps before/after every fused-leg launch (mgfea_trace), captured
 in a CUDA graph so that the stamps are tight.  Stamp kernels serialise the launches (no PDL overlap) and add ~1 us each.
-usage: cycle_trace.py [n] [reps]"""
+usage: cycle_trace.py [n] [reps] [iso|jac|hjac]   (jac / hjac: two-phase 1:100 circle, 16-channel R/P, BASELINE config 3)"""
 import os
 import sys
 
@@ -14,10 +14,27 @@ from FEANet.drivers import Multigrid
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+mode = sys.argv[3] if len(sys.argv) > 3 else "iso"
 np.random.seed(123)
-prob = Multigrid(n)
-eng = prob._engine(1, 1, 0, B=1)
-eng.set_u(prob.initial_v.reshape(1, 1, n + 1, n + 1))
+if mode == "iso":
+    prob = Multigrid(n)
+    eng = prob._engine(1, 1, 0, B=1)
+    eng.set_u(prob.initial_v.reshape(1, 1, n + 1, n + 1))
+else:
+    from FEANet.drivers import HNet, _InterfaceSingleGrid
+    from FEANet.solver import LINEAR_4, VCycleEngine
+
+    OPS = np.load(os.path.join(ROOT, "tests", "golden", "ops.npz"))
+    Lv = int(np.log2(n))
+    grids = [_InterfaceSingleGrid(2, n // 2 ** l, prop=(1, 100), shape=0) for l in range(Lv)]
+    hnet = HNet(3)
+    hnet.load_state_dict({f"convLayers.{i}.weight": torch.from_numpy(OPS["hnet_w"][i]).reshape(1, 1, 3, 3) for i in range(3)})
+    R16 = np.repeat((LINEAR_4 / np.float32(4.0)).reshape(1, 9), 16, 0)
+    P4 = np.repeat(LINEAR_4.reshape(1, 9), 16, 0)
+    eng = VCycleEngine([g.jac for g in grids], B=1, smoother=mode, hnet=hnet, prolong="table", rtab=R16, r_scale=4.0,
+                       ptab=P4, p_scale=1.0)
+    eng.set_u(torch.zeros(1, 1, n + 1, n + 1, device="cuda"))
+    eng.set_f(grids[0].fnet(torch.ones(1, 1, n + 1, n + 1, device="cuda")))
 eng.refresh()
 eng._ctl_reset(0, -1.0, eng.max_cycles)
 eng.cycle(use_ctl=True)  # lazy init outside capture
