@@ -198,6 +198,17 @@ typedef struct mgfea_xchg {
 } mgfea_xchg;
 int mgfea_p2p_exchange(const mgfea_xchg *x, void *stream);
 
+/* ---- fp64 defect correction around the fp32 cycle --------------------------------------- */
+/* The reference's remedy for the fp32 residual floor is `.double()` on everything (MM_poisson.ipynb cell 5).  Here the
+ * iterate, right-hand side and residual are fp64 [B][N][pitch] (same pitch / plane counts as the fp32 fields, 16-byte
+ * aligned) and only the correction runs in fp32:  r = f - K u;  e = V-cycle(0, r);  u += e.  Default Dirichlet ring.
+ * mgfea_defect_f64: r (fp32, 0 on the ring) and sumsq[b] = sum over interior nodes of (f - K u)^2 in fp64; with ctl
+ * it is the residual history / stopping rule of the solve, like mgfea_residual_norm.
+ * mgfea_correct_f64: u += (double) e on interior nodes (no-op once ctl->done is set). */
+int mgfea_defect_f64(const mgfea_grid *g, const double *u, const double *f, float *r, double *sumsq, mgfea_ctl *ctl,
+                     double *hist, int B, void *stream);
+int mgfea_correct_f64(const mgfea_grid *g, double *u, const float *e, const mgfea_ctl *ctl, int B, void *stream);
+
 /* ---- whole V-cycle ----------------------------------------------------------------------------------- */
 typedef struct mgfea_cycle_cfg {
     int32_t nu1, nu2;      /* pre / post sweeps (coarsest level gets nu1 + nu2) */

@@ -201,6 +201,31 @@ class Multigrid():
         self.engine = eng
         return res
 
+    def SolveMixed(self, v1v2=[1, 1], n_iter=None, EPS=None, chunk=4, use_graph=True):
+        '''Solve with the iterate / right-hand side / residual in fp64 and the V-cycle itself in fp32 (defect correction,
+        SURVEY 8f.1): reproduces the residual history the reference gives after `.double()` (MM_poisson.ipynb cell 5) and
+        goes below the fp32 floor.  Result: self.grids[0].v as a float64 (1,1,N,N) tensor; returns the residual list.'''
+        if n_iter is None and EPS is None:
+            print("At least one of EPS and n_iter have to be assigned")
+            return None
+        self.v1, self.v2 = v1v2
+        key = ("mixed", self.v1, self.v2, tuple(id(self.grids[l].jac) for l in range(self.L)))
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = VCycleEngine([self.grids[l].jac for l in range(self.L)], B=1, nu1=self.v1, nu2=self.v2, smoother="jac",
+                               prolong="bilinear", rtab=None, r_scale=4.0, quirk_level0=self._quirk,
+                               max_cycles=self.max_cycles, compute_norm=False, zero_guess=True)
+            self._engines[key] = eng
+        N = self.n + 1
+        u0 = torch.as_tensor(self.initial_v).reshape(1, 1, N, N)
+        f = torch.as_tensor(self.grids[0].f).reshape(1, 1, N, N)
+        on_host = not u0.is_cuda
+        res = eng.run_mixed(u0, f, n_iter=n_iter, EPS=EPS, chunk=chunk, use_graph=use_graph)
+        sol = eng.solution64
+        self.grids[0].v = sol.cpu().contiguous() if on_host else sol
+        self._mixed_engine = eng
+        return res
+
     def solve_jacobi(self, n_iter=None, EPS=None):
         args = _solve_args(n_iter, EPS)
         if args is None:

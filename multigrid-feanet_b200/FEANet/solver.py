@@ -115,6 +115,7 @@ class VCycleEngine:
                self.nu1, self.nu2)
         if sig != self._graph_key:
             self._graph, self._graph_key = None, sig
+            self._graph64 = None
 
     # -- problem data --------------------------------------------------------------------------------------
     def set_u(self, u):
@@ -213,6 +214,104 @@ class VCycleEngine:
         if self.conv_rule == mgfea.CONV_SUM:
             return [float(math.sqrt(v)) for v in h.sum(axis=1)]
         return [np.sqrt(row) for row in h]
+
+    # -- fp64 defect correction around the fp32 cycle (the reference's remedy is `.double()`) ----------
+    def _mixed_setup(self):
+        if not (self.zero_guess and not self.compute_norm):
+            raise mgfea.MgfeaError("run_mixed needs an engine built with zero_guess=True, compute_norm=False")
+        if getattr(self, "u64", None) is None:
+            N, pitch = self.u[0].N, self.u[0].pitch
+            self.u64 = torch.zeros((self.B, N, pitch), dtype=torch.float64, device=self.dev)
+            self.f64 = torch.zeros((self.B, N, pitch), dtype=torch.float64, device=self.dev)
+            self._graph64 = None
+
+    def _load64(self, dst, x, zero_ring):
+        x = torch.as_tensor(x)
+        while x.dim() < 4:
+            x = x[None]
+        N = self.u[0].N
+        if x.shape[0] != self.B and x.shape[0] == 1:
+            x = x.expand(self.B, -1, -1, -1)
+        if tuple(x.shape) != (self.B, 1, N, N):
+            raise mgfea.MgfeaError(f"field shape {tuple(x.shape)} does not match level ({self.B},1,{N},{N})")
+        dst[:, :, :N].copy_(x[:, 0].to(dtype=torch.float64), non_blocking=True)
+        if zero_ring:  # the first reset_boundary of the reference's sweep (default Dirichlet ring)
+            dst[:, 0, :] = 0
+            dst[:, N - 1, :] = 0
+            dst[:, :, 0] = 0
+            dst[:, :, N - 1:] = 0
+
+    def _mixed_step(self, use_ctl=True):
+        """e = V-cycle(0, r) in fp32; u64 += e; r = f64 - K u64 (fp64, rounded to fp32 into the cycle's rhs) + norm"""
+        g0 = ctypes.byref(self._grids[0])
+        ctl = self.ctl.data_ptr() if use_ctl else None
+        self.cycle(use_ctl=use_ctl)
+        check(lib().mgfea_correct_f64(g0, self.u64.data_ptr(), self.u[0].ptr, ctl, self.B, stream_ptr()))
+        check(lib().mgfea_defect_f64(g0, self.u64.data_ptr(), self.f64.data_ptr(), self.f[0].ptr, self.sumsq.data_ptr(),
+                                     ctl, self.hist.data_ptr() if use_ctl else None, self.B, stream_ptr()))
+
+    def run_mixed(self, u0, f, n_iter=None, EPS=None, max_cycles=None, chunk=4, use_graph=True):
+        """Multigrid.Solve loop with the iterate, right-hand side and residual in fp64 and one fp32 V-cycle (from the
+        zero guess, on the fp64 residual) per step.  Returns the fp64 interior residual 2-norms after every cycle (the
+        history the reference produces after `.double()`); the solution is `self.solution64`."""
+        if n_iter is None:
+            if EPS is None:
+                print("At least one of EPS and n_iter have to be assigned")
+                return None
+            n_iter = 0
+        elif EPS is None:
+            EPS = math.inf
+        cap = min(max_cycles or self.max_cycles, self.max_cycles)
+        if n_iter > cap:
+            raise mgfea.MgfeaError(f"n_iter={n_iter} exceeds the history capacity {cap}")
+        eps2 = float(EPS) * float(EPS) if math.isfinite(EPS) else 1.7e308
+        self._mixed_setup()
+        self.refresh()
+        if self._grids[0].bc_idx:
+            raise mgfea.MgfeaError("run_mixed supports the default Dirichlet ring only")
+        self._load64(self.u64, u0, True)
+        self._load64(self.f64, f, False)
+        self._ctl_reset(n_iter, eps2, cap)
+        # r_0 (not part of the history: Solve records the residual AFTER each cycle)
+        check(lib().mgfea_defect_f64(ctypes.byref(self._grids[0]), self.u64.data_ptr(), self.f64.data_ptr(), self.f[0].ptr,
+                                     self.sumsq.data_ptr(), None, None, self.B, stream_ptr()))
+        self.r0_sumsq = self.sumsq.clone()
+        if use_graph and self._graph64 is None:
+            torch.cuda.synchronize()
+            saved = self.ctl.clone()
+            self.ctl[1] = 1  # warm-up pass with the done flag set: nothing is modified
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._mixed_step()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self.ctl.copy_(saved)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._mixed_step()
+            self._graph64 = g
+        done = False
+        while not done:
+            for _ in range(chunk):
+                if use_graph:
+                    self._graph64.replay()
+                else:
+                    self._mixed_step()
+            self._ctl_host.copy_(self.ctl, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            done = bool(self._ctl_host[1].item())
+        ncyc = int(self._ctl_host[0].item())
+        h = self.hist[:ncyc].cpu().numpy()
+        self.last_hist = h
+        if self.conv_rule == mgfea.CONV_SUM:
+            return [float(math.sqrt(v)) for v in h.sum(axis=1)]
+        return [np.sqrt(row) for row in h]
+
+    @property
+    def solution64(self):
+        N = self.u[0].N
+        return self.u64[:, None, :, :N]
 
     @property
     def solution(self):

@@ -16,6 +16,7 @@
 #include "mgfea_stream.cuh"
 #include "mgfea_p2p.cuh"
 #include "mgfea_mid.cuh"
+#include "mgfea_f64.cuh"
 
 #ifndef MGFEA_MINBLOCKS
 #define MGFEA_MINBLOCKS 3
@@ -1745,6 +1746,68 @@ int mgfea_p2p_exchange(const mgfea_xchg *x, void *stream) {
     (void)total;
     trace_stamp((cudaStream_t)stream);
     p2p_exchange_kernel<<<grid, XCHG_THREADS, 0, (cudaStream_t)stream>>>(p);
+    trace_stamp((cudaStream_t)stream);
+    g_launches.fetch_add(1);
+    return (int)cudaGetLastError();
+}
+
+/* ---- fp64 defect correction (mgfea_f64.cuh) -------------------------------------------------------------- */
+int mgfea_defect_f64(const mgfea_grid *g, const double *u, const double *f, float *r, double *sumsq, mgfea_ctl *ctl,
+                     double *hist, int B, void *stream) {
+    if (!g || !u || !f || !r || B < 1 || g->N < 3) return MGFEA_EINVAL;
+    if (g->bc_idx) return MGFEA_EUNSUPPORTED;  // the correction equation has the homogeneous default ring
+    if ((g->pitch & 3) || (g->plane & 3) || ((reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(f)) & 15u) ||
+        (reinterpret_cast<uintptr_t>(r) & 7u))
+        return MGFEA_EALIGN;
+    if (g->npat < 1 || g->npat > MAXPAT || !g->ktab) return MGFEA_EINVAL;
+    F64Params p;
+    memset(&p, 0, sizeof(p));
+    p.N = g->N;
+    p.B = B;
+    p.pitch = g->pitch;
+    p.plane = g->plane;
+    p.u = u;
+    p.f = f;
+    p.r = r;
+    p.keys = g->keys;
+    p.key_pitch = g->key_pitch;
+    p.npat = g->npat;
+    p.ktab = g->ktab;
+    p.nbx = (g->pitch / 2 + F64_TX - 1) / F64_TX;
+    p.nby = (g->N + F64_TY - 1) / F64_TY;
+    if (p.nby > 65535 || B > 65535) return MGFEA_EUNSUPPORTED;
+    DeviceScratch *scr = nullptr;
+    int rc = get_scratch((size_t)p.nbx * p.nby * B, &scr);
+    if (rc) return rc;
+    p.partials = scr->tile_partials;
+    p.counter = scr->counter;
+    p.sumsq = sumsq;
+    p.hist = hist;
+    p.ctl = ctl;
+    const dim3 grid((unsigned)p.nbx, (unsigned)p.nby, (unsigned)B), block(F64_TX, F64_TY);
+    trace_stamp((cudaStream_t)stream);
+    if (g->keys)
+        mg_defect_f64_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(p);
+    else
+        mg_defect_f64_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(p);
+    trace_stamp((cudaStream_t)stream);
+    g_launches.fetch_add(1);
+    return (int)cudaGetLastError();
+}
+
+int mgfea_correct_f64(const mgfea_grid *g, double *u, const float *e, const mgfea_ctl *ctl, int B, void *stream) {
+    if (!g || !u || !e || B < 1) return MGFEA_EINVAL;
+    if ((g->pitch & 3) || (g->plane & 3) || (reinterpret_cast<uintptr_t>(u) & 15u) || (reinterpret_cast<uintptr_t>(e) & 7u))
+        return MGFEA_EALIGN;
+    const long long total = (long long)B * g->N * (g->pitch / 2);
+    DeviceScratch *scr = nullptr;
+    int rc = get_scratch(1, &scr);
+    if (rc) return rc;
+    long long blocks = (total + 255) / 256;
+    const long long maxb = (long long)scr->num_sms * 16;
+    if (blocks > maxb) blocks = maxb;
+    trace_stamp((cudaStream_t)stream);
+    mg_correct_f64_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(u, e, g->N, g->pitch, g->plane, B, ctl);
     trace_stamp((cudaStream_t)stream);
     g_launches.fetch_add(1);
     return (int)cudaGetLastError();

@@ -546,3 +546,120 @@ def test_slab_kernels_match_single_gpu(world, n, dist_min_n, p2p):
     assert ret["ld"] >= 2
     exact(ret["sol"], prob.grids[0].v.numpy()[0, 0], "slab solution")
     assert np.allclose(ret["hist"], res, rtol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------ fp64 defect correction (8f.1)
+def _ku64(u, keys, ktab):
+    """K u in numpy fp64 with source-key indexed weights and zero padding (the `.double()` reference operator)"""
+    N = u.shape[-1]
+    up = np.zeros((N + 2, N + 2))
+    up[1:-1, 1:-1] = u
+    kp = np.zeros((N + 2, N + 2), np.int64)
+    if keys is not None:
+        kp[1:-1, 1:-1] = keys
+    W = np.asarray(ktab, np.float64).reshape(-1, 9)
+    out = np.zeros((N, N))
+    for a in range(3):
+        for c in range(3):
+            out += W[kp[a:a + N, c:c + N], 3 * a + c] * up[a:a + N, c:c + N]
+    return out
+
+
+@pytest.mark.parametrize("kind", ["iso", "c20", "s100"])
+def test_defect_f64_matches_numpy(O, kind):
+    """mgfea_defect_f64 / mgfea_correct_f64 against numpy fp64 (iso and two-phase pattern keys)"""
+    import ctypes
+
+    import mgfea
+
+    n = 128
+    N = n + 1
+    mesh = make_mesh(kind, N)
+    from FEANet.jacobi import JacobiBlock
+    from FEANet.model import KNet
+
+    jac = JacobiBlock(KNet(mesh), mesh, 2 / 3., None, None)
+    fld = mgfea.Field(2, N, mgfea.require_cuda())
+    g = jac.grid_struct(fld)
+    keys, ktab, _ = oracle_setup(O, kind, N)
+    rs = np.random.RandomState(11)
+    u = rs.standard_normal((2, N, N))
+    u[:, 0, :] = u[:, -1, :] = 0
+    u[:, :, 0] = u[:, :, -1] = 0
+    f = rs.standard_normal((2, N, N))
+    pitch = fld.pitch
+    u64 = torch.zeros((2, N, pitch), dtype=torch.float64, device="cuda")
+    f64 = torch.zeros_like(u64)
+    u64[:, :, :N] = torch.from_numpy(u).cuda()
+    f64[:, :, :N] = torch.from_numpy(f).cuda()
+    r32 = torch.full((2, N, pitch), 7.0, dtype=torch.float32, device="cuda")
+    ss = torch.zeros(2, dtype=torch.float64, device="cuda")
+    mgfea.check(mgfea.lib().mgfea_defect_f64(ctypes.byref(g), u64.data_ptr(), f64.data_ptr(), r32.data_ptr(),
+                                             ss.data_ptr(), None, None, 2, mgfea.stream_ptr()))
+    for b in range(2):
+        r = f[b] - _ku64(u[b], keys, ktab)
+        r[0, :] = r[-1, :] = 0
+        r[:, 0] = r[:, -1] = 0
+        got = host(r32[b])
+        assert np.abs(got[:, :N] - r).max() <= 2e-7 * np.abs(r).max()
+        assert (got[:, N:] == 0).all()
+        assert np.allclose(host(ss)[b], (r ** 2).sum(), rtol=1e-12)
+    e = torch.zeros((2, N, pitch), dtype=torch.float32, device="cuda")
+    e[:, :, :N] = torch.from_numpy(rs.standard_normal((2, N, N)).astype(np.float32)).cuda()
+    before = u64.clone()
+    mgfea.check(mgfea.lib().mgfea_correct_f64(ctypes.byref(g), u64.data_ptr(), e.data_ptr(), None, 2, mgfea.stream_ptr()))
+    want = before.clone()
+    want[:, 1:N - 1, 1:N - 1] += e[:, 1:N - 1, 1:N - 1].double()
+    assert torch.equal(u64, want)
+
+
+@pytest.mark.parametrize("tag", ["modelA_n64_rhs", "modelA_n64_v11", "modelA_n1024_L10"])
+def test_solve_mixed_matches_fp64_reference(tag):
+    """SolveMixed (fp64 iterate / residual, fp32 V-cycle as the correction) vs the reference run after `.double()`
+    (res64 in tests/golden/solve_histories.json): per-cycle residual within 1e-5 relative, far below the fp32 floor"""
+    from FEANet.drivers import Multigrid
+
+    h = HIST[tag]
+    n = h["n"]
+    np.random.seed(123)
+    prob = Multigrid(n, h["L"])
+    if h["rhs_seed"] is None:
+        prob.initial_v = torch.from_numpy(model_u0(n))
+    else:
+        rs = np.random.RandomState(h["rhs_seed"])
+        F = torch.from_numpy(rs.standard_normal((1, 1, n + 1, n + 1)).astype(np.float32))
+        prob.grids[0].f = prob.grids[0].fnet(F)
+        prob.initial_v = torch.zeros(n + 1, n + 1)
+    ref = np.array(h["res64"])
+    res = np.array(prob.SolveMixed(list(h["v1v2"]), n_iter=len(ref), chunk=3))
+    assert len(res) == len(ref)
+    rel = np.abs(res - ref) / ref
+    assert (rel <= 1e-5).all(), (tag, rel)
+    assert prob.grids[0].v.dtype == torch.float64 and tuple(prob.grids[0].v.shape) == (1, 1, n + 1, n + 1)
+
+
+def test_solve_mixed_goes_below_fp32_floor():
+    """nonzero right-hand side at 257^2: fp32 Solve stalls near 1e-6 relative, the mixed solve
+    reaches 1e-10 with the reference's convergence factor"""
+    from FEANet.drivers import Multigrid
+
+    n = 256
+    np.random.seed(123)
+    prob = Multigrid(n)
+    rs = np.random.RandomState(5)
+    F = torch.from_numpy(rs.standard_normal((1, 1, n + 1, n + 1)).astype(np.float32))
+    prob.grids[0].f = prob.grids[0].fnet(F)
+    prob.initial_v = torch.zeros(n + 1, n + 1)
+    res32 = np.array(prob.Solve([1, 1], n_iter=25))
+    prob.initial_v = torch.zeros(n + 1, n + 1)
+    res64 = np.array(prob.SolveMixed([1, 1], n_iter=25))
+    eng = prob._mixed_engine
+    r0 = float(np.sqrt(eng.r0_sumsq.sum().item()))
+    assert res32[-1] / r0 > 1e-7  # the fp32 floor
+    assert res64[-1] / r0 < 1e-10
+    q = (res64[14] / res64[4]) ** 0.1
+    assert 0.15 < q < 0.35, q
+    # EPS semantics: stops at the first cycle below the threshold
+    prob.initial_v = torch.zeros(n + 1, n + 1)
+    r = prob.SolveMixed([1, 1], EPS=1e-8 * r0)
+    assert r[-1] <= 1e-8 * r0 < r[-2]
