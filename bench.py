@@ -370,6 +370,31 @@ def run_ours(args):
     torch.cuda.synchronize()
     t_tol = time.perf_counter() - t0
 
+    # ---- time to 1e-8 relative residual with a NONZERO right-hand side (fp32 alone stalls near 1e-6, BASELINE.md
+    # section 2): fp64 defect correction around the fp32 cycle (Multigrid.SolveMixed), device resident
+    mixed = None
+    if not args.no_mixed:
+        from FEANet.model import FNet  # noqa: F401
+
+        g = torch.Generator(device="cuda").manual_seed(0)
+        Fr = torch.randn(1, 1, N, N, generator=g, device="cuda")
+        prob.grids[0].f = prob.grids[0].fnet(Fr)
+        prob.initial_v = torch.zeros(1, 1, N, N, device="cuda")
+        prob.SolveMixed([1, 1], n_iter=2)  # builds the engine + graph
+        engm = prob._mixed_engine
+        r0m = float(torch.sqrt(engm.r0_sumsq.sum()).item())
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        hm = prob.SolveMixed([1, 1], EPS=1e-8 * r0m, chunk=4)
+        torch.cuda.synchronize()
+        tm = time.perf_counter() - t0
+        mixed = {"cycles_to_1e-8_rel": len(hm), "ms": 1e3 * tm, "ms_per_cycle": 1e3 * tm / max(len(hm), 1),
+                 "final_rel_residual": hm[-1] / r0m,
+                 "what": "randn right-hand side (seed 0) through FNet, u0 = 0; iterate / residual in fp64, V-cycle in "
+                         "fp32; includes the H2D-free setup copies of u0 and f into the fp64 buffers"}
+        prob.grids[0].f = f_host
+        prob.initial_v = u0_host
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -379,7 +404,7 @@ def run_ours(args):
             "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "v_cycles_per_s": cycles_per_s,
-            "time_to_1e-8_rel_ms": 1e3 * t_tol, "cycles_to_1e-8_rel": len(hist),
+            "time_to_1e-8_rel_ms": 1e3 * t_tol, "cycles_to_1e-8_rel": len(hist), "mixed_precision_solve": mixed,
             "config": {"workload": f"iso Poisson {N}x{N}, V(1,1), {L} levels, single RHS per GPU, f=0 model problem "
                                    "(MM_Model_convergence.ipynb cell 3), residual norm fused in every cycle",
                        "n": n, "levels": L, "nu": [1, 1], "batch": 1,
@@ -575,6 +600,7 @@ def main():
     ap.add_argument("--loader", default="tma", choices=["tma", "cpasync"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-mixed", action="store_true", help="skip the fp64 defect-correction time-to-tolerance run")
     ap.add_argument("--n-multi", type=int, default=0, help="grid intervals for the row-slab run at N > 1 (default by N)")
     args = ap.parse_args()
     if args.impl == "reference":

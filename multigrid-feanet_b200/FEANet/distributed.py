@@ -196,7 +196,7 @@ class PeerSlabMemory:
 class CudaSlabOps:
     """local operators on the GPU: the slab forms of the streaming kernels + the replicated coarse engine"""
 
-    def __init__(self, part, nu1=1, nu2=1, coarse_f_store=None):
+    def __init__(self, part, nu1=1, nu2=1, coarse_f_store=None, prop=None, shape=0):
         import mgfea
         from .jacobi import JacobiBlock
         from .mesh import MeshSquare
@@ -211,7 +211,11 @@ class CudaSlabOps:
         n, L = part.n, part.L
         self.jacs = []
         for l in range(L):  # light-weight levels: no full-size host tensors (a 16385^2 mask alone is 1 GB)
-            mesh = MeshSquare(2, n // 2 ** l + 1)
+            if prop is None:
+                mesh = MeshSquare(2, n // 2 ** l + 1)
+            else:  # two-phase inclusion (FEANet/mesh.py:4-120): every rank keeps the GLOBAL uint8 key map of a level
+                from .mesh import MeshCenterInterface
+                mesh = MeshCenterInterface(2, list(prop), n // 2 ** l + 1, shape=shape)
             self.jacs.append(JacobiBlock(KNet(mesh), mesh, 2 / 3., None, None))
         self.rtab = torch.from_numpy(FULL_WEIGHTING_16.reshape(1, 9).copy()).to(self.dev)
         # the replicated coarse cycle always starts from a zero guess and nobody reads its residual norm -- unless it IS
@@ -274,7 +278,7 @@ class CudaSlabOps:
 class SlabMultigrid:
     """V(1,1) solver for the iso Poisson problem on row slabs.  `ops` supplies the local operators."""
 
-    def __init__(self, n, ops_factory=CudaSlabOps, L=None, dist_min_n=2049, group=None, p2p=None):
+    def __init__(self, n, ops_factory=CudaSlabOps, L=None, dist_min_n=2049, group=None, p2p=None, prop=None, shape=0):
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.group = group
@@ -288,14 +292,15 @@ class SlabMultigrid:
             p2p = os.environ.get("MGFEA_P2P", "1") != "0"
         if p2p and self.world > 1 and 0 < ld < self.L and ops_factory is CudaSlabOps and torch.cuda.is_available():
             self.peer = self._try_peer_memory()
+        kw = {} if prop is None else {"prop": prop, "shape": shape}  # two-phase conductivity (CUDA operators only)
         if self.peer is not None:
-            self.ops = ops_factory(self.part, coarse_f_store=self.peer.array("f", ld))
+            self.ops = ops_factory(self.part, coarse_f_store=self.peer.array("f", ld), **kw)
             self.ops._sumsq = self.peer.partial
             self.u = [self.peer.array("u", l) for l in range(ld)]
             self.u_alt = [self.peer.array("u_alt", l) for l in range(ld)]
             self.f = [self.peer.array("f", l) for l in range(ld)]
         else:
-            self.ops = ops_factory(self.part)
+            self.ops = ops_factory(self.part, **kw)
             self.u = [self.ops.alloc(l) for l in range(ld)]
             self.u_alt = [self.ops.alloc(l) for l in range(ld)]
             self.f = [self.ops.alloc(l) for l in range(ld)]

@@ -43,7 +43,9 @@ def build(verbose: bool = False) -> str:
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(INCLUDE, "mgfea.h")]
     if os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
         return LIB_PATH
-    cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
+    # -fmad=false: every multiply-add the arithmetic contract allows is written as an explicit fma intrinsic; nothing
+    # else may be contracted (NB: ptxas still fuses inline-PTX mul.rn.f32x2 + add.rn.f32x2, see mgfea_stream.cuh)
+    cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-fmad=false", "-lineinfo", "-std=c++17", "-shared",
            "-Xcompiler", "-fPIC", os.path.join(CSRC, "mgfea.cu"), "-o", LIB_PATH]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

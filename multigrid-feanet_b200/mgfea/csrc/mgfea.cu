@@ -700,6 +700,7 @@ struct Knobs {
     int stream_min_n = 129;   // levels with N >= this use the register-chained streaming kernels (0 disables)
     int stream_r = 0;         // rows per strip (0 = auto)
     int stream_packed = 1;    // 1: FFMA2 (fma.rn.f32x2) streaming kernels, 0: scalar FFMA
+    int stream_keys = 0;      // 1: two-phase levels also stream (see stream_eligible)
     int mid_min_n = 66;       // coarse levels with mid_min_n <= N <= mid_max_n use the latency-oriented mid kernels
     int mid_max_n = 513;      // (mid_max_n = 0 disables them; at 1025 the streaming DOWN kernel wins: profiles/)
     int mid_max_n_up = 1025;  // the up leg stays ahead one level longer
@@ -715,6 +716,7 @@ struct Knobs {
         if (const char *e = getenv("MGFEA_STREAM_MIN_N")) stream_min_n = atoi(e);
         if (const char *e = getenv("MGFEA_STREAM_R")) stream_r = atoi(e);
         if (const char *e = getenv("MGFEA_STREAM_PACKED")) stream_packed = atoi(e);
+        if (const char *e = getenv("MGFEA_STREAM_KEYS")) stream_keys = atoi(e);
         if (const char *e = getenv("MGFEA_THREADS")) threads = atoi(e);
         threads = 256;
         if (th < 8 || th > 64 || (th & 1)) th = 32;
@@ -754,7 +756,13 @@ static int check_field(const void *p, int pitch, long long plane) {
 static bool stream_eligible(const Program &pr, bool keys, bool gbc) {
     const int minn = knobs().stream_min_n;
     if (minn <= 0 || pr.g->N < minn) return false;
-    if (keys || gbc || pr.reset_only || pr.ktab_override) return false;
+    if (gbc || pr.reset_only || pr.ktab_override) return false;
+    // pattern keys: the keyed streaming kernels (mg_stream2_kernel<.., KEYS>) are bit-exact but NOT the default on one
+    // GPU: a strip that follows a vertical piece of the material interface takes the per-node weight lookup for all
+    // of its rows (2.7x slower), and with one strip per warp the launch waits for those warps (level 0 of the 1:20
+    // circle at 4097^2: 125 us vs 84 us for the tile kernels, profiles/r01_keyed_stream_trace.log).  They stay
+    // available (MGFEA_STREAM_KEYS=1) and carry the row-slab path, where no tile kernel exists.
+    if (keys && (!knobs().stream_packed || !knobs().stream_keys)) return false;
     if (pr.smoother != MGFEA_SMOOTH_JACOBI || pr.nsweeps != 1 || !pr.u_out || !pr.f) return false;
     if (pr.out_mode == OUT_RESTRICT && pr.prolong_mode == 0) return pr.rtab_n == 1;
     if (pr.prolong_mode == MGFEA_PROLONG_BILINEAR && (pr.out_mode == OUT_NONE || pr.out_mode == OUT_NORM))
@@ -814,6 +822,7 @@ static int run_stream(const Program &pr, cudaStream_t st) {
     p.nstrips = p.ntx * p.nry;
     const long long total = (long long)p.nstrips * pr.B;
     if (total >= (1 << 24)) return MGFEA_EUNSUPPORTED;
+    p.one = 1.0f;
     p.inv_nstrips = 1.0f / (float)p.nstrips;
     p.inv_ntx = 1.0f / (float)p.ntx;
     p.u_in = pr.u_in;
@@ -821,6 +830,13 @@ static int run_stream(const Program &pr, cudaStream_t st) {
     p.f = pr.f;
     p.ktab = g->ktab;
     p.invd = g->invd;
+    const bool keys = (g->keys != nullptr) && !pr.ignore_keys;
+    if (keys) {
+        if ((g->key_pitch & 15) || g->npat < 1 || g->npat > MAXPAT) return MGFEA_EALIGN;
+        p.keys = g->keys;
+        p.key_pitch = g->key_pitch;
+        p.npat = g->npat;
+    }
     if (mode == 0) {
         p.fc = pr.fc;
         p.pitch_c = pr.pitch_c;
@@ -844,31 +860,39 @@ static int run_stream(const Program &pr, cudaStream_t st) {
     p.sumsq = pr.sumsq;
     p.hist = pr.hist;
     p.ctl = pr.ctl;
-    const size_t smem = (size_t)ST_WARPS * ST_RING_F4 * 32 * 16;
+    const size_t smem = (size_t)ST_WARPS * ST_RING_F4 * 32 * 16 + (keys ? (size_t)ST_WARPS * ST_KDEPTH * 32 * 4 : 0);
     long long ctas = (total + ST_WARPS - 1) / ST_WARPS;
     const long long maxc = (long long)scr->num_sms * 2;
     const int grid = (int)(ctas < maxc ? ctas : maxc);
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(mg_stream_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(mg_stream_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(mg_stream_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(mg_stream2_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(mg_stream2_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(mg_stream2_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const int big = (int)((size_t)ST_WARPS * ST_RING_F4 * 32 * 16 + (size_t)ST_WARPS * ST_KDEPTH * 32 * 4);
+        cudaFuncSetAttribute(mg_stream_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(mg_stream_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(mg_stream_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(mg_stream2_kernel<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(mg_stream2_kernel<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(mg_stream2_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(mg_stream2_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(mg_stream2_kernel<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(mg_stream2_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         configured = true;
     }
     const bool pk = knobs().stream_packed != 0;
+    if (keys && !pk) return MGFEA_EUNSUPPORTED;
     if (mode == 0) {
         if (pr.u_in) {
-            if (pk) launch_pdl(mg_stream2_kernel<0, false>, grid, ST_WARPS * 32, smem, st, p);
+            if (keys) launch_pdl(mg_stream2_kernel<0, false, true>, grid, ST_WARPS * 32, smem, st, p);
+            else if (pk) launch_pdl(mg_stream2_kernel<0, false, false>, grid, ST_WARPS * 32, smem, st, p);
             else launch_pdl(mg_stream_kernel<0, false>, grid, ST_WARPS * 32, smem, st, p);
         } else {
-            if (pk) launch_pdl(mg_stream2_kernel<0, true>, grid, ST_WARPS * 32, smem, st, p);
+            if (keys) launch_pdl(mg_stream2_kernel<0, true, true>, grid, ST_WARPS * 32, smem, st, p);
+            else if (pk) launch_pdl(mg_stream2_kernel<0, true, false>, grid, ST_WARPS * 32, smem, st, p);
             else launch_pdl(mg_stream_kernel<0, true>, grid, ST_WARPS * 32, smem, st, p);
         }
     } else {
-        if (pk) launch_pdl(mg_stream2_kernel<1, false>, grid, ST_WARPS * 32, smem, st, p);
+        if (keys) launch_pdl(mg_stream2_kernel<1, false, true>, grid, ST_WARPS * 32, smem, st, p);
+        else if (pk) launch_pdl(mg_stream2_kernel<1, false, false>, grid, ST_WARPS * 32, smem, st, p);
         else launch_pdl(mg_stream_kernel<1, false>, grid, ST_WARPS * 32, smem, st, p);
     }
     g_launches.fetch_add(1);
@@ -1615,7 +1639,7 @@ int mgfea_residual_norm(const mgfea_grid *g, const float *u, const float *f, dou
 /* ---- row-slab (multi-GPU) forms of the two fused legs; see include/mgfea.h ------------------------------ */
 static int slab_common(Program &pr, const mgfea_grid *g, const mgfea_slab *s, const mgfea_slab *sc) {
     if (!g || !s || !sc) return MGFEA_EINVAL;
-    if (g->keys || g->bc_idx || g->npat != 1) return MGFEA_EUNSUPPORTED;  // single-pattern, default Dirichlet ring
+    if (g->bc_idx) return MGFEA_EUNSUPPORTED;  // default Dirichlet ring; pattern keys: GLOBAL [N][key_pitch] map
     pr.g = g;
     pr.slab = 1;
     pr.row0 = s->row0;

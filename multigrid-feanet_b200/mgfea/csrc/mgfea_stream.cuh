@@ -24,6 +24,7 @@ constexpr int ST_WARPS = 8;    // warps per CTA
 constexpr int ST_DEPTH = 6;    // prefetch ring depth (rows) == unroll factor of the row loop: ring slots are compile-time
 constexpr int ST_TWI = BW - 8; // interior columns per strip (HX = 4)
 constexpr int ST_RING_F4 = 2 * ST_DEPTH + ST_DEPTH / 2;  // float4 units per lane: u ring, f ring, coarse float2 ring
+constexpr int ST_KDEPTH = 3 * ST_DEPTH;                  // key-word ring depth in rows (KEYS kernels only)
 
 struct StreamParams {
     int N, B, pitch;
@@ -34,10 +35,14 @@ struct StreamParams {
     // Coarse arrays hold global coarse rows [crow0, crow0+nrc).  Single GPU: row0=0, nrloc=N, own=[0,N), crow0=0, nrc=Nc.
     int row0, nrloc, own0, own1, crow0, nrc;
     float inv_nstrips, inv_ntx;
+    float one;  // = 1.0f, deliberately a run-time value
     const float *u_in;   // NULL: zero initial guess (down leg of coarse levels)
     float *u_out;
     const float *f;
-    const float *ktab, *invd;  // [9], [1] (single pattern)
+    const float *ktab, *invd;  // [npat][9], [npat] (single pattern: [9], [1])
+    // material pattern keys (mg_stream2_kernel<.., KEYS = true>): GLOBAL [N][key_pitch] map, also on a slab
+    const unsigned char *keys;
+    int key_pitch, npat;
     // down leg
     float *fc;
     int Nc, pitch_c;
@@ -519,15 +524,73 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream_kernel(const Strea
 }
 
 
+// ---- source-key indexed stencil (two-phase meshes): slow path for the rows a material interface crosses
+struct K6 {
+    int k[6];  // pattern keys of box columns 4l-1 .. 4l+4
+};
+__device__ __forceinline__ K6 key6(unsigned int w) {
+    const unsigned int l = __shfl_up_sync(0xffffffffu, w, 1), r = __shfl_down_sync(0xffffffffu, w, 1);
+    K6 o;
+    o.k[0] = (int)(l >> 24);
+    o.k[1] = (int)(w & 0xffu);
+    o.k[2] = (int)((w >> 8) & 0xffu);
+    o.k[3] = (int)((w >> 16) & 0xffu);
+    o.k[4] = (int)(w >> 24);
+    o.k[5] = (int)(r & 0xffu);
+    return o;
+}
+__device__ __forceinline__ void unpack_row(const RP &r, float (&a)[6]) {
+    unpack2(r.q[0], a[0], a[1]);
+    unpack2(r.q[2], a[2], a[3]);
+    unpack2(r.q[4], a[4], a[5]);
+}
+// same row-major FMA chain as stencil_rows2, weights tab[key(source)][tap]; out = {K lo, K hi, inv lo, inv hi}.
+// Deliberately NOT inlined: only the few windows a material interface crosses come here, and keeping this register-hungry
+// code out of line leaves the single-pattern fast path's register allocation untouched.
+__device__ __noinline__ void stencil_rows_keys(const float *tab, const float *invt, unsigned int w0, unsigned int w1,
+                                               unsigned int w2, RP t, RP m, RP b, u64 *out) {
+    const K6 kt = key6(w0), km = key6(w1), kb = key6(w2);
+    float ta[6], ma[6], ba[6], acc[4];
+    unpack_row(t, ta);
+    unpack_row(m, ma);
+    unpack_row(b, ba);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        float s = __fmul_rn(tab[9 * kt.k[e] + 0], ta[e]);
+        s = __fmaf_rn(tab[9 * kt.k[e + 1] + 1], ta[e + 1], s);
+        s = __fmaf_rn(tab[9 * kt.k[e + 2] + 2], ta[e + 2], s);
+        s = __fmaf_rn(tab[9 * km.k[e] + 3], ma[e], s);
+        s = __fmaf_rn(tab[9 * km.k[e + 1] + 4], ma[e + 1], s);
+        s = __fmaf_rn(tab[9 * km.k[e + 2] + 5], ma[e + 2], s);
+        s = __fmaf_rn(tab[9 * kb.k[e] + 6], ba[e], s);
+        s = __fmaf_rn(tab[9 * kb.k[e + 1] + 7], ba[e + 1], s);
+        s = __fmaf_rn(tab[9 * kb.k[e + 2] + 8], ba[e + 2], s);
+        acc[e] = s;
+    }
+    out[0] = pack2(acc[0], acc[1]);
+    out[1] = pack2(acc[2], acc[3]);
+    out[2] = pack2(invt[km.k[1]], invt[km.k[2]]);
+    out[3] = pack2(invt[km.k[3]], invt[km.k[4]]);
+}
+
 // Packed variant: the two stencil chains per row run on fma.rn.f32x2 (FFMA2): same IEEE result per lane, half the
 // issue slots.  Rows are kept as 5 overlapping column PAIRS q[i] = (a[i], a[i+1]).
 // MODE 0: down leg (Jacobi sweep, store u, residual, restriction -> fc)
 // MODE 1: up leg   (bilinear prolongation + correction, Jacobi sweep, store u, optional interior residual norm)
-template <int MODE, bool ZERO_INIT>
+// KEYS: two-phase meshes.  The key words (4 keys per lane) of the NEXT block of 6 rows ride the prefetch group of the
+// current block's first row into an 18-row ring.  At every block start one vote decides whether the block (and the one
+// before it, for the stencils' look-back) carries ONE pattern over the whole strip: then the block runs the very same
+// single-pattern code as an iso mesh, with that pattern's weights (reloaded from shared memory when the key changes,
+// i.e. twice per strip that crosses the inclusion).  Blocks that touch the interface run a general variant whose
+// stencils look every weight up by the source node's key (out of line, so the fast path's code and registers are
+// those of the iso kernel).
+template <int MODE, bool ZERO_INIT, bool KEYS = false>
 __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const StreamParams p) {
     extern __shared__ __align__(16) unsigned char st_smem[];
     __shared__ double red[ST_WARPS];
     __shared__ int lastflag;
+    __shared__ float s_tab[KEYS ? MAXPAT * 9 : 1];   // stiffness tables of all patterns
+    __shared__ float s_inv[KEYS ? MAXPAT : 1];       // omega / d per pattern
     pdl_launch_dependents();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int N = p.N;
@@ -543,8 +606,15 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
     u64 kw2[9];
 #pragma unroll
     for (int q = 0; q < 9; ++q) kw2[q] = pack2(kw[q], kw[q]);
-    const u64 inv2 = pack2(inv, inv);
+    u64 inv2 = pack2(inv, inv);
+    const u64 one2 = pack2(p.one, p.one);  // 1.0f from the launch parameters: opaque to ptxas (see the Jacobi update)
     const float rscale = (MODE == 0 && p.r_has_scale) ? (p.r_scale_dev ? *p.r_scale_dev : p.r_scale) : 1.0f;
+    if (KEYS) {
+        for (int i = threadIdx.x; i < MAXPAT * 9; i += ST_WARPS * 32) s_tab[i] = (i < p.npat * 9) ? p.ktab[i] : 0.0f;
+        if (threadIdx.x < MAXPAT) s_inv[threadIdx.x] = (threadIdx.x < p.npat) ? p.invd[threadIdx.x] : 0.0f;
+        __syncthreads();
+    }
+    int kcur = 0;  // pattern whose weights sit in kw2 / inv2
     pdl_wait();  // weights above are never written by a kernel; all field data is touched only after this point
     // the solve-control word is requested here but tested only after the first prefetches are in flight, so the two
     // memory round trips overlap (a finished solve returns before anything is stored)
@@ -554,6 +624,8 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
     float4 *ring_u = reinterpret_cast<float4 *>(st_smem) + warp * (ST_RING_F4 * 32);
     float4 *ring_f = ring_u + ST_DEPTH * 32;
     float2 *ring_c = reinterpret_cast<float2 *>(ring_f + ST_DEPTH * 32);
+    // key words: 12 rows deep (the residual stage looks back further than the 6-row data ring keeps its rows)
+    unsigned int *ring_k = reinterpret_cast<unsigned int *>(st_smem + ST_WARPS * ST_RING_F4 * 32 * 16) + warp * (ST_KDEPTH * 32);
 
     const int total = p.nstrips * p.B;
     for (int s = blockIdx.x * ST_WARPS + warp; s < total; s += gridDim.x * ST_WARPS) {
@@ -614,6 +686,19 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
         const float *pf_u = ZERO_INIT ? nullptr : ub + (long long)(a0 - p.row0) * p.pitch;
         const float *pf_f = fb + (long long)(a0 - p.row0) * p.pitch;
         int kpf = 0;
+        // KEYS: keys of the 6 streamed rows keyrow0 .. keyrow0+5 join the current commit group
+        auto fetch_keys = [&](int keyrow0) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const int kr = keyrow0 + j, gy = a0 + kr;
+                const bool okk = (gx >= 0 && gx + 3 < p.key_pitch && gy >= 0 && gy < N);
+                const void *src = okk ? (const void *)(p.keys + (long long)gy * p.key_pitch + gx) : (const void *)p.f;
+                const uint32_t sz = okk ? 4u : 0u;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(&ring_k[(kr % ST_KDEPTH) * 32 + lane])),
+                             "l"(src), "r"(sz)
+                             : "memory");
+            }
+        };
         auto prefetch = [&](auto check_tag, int slot_row) {
             constexpr bool CHECK = decltype(check_tag)::value;
             const bool ok = !CHECK || (col_ok && kpf >= klo && kpf < khi);
@@ -636,6 +721,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
             ++kpf;
         };
 #pragma unroll
+        if (KEYS) fetch_keys(0);  // block 0's keys travel with the first row
         for (int k = 0; k < ST_DEPTH - 3; ++k) prefetch(std::true_type{}, k);
         if (solve_done) break;
 
@@ -656,14 +742,17 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
         }
 
         // one block of 6 row steps.  GUARD: start-up / drain steps (pipeline fill, store ranges); EDGE: masks needed.
-        auto block6 = [&](auto guard_tag, auto edge_tag, auto pf_tag, int k0) {
+        // KEYED (two-phase meshes only): the block touches a material interface -> per-node weight lookup
+        auto block6 = [&](auto guard_tag, auto edge_tag, auto pf_tag, auto keyed_tag, int k0) {
             constexpr bool GUARD = decltype(guard_tag)::value;
             constexpr bool EDGE = decltype(edge_tag)::value;
+            constexpr bool KEYED = decltype(keyed_tag)::value;
 #pragma unroll
             for (int ph = 0; ph < 6; ++ph) {
                 const int k = k0 + ph;
                 if (GUARD && k >= K) break;
                 const int a = a0 + k;
+                if (KEYS && ph == 0) fetch_keys(k0 + 6);  // next block's keys, same commit group as row k0+3
                 prefetch(pf_tag, (ph + ST_DEPTH - 3) % ST_DEPTH);  // rows k-2..k stay in the ring (f is re-read)
                 asm volatile("cp.async.wait_group %0;" ::"n"(ST_DEPTH - 3) : "memory");
                 const int slot = ph * 32 + lane;
@@ -718,11 +807,27 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
                 if (!GUARD || k >= 2) {
                     const int y = a - 1;
                     const RP &t = A[(ph + 0) % 3], &m = A[(ph + 1) % 3], &bq = A[(ph + 2) % 3];
-                    u64 klo, khi;
-                    stencil_rows2(kw2, t, m, bq, klo, khi);
+                    u64 klo, khi, ivlo = inv2, ivhi = inv2;
+                    if (KEYED) {  // rows k-2, k-1, k
+                        u64 out[4];
+                        stencil_rows_keys(s_tab, s_inv, ring_k[((k - 2 + ST_KDEPTH) % ST_KDEPTH) * 32 + lane],
+                                          ring_k[((k - 1 + ST_KDEPTH) % ST_KDEPTH) * 32 + lane],
+                                          ring_k[(k % ST_KDEPTH) * 32 + lane], t, m, bq, out);
+                        klo = out[0];
+                        khi = out[1];
+                        ivlo = out[2];
+                        ivhi = out[3];
+                    } else {
+                        stencil_rows2(kw2, t, m, bq, klo, khi);
+                    }
                     const ulonglong2 ff = *reinterpret_cast<const ulonglong2 *>(&ring_f[((ph + ST_DEPTH - 1) % ST_DEPTH) * 32 + lane]);
-                    u64 olo = add2(mul2(inv2, sub2(ff.x, klo)), m.q[1]);
-                    u64 ohi = add2(mul2(inv2, sub2(ff.y, khi)), m.q[3]);
+                    // u + inv * (f - K u) with TWO roundings (reference: separate mul and add).  ptxas contracts
+                    // mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (measured: the result then carries the fused rounding,
+                    // visible as soon as omega/d is not a power of two), so the sum is written as fma(p, 1, u) = fl(p + u):
+                    // a product feeding an fma's MULTIPLICAND cannot be contracted (and the 1 is a launch parameter, or
+                    // ptxas folds the fma back into an add and contracts again)
+                    const u64 plo = mul2(ivlo, sub2(ff.x, klo)), phi = mul2(ivhi, sub2(ff.y, khi));
+                    const u64 olo = fma2(plo, one2, m.q[1]), ohi = fma2(phi, one2, m.q[3]);
                     float o0, o1, o2, o3;
                     unpack2(olo, o0, o1);
                     unpack2(ohi, o2, o3);
@@ -740,7 +845,17 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
                     if (!GUARD || k >= 4) {
                         const int yr = a - 2;
                         u64 rlo, rhi;
-                        stencil_rows2(kw2, Bw[(ph + 0) % 3], Bw[(ph + 1) % 3], Bw[(ph + 2) % 3], rlo, rhi);
+                        if (KEYED) {  // rows k-3, k-2, k-1
+                            u64 out[4];
+                            stencil_rows_keys(s_tab, s_inv, ring_k[((k - 3 + ST_KDEPTH) % ST_KDEPTH) * 32 + lane],
+                                              ring_k[((k - 2 + ST_KDEPTH) % ST_KDEPTH) * 32 + lane],
+                                              ring_k[((k - 1 + ST_KDEPTH) % ST_KDEPTH) * 32 + lane], Bw[(ph + 0) % 3],
+                                              Bw[(ph + 1) % 3], Bw[(ph + 2) % 3], out);
+                            rlo = out[0];
+                            rhi = out[1];
+                        } else {
+                            stencil_rows2(kw2, Bw[(ph + 0) % 3], Bw[(ph + 1) % 3], Bw[(ph + 2) % 3], rlo, rhi);
+                        }
                         const ulonglong2 f2 = *reinterpret_cast<const ulonglong2 *>(&ring_f[((ph + ST_DEPTH - 2) % ST_DEPTH) * 32 + lane]);
                         rlo = sub2(f2.x, rlo);
                         rhi = sub2(f2.y, rhi);
@@ -808,14 +923,49 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
         using F_ = std::false_type;
         // steady state: k0 >= 6 (pipeline full, all store rows >= y0) and k0 + 5 <= K - 4 (all store rows < y1)
         int k0 = 0;
-        if (edge) {
-            for (; k0 < K; k0 += 6) block6(T_{}, T_{}, T_{}, k0);
+        if (!KEYS) {
+            if (edge) {
+                for (; k0 < K; k0 += 6) block6(T_{}, T_{}, T_{}, F_{}, k0);
+            } else {
+                block6(T_{}, F_{}, T_{}, F_{}, 0);
+                // steady state: no pipeline / store-range guards; prefetches unchecked while every prefetched row exists
+                for (k0 = 6; k0 + 5 <= K - 4 && k0 + 5 + ST_DEPTH - 1 < khi; k0 += 6) block6(F_{}, F_{}, F_{}, F_{}, k0);
+                for (; k0 + 5 <= K - 4; k0 += 6) block6(F_{}, F_{}, T_{}, F_{}, k0);
+                for (; k0 < K; k0 += 6) block6(T_{}, F_{}, T_{}, F_{}, k0);
+            }
         } else {
-            block6(T_{}, F_{}, T_{}, 0);
-            // steady state: no pipeline / store-range guards; prefetches unchecked while every prefetched row exists
-            for (k0 = 6; k0 + 5 <= K - 4 && k0 + 5 + ST_DEPTH - 1 < khi; k0 += 6) block6(F_{}, F_{}, F_{}, k0);
-            for (; k0 + 5 <= K - 4; k0 += 6) block6(F_{}, F_{}, T_{}, k0);
-            for (; k0 < K; k0 += 6) block6(T_{}, F_{}, T_{}, k0);
+            int prev_key = -2;  // uniform key of the previous block (-1: mixed, -2: no previous block)
+            asm volatile("cp.async.wait_group %0;" ::"n"(ST_DEPTH - 4) : "memory");  // block 0's keys (first group) are in
+            for (; k0 < K; k0 += 6) {
+                // one vote per block: do the 6 rows carry ONE pattern over the whole strip?
+                const unsigned int w0 = ring_k[(k0 % ST_KDEPTH) * 32 + lane];
+                const unsigned int pat = (__shfl_sync(0xffffffffu, w0, 0) & 0xffu) * 0x01010101u;
+                unsigned int diff = w0 ^ pat;
+#pragma unroll
+                for (int j = 1; j < 6; ++j) diff |= ring_k[((k0 + j) % ST_KDEPTH) * 32 + lane] ^ pat;
+                const int bkey = __all_sync(0xffffffffu, diff == 0u) ? (int)(pat & 0xffu) : -1;
+                const bool fast = (bkey >= 0) && (prev_key == -2 || prev_key == bkey);
+                prev_key = bkey;
+                if (!fast) {
+                    block6(T_{}, T_{}, T_{}, T_{}, k0);
+                    continue;
+                }
+                if (bkey != kcur) {  // entering / leaving the inclusion: this pattern's weights into the registers
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) {
+                        const float w = s_tab[9 * bkey + q];
+                        kw2[q] = pack2(w, w);
+                    }
+                    const float iv = s_inv[bkey];
+                    inv2 = pack2(iv, iv);
+                    kcur = bkey;
+                }
+                if (edge) block6(T_{}, T_{}, T_{}, F_{}, k0);
+                else if (k0 == 0) block6(T_{}, F_{}, T_{}, F_{}, k0);
+                else if (k0 + 5 <= K - 4 && k0 + 5 + ST_DEPTH - 1 < khi) block6(F_{}, F_{}, F_{}, F_{}, k0);
+                else if (k0 + 5 <= K - 4) block6(F_{}, F_{}, T_{}, F_{}, k0);
+                else block6(T_{}, F_{}, T_{}, F_{}, k0);
+            }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (MODE == 1 && p.want_norm) {

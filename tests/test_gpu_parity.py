@@ -494,7 +494,7 @@ def test_full_size_properties_4097():
 
 
 # ------------------------------------------------------------------------------------------ row slabs (multi-GPU path)
-def _slab_worker(rank, world, n, dist_min_n, port, p2p, ret):
+def _slab_worker(rank, world, n, dist_min_n, port, p2p, ret, prop=None):
     import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -510,7 +510,7 @@ def _slab_worker(rank, world, n, dist_min_n, port, p2p, ret):
         rs = np.random.RandomState(3)
         u0 = rs.standard_normal((n + 1, n + 1)).astype(np.float32)
         f = 0.01 * rs.standard_normal((n + 1, n + 1)).astype(np.float32)
-        mg = SlabMultigrid(n, dist_min_n=dist_min_n, p2p=p2p)
+        mg = SlabMultigrid(n, dist_min_n=dist_min_n, p2p=p2p, prop=prop)
         mg.set_problem(torch.from_numpy(u0), torch.from_numpy(f))
         hist = mg.Solve(n_iter=3)
         sol = mg.gather_solution()
@@ -546,6 +546,33 @@ def test_slab_kernels_match_single_gpu(world, n, dist_min_n, p2p):
     assert ret["ld"] >= 2
     exact(ret["sol"], prob.grids[0].v.numpy()[0, 0], "slab solution")
     assert np.allclose(ret["hist"], res, rtol=1e-12)
+
+
+@pytest.mark.parametrize("world,n,dist_min_n,prop", [(2, 512, 129, (1, 20)), (4, 1024, 257, (1, 100))])
+def test_slab_two_phase_matches_single_gpu(world, n, dist_min_n, prop):
+    """row slabs with a two-phase inclusion (keyed streaming kernels + peer exchange) against the single-GPU cycle on the
+    same mesh (tile kernels): bit-identical solution"""
+    import torch.multiprocessing as mp
+
+    from FEANet.drivers import _InterfaceSingleGrid
+    from FEANet.solver import VCycleEngine
+
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29800 + (os.getpid() % 1000) + world
+    mp.spawn(_slab_worker, args=(world, n, dist_min_n, port, True, ret, prop), nprocs=world, join=True)
+    assert ret["peer"], ret["peer_error"]
+    rs = np.random.RandomState(3)
+    u0 = rs.standard_normal((n + 1, n + 1)).astype(np.float32)
+    f = 0.01 * rs.standard_normal((n + 1, n + 1)).astype(np.float32)
+    L = int(np.log2(n))
+    grids = [_InterfaceSingleGrid(2, n // 2 ** l, prop=prop, shape=0) for l in range(L)]
+    eng = VCycleEngine([g.jac for g in grids], B=1, smoother="jac")
+    eng.set_u(torch.from_numpy(u0))
+    eng.set_f(torch.from_numpy(f))
+    res = eng.run(n_iter=3)
+    exact(ret["sol"], host(eng.solution)[0, 0], "two-phase slab solution")
+    assert np.allclose(ret["hist"], res, rtol=2e-7)
 
 
 # ------------------------------------------------------------------------------------------ fp64 defect correction (8f.1)
@@ -663,3 +690,24 @@ def test_solve_mixed_goes_below_fp32_floor():
     prob.initial_v = torch.zeros(n + 1, n + 1)
     r = prob.SolveMixed([1, 1], EPS=1e-8 * r0)
     assert r[-1] <= 1e-8 * r0 < r[-2]
+
+
+def test_jacobi_omega_not_power_of_two(O):
+    """omega/d = 0.25 (omega = 2/3) hides a fused multiply-add in the Jacobi update; omega = 0.8 does not.  Every kernel
+    family (streaming at 1025, mid at 257, tail at 65) against the oracle, bit-exact"""
+    from FEANet.jacobi import JacobiBlock
+    from FEANet.mesh import MeshSquare
+    from FEANet.model import KNet
+    from FEANet.solver import VCycleEngine
+
+    n, omega = 1024, 0.8
+    L = int(np.log2(n))
+    jacs = []
+    for l in range(L):
+        mesh = MeshSquare(2, n // 2 ** l + 1)
+        jacs.append(JacobiBlock(KNet(mesh), mesh, omega, None, None))
+    levels = O.make_levels(n, None, omega=omega)
+    rs = np.random.RandomState(21)
+    u0 = rs.standard_normal((1, 1, n + 1, n + 1)).astype(np.float32)
+    f = 0.01 * rs.standard_normal((1, n + 1, n + 1)).astype(np.float32)
+    engine_vs_oracle(O, jacs, levels, O.CycleCfg(), {}, u0, f, ncyc=2, name="omega 0.8")

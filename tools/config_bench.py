@@ -80,3 +80,17 @@ for tag, smoother in (("cfg3", "hjac"), ("cfg3jac", "jac")):
         h = eng.run(n_iter=8)
         report(f"{tag}: two-phase circle 1:100, 4097^2, 12 levels, V(1,1) {smoother}, 16-ch R/P", eng, n, L, B, 1,
                [x / r0 for x in h])
+
+if which in ("cfg3bil", "all"):
+    # two-material circle 1:20, 4097^2, 12 levels, Jacobi, full weighting + bilinear prolongation (MM_Interface_error
+    # operators without the level-0 quirk): the configuration the keyed streaming kernels serve
+    n, L, B = 4096, 12, 1
+    grids = [_InterfaceSingleGrid(2, n // 2 ** l, prop=(1, 20), shape=0) for l in range(L)]
+    eng = VCycleEngine([g.jac for g in grids], B=B, smoother="jac")
+    f = grids[0].fnet(torch.ones(1, 1, n + 1, n + 1, device="cuda"))
+    eng.set_u(torch.zeros(1, 1, n + 1, n + 1, device="cuda"))
+    eng.set_f(f)
+    r0 = float(torch.sqrt(eng.residual_sumsq().sum()).item())
+    h = eng.run(n_iter=8)
+    report("cfg3bil: two-phase circle 1:20, 4097^2, 12 levels, V(1,1) jac, FW restriction + bilinear prolongation",
+           eng, n, L, B, 1, [x / r0 for x in h])

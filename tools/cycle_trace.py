@@ -31,8 +31,12 @@ else:
     hnet.load_state_dict({f"convLayers.{i}.weight": torch.from_numpy(OPS["hnet_w"][i]).reshape(1, 1, 3, 3) for i in range(3)})
     R16 = np.repeat((LINEAR_4 / np.float32(4.0)).reshape(1, 9), 16, 0)
     P4 = np.repeat(LINEAR_4.reshape(1, 9), 16, 0)
-    eng = VCycleEngine([g.jac for g in grids], B=1, smoother=mode, hnet=hnet, prolong="table", rtab=R16, r_scale=4.0,
-                       ptab=P4, p_scale=1.0)
+    if mode == "jacbil":  # full weighting + bilinear prolongation: the keyed streaming kernels
+        grids = [_InterfaceSingleGrid(2, n // 2 ** l, prop=(1, 20), shape=0) for l in range(Lv)]
+        eng = VCycleEngine([g.jac for g in grids], B=1, smoother="jac")
+    else:
+        eng = VCycleEngine([g.jac for g in grids], B=1, smoother=mode, hnet=hnet, prolong="table", rtab=R16, r_scale=4.0,
+                           ptab=P4, p_scale=1.0)
     eng.set_u(torch.zeros(1, 1, n + 1, n + 1, device="cuda"))
     eng.set_f(grids[0].fnet(torch.ones(1, 1, n + 1, n + 1, device="cuda")))
 eng.refresh()
@@ -65,5 +69,7 @@ for i in range(0, k, 2):
     print(f"launch {i // 2:2d}: start {acc[i]:8.2f} us  dur {acc[i + 1] - acc[i]:7.2f} us  gap after {(acc[i + 2] - acc[i + 1]) if i + 2 < k else 0:5.2f}")
 print(f"total {acc[k - 1]:8.2f} us over {k // 2} launches")
 tail = tail[tail > 0]
+if len(tail) < 2:
+    sys.exit(0)
 print("tail stages (clock64 deltas, us at 1.965 GHz):", " ".join(f"{d / 1965.0:.2f}" for d in np.diff(tail)))
 print(f"tail total {(tail[-1] - tail[0]) / 1965.0:.2f} us, {len(tail) - 1} stages")
