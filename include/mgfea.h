@@ -208,6 +208,12 @@ int mgfea_p2p_exchange(const mgfea_xchg *x, void *stream);
 int mgfea_defect_f64(const mgfea_grid *g, const double *u, const double *f, float *r, double *sumsq, mgfea_ctl *ctl,
                      double *hist, int B, void *stream);
 int mgfea_correct_f64(const mgfea_grid *g, double *u, const float *e, const mgfea_ctl *ctl, int B, void *stream);
+/* row-slab forms (arrays hold the global rows [s->row0, ..), g->plane = local rows * pitch): the defect is written on
+ * the owned rows and on the 3 ghost rows per side the next down leg reads (u needs 4 valid ghost rows), sumsq covers
+ * the owned rows only (the caller all-reduces it); the correction touches the owned rows */
+int mgfea_slab_defect_f64(const mgfea_grid *g, const mgfea_slab *s, const double *u, const double *f, float *r,
+                          double *sumsq, int B, void *stream);
+int mgfea_slab_correct_f64(const mgfea_grid *g, const mgfea_slab *s, double *u, const float *e, int B, void *stream);
 
 /* ---- whole V-cycle ----------------------------------------------------------------------------------- */
 typedef struct mgfea_cycle_cfg {

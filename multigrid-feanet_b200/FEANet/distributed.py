@@ -111,6 +111,10 @@ class PeerSlabMemory:
             for name in (("u", "u_alt", "f") if l < ld else ("f",)):
                 self.off[(name, l)] = off
                 off += size
+            if l == 0 and l < ld:  # fp64 iterate / right-hand side of the defect-correction solve (SolveMixed)
+                for name in ("u64", "f64"):
+                    self.off[(name, l)] = off
+                    off += 2 * size
         self.block = mgfea.PeerBlock(off)
         self.bases = None
         self.partial = self.block.tensor(self.PARTIAL, (2,), torch.float64)  # [0]: this rank's interior sum of squares
@@ -125,7 +129,8 @@ class PeerSlabMemory:
 
     def array(self, name, l):
         lev = self.part.levels[l]
-        return self.block.tensor(self.off[(name, l)], (1, lev["nrows"], self.pitch[l]), torch.float32)
+        dtype = torch.float64 if name.endswith("64") else torch.float32
+        return self.block.tensor(self.off[(name, l)], (1, lev["nrows"], self.pitch[l]), dtype)
 
     def _build(self, halos, gather, reduce):
         mg, part, rank, world = self.mg, self.part, self.part.rank, self.part.world
@@ -138,7 +143,7 @@ class PeerSlabMemory:
 
         me = self.bases[rank]
         for name, l in halos:  # GHOST boundary rows of my owned range -> the neighbours' ghost rows
-            lev, rowb, off = part.levels[l], self.pitch[l] * 4, self.off[(name, l)]
+            lev, rowb, off = part.levels[l], self.pitch[l] * (8 if name.endswith("64") else 4), self.off[(name, l)]
             for q, first in ((rank - 1, lev["own0"]), (rank + 1, lev["own1"] - GHOST)):
                 if 0 <= q < world:
                     job(me + off + (first - lev["row0"]) * rowb,
@@ -173,7 +178,7 @@ class PeerSlabMemory:
         x.mode = mg.XCHG_PUSH | mg.XCHG_WAIT
         # CTAs of the step: a function of the step alone (NOT of the rank): the flags count the pushing CTAs.  About one
         # 16-byte chunk per thread for the halo rows, more CTAs when whole coarse slabs travel
-        halo_chunks = sum(GHOST * self.pitch[l] * 4 // 16 for _, l in halos) * 2
+        halo_chunks = sum(GHOST * self.pitch[l] * (8 if nm.endswith("64") else 4) // 16 for nm, l in halos) * 2
         gather_chunks = ((part.n // 2 ** part.ld) // world) * self.pitch[part.ld] * 4 // 16 * (world - 1) if gather else 0
         x.grid = int(min(64, max(1, (halo_chunks + gather_chunks // 4 + 255) // 256)))
         return x
@@ -481,7 +486,7 @@ class SlabMultigrid:
             return tot
         return None
 
-    def _cycle_peer(self, want_norm=True):
+    def _cycle_peer(self, want_norm=True, zero_guess=False):
         """the same cycle with every exchange done by peer stores (PeerSlabMemory.step): 2 * ld kernels, no NCCL.
         Buffer discipline (what makes overwriting a neighbour's ghost rows safe without a second handshake): the step
         after down(l) pushes u_alt[l] / f[l+1], the step after up(l) pushes u[l] -- never an array that the kernel
@@ -489,7 +494,8 @@ class SlabMultigrid:
         ops, ld, peer = self.ops, self.part.ld, self.peer
         for l in range(ld):
             last = l == ld - 1
-            ops.down(l, self.u[l] if l == 0 else None, self.u_alt[l], self.f[l], ops.coarse_f() if last else self.f[l + 1])
+            ops.down(l, self.u[l] if (l == 0 and not zero_guess) else None, self.u_alt[l], self.f[l],
+                     ops.coarse_f() if last else self.f[l + 1])
             peer.step((("u_alt", l),) if last else (("u_alt", l), ("f", l + 1)), gather=last)
         ops.coarse_cycle()
         for l in range(ld - 1, -1, -1):
@@ -507,6 +513,77 @@ class SlabMultigrid:
         else:
             halo_exchange(self.u[0], self.part.levels[0], self.rank, self.world, self.group)
             halo_exchange(self.f[0], self.part.levels[0], self.rank, self.world, self.group)
+
+    # ---- fp64 defect correction on the slabs (SURVEY 8f.1 + 8e): iterate / rhs / residual in fp64, cycle in fp32
+    def set_problem64(self, u0_full, f_full):
+        """every rank takes its rows (owned + ghost) of the fp64 problem from the full host arrays; the ring of the
+        iterate is zeroed (the reference's first reset_boundary)"""
+        if self.peer is None:
+            raise self.ops.mg.MgfeaError("SolveMixed on slabs needs the peer-memory exchange")
+        lev = self.part.levels[0]
+        N = lev["N"]
+        rows = slice(lev["row0"], lev["row0"] + lev["nrows"])
+        self.u64, self.f64 = self.peer.array("u64", 0), self.peer.array("f64", 0)
+        for dst, src, ring in ((self.u64, u0_full, True), (self.f64, f_full, False)):
+            src = torch.as_tensor(src).reshape(N, N).to(torch.float64)
+            if ring:
+                src = src.clone()
+                src[0, :] = 0
+                src[-1, :] = 0
+                src[:, 0] = 0
+                src[:, -1] = 0
+            dst.zero_()
+            dst[0, :, :N].copy_(src[rows], non_blocking=True)
+
+    def SolveMixed(self, n_iter=None, EPS=None, max_cycles=200):
+        """Multigrid.Solve semantics on the fp64 problem set by set_problem64: every step is one slab V-cycle (fp32, zero
+        guess) on the fp64 residual.  Returns the fp64 interior residual 2-norms after each cycle; `self.u64` holds the
+        local rows of the solution (gather_solution64 assembles it)."""
+        mg, ops, peer = self.ops.mg, self.ops, self.peer
+        if n_iter is None:
+            n_iter = 0
+        elif EPS is None:
+            EPS = math.inf
+        lev = self.part.levels[0]
+        g = ops._grid(0, self.f[0])
+        sl = ops._slab(0)
+
+        def defect():
+            peer.step((("u64", 0),))  # 4 ghost rows of the iterate: the defect is also formed on 3 ghost rows per side
+            mg.check(mg.lib().mgfea_slab_defect_f64(ctypes.byref(g), ctypes.byref(sl), self.u64.data_ptr(),
+                                                    self.f64.data_ptr(), self.f[0].data_ptr(), peer.partial.data_ptr(), 1,
+                                                    mg.stream_ptr()))
+            peer.step((), reduce=True)
+            return float(torch.sqrt(peer.total.sum()).item())
+
+        self.r0 = defect()
+        res, hist = self.r0, []
+        while (res > EPS or len(hist) < n_iter) and len(hist) < max_cycles:
+            self._cycle_peer(want_norm=False, zero_guess=True)  # e = V-cycle(0, r) -> u[0]
+            mg.check(mg.lib().mgfea_slab_correct_f64(ctypes.byref(g), ctypes.byref(sl), self.u64.data_ptr(),
+                                                     self.u[0].data_ptr(), 1, mg.stream_ptr()))
+            res = defect()
+            hist.append(res)
+        peer.check()
+        self.residuals = hist
+        return hist
+
+    def gather_solution64(self):
+        """full fp64 solution on every rank (host tensor)"""
+        lev = self.part.levels[0]
+        N = lev["N"]
+        own = self.u64[0, lev["own0"] - lev["row0"]: lev["own1"] - lev["row0"], :N].contiguous()
+        per = self.n // self.world
+        chunk = torch.zeros((per + 1, N), dtype=own.dtype)
+        chunk[: own.shape[0]] = own.cpu()
+        out = [torch.zeros_like(chunk) for _ in range(self.world)]
+        if dist.get_backend(self.group) == "nccl":
+            outd = [o.to(own.device) for o in out]
+            dist.all_gather(outd, chunk.to(own.device), group=self.group)
+            out = [o.cpu() for o in outd]
+        else:
+            dist.all_gather(out, chunk, group=self.group)
+        return torch.cat([o[:per] for o in out[:-1]] + [out[-1][: per + 1]], dim=0)
 
     def Solve(self, n_iter=None, EPS=None, max_cycles=200):
         """Multigrid.Solve semantics (MM_Model_convergence.ipynb cell 3): cycles while (res > EPS or n < n_iter)"""

@@ -30,7 +30,7 @@ EXPORTS = [
     "mgfea_slab_smooth_residual_restrict", "mgfea_slab_prolong_correct_smooth",
     "mgfea_peer_alloc", "mgfea_peer_free", "mgfea_peer_export", "mgfea_peer_open", "mgfea_peer_close",
     "mgfea_p2p_exchange", "mgfea_trace", "mgfea_prolong_correct_smooth_norm",
-    "mgfea_defect_f64", "mgfea_correct_f64",
+    "mgfea_defect_f64", "mgfea_correct_f64", "mgfea_slab_defect_f64", "mgfea_slab_correct_f64",
 ]
 
 
@@ -134,6 +134,8 @@ def lib():
                                                         i32, vp, i32, vp]
         L.mgfea_defect_f64.argtypes = [G, vp, vp, vp, vp, vp, vp, i32, vp]
         L.mgfea_correct_f64.argtypes = [G, vp, vp, vp, i32, vp]
+        L.mgfea_slab_defect_f64.argtypes = [G, ctypes.POINTER(Slab), vp, vp, vp, vp, i32, vp]
+        L.mgfea_slab_correct_f64.argtypes = [G, ctypes.POINTER(Slab), vp, vp, i32, vp]
         L.mgfea_restrict_channels.argtypes = [vp, vp, vp, i32, i32, i32, vp]
         L.mgfea_prolong_channels.argtypes = [vp, vp, vp, i32, i32, i32, vp]
         L.mgfea_residual_norm.argtypes = [G, vp, vp, vp, vp, vp, i32, vp]

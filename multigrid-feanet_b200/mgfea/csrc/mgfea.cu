@@ -1776,8 +1776,8 @@ int mgfea_p2p_exchange(const mgfea_xchg *x, void *stream) {
 }
 
 /* ---- fp64 defect correction (mgfea_f64.cuh) -------------------------------------------------------------- */
-int mgfea_defect_f64(const mgfea_grid *g, const double *u, const double *f, float *r, double *sumsq, mgfea_ctl *ctl,
-                     double *hist, int B, void *stream) {
+static int defect_f64(const mgfea_grid *g, const mgfea_slab *sl, const double *u, const double *f, float *r,
+                      double *sumsq, mgfea_ctl *ctl, double *hist, int B, void *stream) {
     if (!g || !u || !f || !r || B < 1 || g->N < 3) return MGFEA_EINVAL;
     if (g->bc_idx) return MGFEA_EUNSUPPORTED;  // the correction equation has the homogeneous default ring
     if ((g->pitch & 3) || (g->plane & 3) || ((reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(f)) & 15u) ||
@@ -1797,8 +1797,23 @@ int mgfea_defect_f64(const mgfea_grid *g, const double *u, const double *f, floa
     p.key_pitch = g->key_pitch;
     p.npat = g->npat;
     p.ktab = g->ktab;
+    if (sl) {  // owned rows + the 3 ghost rows per side the next down leg reads; needs u on one more row each side
+        if (sl->own0 < 0 || sl->own1 > g->N || sl->own0 >= sl->own1 || sl->own0 < sl->row0 ||
+            sl->own1 > sl->row0 + sl->nrows)
+            return MGFEA_EINVAL;
+        p.row0 = sl->row0;
+        p.own0 = sl->own0;
+        p.own1 = sl->own1;
+        p.ylo = sl->own0 - 3 > 0 ? sl->own0 - 3 : 0;
+        p.yhi = sl->own1 + 3 < g->N ? sl->own1 + 3 : g->N;
+        if ((p.ylo > 0 && p.ylo - 1 < sl->row0) || (p.yhi < g->N && p.yhi + 1 > sl->row0 + sl->nrows)) return MGFEA_EINVAL;
+    } else {
+        p.row0 = 0;
+        p.own0 = p.ylo = 0;
+        p.own1 = p.yhi = g->N;
+    }
     p.nbx = (g->pitch / 2 + F64_TX - 1) / F64_TX;
-    p.nby = (g->N + F64_TY - 1) / F64_TY;
+    p.nby = (p.yhi - p.ylo + F64_TY - 1) / F64_TY;
     if (p.nby > 65535 || B > 65535) return MGFEA_EUNSUPPORTED;
     DeviceScratch *scr = nullptr;
     int rc = get_scratch((size_t)p.nbx * p.nby * B, &scr);
@@ -1819,11 +1834,14 @@ int mgfea_defect_f64(const mgfea_grid *g, const double *u, const double *f, floa
     return (int)cudaGetLastError();
 }
 
-int mgfea_correct_f64(const mgfea_grid *g, double *u, const float *e, const mgfea_ctl *ctl, int B, void *stream) {
+static int correct_f64(const mgfea_grid *g, const mgfea_slab *sl, double *u, const float *e, const mgfea_ctl *ctl, int B,
+                       void *stream) {
     if (!g || !u || !e || B < 1) return MGFEA_EINVAL;
     if ((g->pitch & 3) || (g->plane & 3) || (reinterpret_cast<uintptr_t>(u) & 15u) || (reinterpret_cast<uintptr_t>(e) & 7u))
         return MGFEA_EALIGN;
-    const long long total = (long long)B * g->N * (g->pitch / 2);
+    const int own0 = sl ? sl->own0 : 0, own1 = sl ? sl->own1 : g->N, row0 = sl ? sl->row0 : 0;
+    if (own0 < row0 || own1 <= own0 || own1 > g->N) return MGFEA_EINVAL;
+    const long long total = (long long)B * (own1 - own0) * (g->pitch / 2);
     DeviceScratch *scr = nullptr;
     int rc = get_scratch(1, &scr);
     if (rc) return rc;
@@ -1831,10 +1849,28 @@ int mgfea_correct_f64(const mgfea_grid *g, double *u, const float *e, const mgfe
     const long long maxb = (long long)scr->num_sms * 16;
     if (blocks > maxb) blocks = maxb;
     trace_stamp((cudaStream_t)stream);
-    mg_correct_f64_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(u, e, g->N, g->pitch, g->plane, B, ctl);
+    mg_correct_f64_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(u, e, g->N, g->pitch, g->plane, B, ctl, own0, own1,
+                                                                          row0);
     trace_stamp((cudaStream_t)stream);
     g_launches.fetch_add(1);
     return (int)cudaGetLastError();
+}
+
+int mgfea_defect_f64(const mgfea_grid *g, const double *u, const double *f, float *r, double *sumsq, mgfea_ctl *ctl,
+                     double *hist, int B, void *stream) {
+    return defect_f64(g, nullptr, u, f, r, sumsq, ctl, hist, B, stream);
+}
+int mgfea_correct_f64(const mgfea_grid *g, double *u, const float *e, const mgfea_ctl *ctl, int B, void *stream) {
+    return correct_f64(g, nullptr, u, e, ctl, B, stream);
+}
+int mgfea_slab_defect_f64(const mgfea_grid *g, const mgfea_slab *s, const double *u, const double *f, float *r,
+                          double *sumsq, int B, void *stream) {
+    if (!s) return MGFEA_EINVAL;
+    return defect_f64(g, s, u, f, r, sumsq, nullptr, nullptr, B, stream);
+}
+int mgfea_slab_correct_f64(const mgfea_grid *g, const mgfea_slab *s, double *u, const float *e, int B, void *stream) {
+    if (!s) return MGFEA_EINVAL;
+    return correct_f64(g, s, u, e, nullptr, B, stream);
 }
 
 int mgfea_vcycle(const mgfea_grid *grids, const mgfea_level_bufs *bufs, int nlevels, const mgfea_cycle_cfg *cfg,

@@ -28,6 +28,10 @@ struct F64Params {
     int key_pitch, npat;
     const float *ktab;
     int nbx, nby;  // blocks per sample in x / y
+    // row slab (multi-GPU): the arrays hold the global rows [row0, ..); rows [ylo, yhi) are computed (the owned rows
+    // plus the 3 ghost rows per side the next down leg reads), the norm covers the owned rows [own0, own1) only.
+    // Single GPU: row0 = 0, [ylo, yhi) = [own0, own1) = [0, N)
+    int row0, ylo, yhi, own0, own1;
     double *partials;
     unsigned int *counter;
     double *sumsq;
@@ -52,10 +56,10 @@ __global__ void __launch_bounds__(F64_TX *F64_TY) mg_defect_f64_kernel(const F64
     __syncthreads();
     if (solve_done) return;
     const int N = p.N, b = blockIdx.z;
-    const int x = (blockIdx.x * F64_TX + threadIdx.x) * 2, y = blockIdx.y * F64_TY + threadIdx.y;
-    const double *ub = p.u + (long long)b * p.plane;
+    const int x = (blockIdx.x * F64_TX + threadIdx.x) * 2, y = p.ylo + blockIdx.y * F64_TY + threadIdx.y;
+    const double *ub = p.u + (long long)b * p.plane - (long long)p.row0 * p.pitch;  // indexed by GLOBAL row below
     double part = 0.0;
-    if (y < N && x < p.pitch) {
+    if (y < p.yhi && x < p.pitch) {
         double r0 = 0.0, r1 = 0.0;
         const bool rin = (y >= 1 && y <= N - 2);
         if (rin && x <= N - 2) {  // at least one of the two columns may be interior
@@ -84,13 +88,13 @@ __global__ void __launch_bounds__(F64_TX *F64_TY) mg_defect_f64_kernel(const F64
                     acc1 = fma(tab[9 * k[q + 1] + 3 * d + q], v[q + 1], acc1);
                 }
             }
-            const double2 fv = *reinterpret_cast<const double2 *>(p.f + (long long)b * p.plane + (long long)y * p.pitch + x);
+            const double2 fv = *reinterpret_cast<const double2 *>(p.f + (long long)b * p.plane + (long long)(y - p.row0) * p.pitch + x);
             if (x >= 1) r0 = fv.x - acc0;
             if (x + 1 <= N - 2) r1 = fv.y - acc1;
         }
-        *reinterpret_cast<float2 *>(p.r + (long long)b * p.plane + (long long)y * p.pitch + x) =
+        *reinterpret_cast<float2 *>(p.r + (long long)b * p.plane + (long long)(y - p.row0) * p.pitch + x) =
             make_float2((float)r0, (float)r1);
-        part = r0 * r0 + r1 * r1;
+        if (y >= p.own0 && y < p.own1) part = r0 * r0 + r1 * r1;
     }
     // ---- block partial -> per-sample sum by the last block (deterministic order), convergence control
     part = warp_sum_f64(part);
@@ -142,20 +146,22 @@ __global__ void __launch_bounds__(F64_TX *F64_TY) mg_defect_f64_kernel(const F64
     }
 }
 
+// rows [own0, own1) of arrays that hold the global rows [row0, ..) (single GPU: 0, N, 0)
 __global__ void __launch_bounds__(256) mg_correct_f64_kernel(double *u, const float *e, int N, int pitch, long long plane,
-                                                            int B, const void *ctl) {
+                                                            int B, const void *ctl, int own0, int own1, int row0) {
     if (ctl != nullptr && ld_volatile_s32(&reinterpret_cast<const Ctl *>(ctl)->done) != 0) return;
     const int half = pitch >> 1;  // column pairs per row
-    const long long total = (long long)B * N * half;
+    const int nown = own1 - own0;
+    const long long total = (long long)B * nown * half;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int xp = (int)(i % half);
         const long long ry = i / half;
-        const int y = (int)(ry % N);
-        const long long b = ry / N;
+        const int y = own0 + (int)(ry % nown);
+        const long long b = ry / nown;
         if (y < 1 || y > N - 2) continue;
         const int x = 2 * xp;
         if (x > N - 2) continue;
-        const long long o = b * plane + (long long)y * pitch + x;
+        const long long o = b * plane + (long long)(y - row0) * pitch + x;
         const float2 ev = *reinterpret_cast<const float2 *>(e + o);
         double2 uv = *reinterpret_cast<double2 *>(u + o);
         if (x >= 1) uv.x += (double)ev.x;

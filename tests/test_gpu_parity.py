@@ -494,7 +494,7 @@ def test_full_size_properties_4097():
 
 
 # ------------------------------------------------------------------------------------------ row slabs (multi-GPU path)
-def _slab_worker(rank, world, n, dist_min_n, port, p2p, ret, prop=None):
+def _slab_worker(rank, world, n, dist_min_n, port, p2p, ret, prop=None, mixed=False):
     import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -511,9 +511,14 @@ def _slab_worker(rank, world, n, dist_min_n, port, p2p, ret, prop=None):
         u0 = rs.standard_normal((n + 1, n + 1)).astype(np.float32)
         f = 0.01 * rs.standard_normal((n + 1, n + 1)).astype(np.float32)
         mg = SlabMultigrid(n, dist_min_n=dist_min_n, p2p=p2p, prop=prop)
-        mg.set_problem(torch.from_numpy(u0), torch.from_numpy(f))
-        hist = mg.Solve(n_iter=3)
-        sol = mg.gather_solution()
+        if mixed:
+            mg.set_problem64(torch.from_numpy(u0), torch.from_numpy(f))
+            hist = mg.SolveMixed(n_iter=12)
+            sol = mg.gather_solution64()
+        else:
+            mg.set_problem(torch.from_numpy(u0), torch.from_numpy(f))
+            hist = mg.Solve(n_iter=3)
+            sol = mg.gather_solution()
         if rank == 0:
             ret["hist"], ret["sol"], ret["ld"] = hist, sol.numpy(), mg.part.ld
             ret["peer"], ret["peer_error"] = mg.peer is not None, getattr(mg, "peer_error", None)
@@ -573,6 +578,32 @@ def test_slab_two_phase_matches_single_gpu(world, n, dist_min_n, prop):
     res = eng.run(n_iter=3)
     exact(ret["sol"], host(eng.solution)[0, 0], "two-phase slab solution")
     assert np.allclose(ret["hist"], res, rtol=2e-7)
+
+
+@pytest.mark.parametrize("world,n,dist_min_n", [(2, 512, 129), (4, 1024, 257)])
+def test_slab_mixed_precision_matches_single_gpu(world, n, dist_min_n):
+    """fp64 defect correction on row slabs (mgfea_slab_defect_f64 / _correct_f64 + peer exchange of the fp64 halo) against
+    Multigrid.SolveMixed on one GPU: bit-identical fp64 solution, same residual history, below the fp32 floor"""
+    import torch.multiprocessing as mp
+
+    from FEANet.drivers import Multigrid
+
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29900 + (os.getpid() % 1000) + world
+    mp.spawn(_slab_worker, args=(world, n, dist_min_n, port, True, ret, None, True), nprocs=world, join=True)
+    assert ret["peer"], ret["peer_error"]
+    rs = np.random.RandomState(3)
+    u0 = rs.standard_normal((n + 1, n + 1)).astype(np.float32)
+    f = 0.01 * rs.standard_normal((n + 1, n + 1)).astype(np.float32)
+    prob = Multigrid(n)
+    prob.initial_v = torch.from_numpy(u0)
+    prob.grids[0].f = torch.from_numpy(f).reshape(1, 1, n + 1, n + 1)
+    res = prob.SolveMixed([1, 1], n_iter=12)
+    assert np.allclose(ret["hist"], res, rtol=1e-10)
+    assert res[-1] / res[0] < 1e-5
+    got, want = ret["sol"], prob.grids[0].v.numpy()[0, 0]
+    assert got.dtype == np.float64 and np.array_equal(got, want)
 
 
 # ------------------------------------------------------------------------------------------ fp64 defect correction (8f.1)
