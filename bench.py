@@ -374,8 +374,6 @@ def run_ours(args):
     # section 2): fp64 defect correction around the fp32 cycle (Multigrid.SolveMixed), device resident
     mixed = None
     if not args.no_mixed:
-        from FEANet.model import FNet  # noqa: F401
-
         g = torch.Generator(device="cuda").manual_seed(0)
         Fr = torch.randn(1, 1, N, N, generator=g, device="cuda")
         prob.grids[0].f = prob.grids[0].fnet(Fr)
@@ -426,6 +424,12 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def mg_r0(mg):
+    """initial fp64 residual norm of the slab problem (collective)"""
+    mg.SolveMixed(n_iter=0, EPS=float("inf"))
+    return mg.r0
+
+
 def run_multi(args):
     """N > 1: ONE problem partitioned into row slabs (FEANet.distributed): NCCL halo exchange, replicated coarse levels"""
     import ctypes
@@ -446,7 +450,8 @@ def run_multi(args):
     dof = N * N
     L = int(np.log2(n))
     steps, warm = args.steps, max(args.warmup, 3)
-    mg = SlabMultigrid(n)
+    prop = tuple(float(x) for x in args.prop.split(",")) if args.prop else None
+    mg = SlabMultigrid(n, prop=prop)  # --prop a,b: two-phase circle inclusion (keyed streaming kernels on the slabs)
     lev = mg.part.levels[0]
 
     def u_rows(row0, nrows, NN):  # same random family as the reference's model problem, generated per rank on the device
@@ -551,13 +556,33 @@ def run_multi(args):
     te = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
     dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_dt = float(te.item())
+    # ---- time to 1e-8 relative residual, nonzero right-hand side: fp64 defect correction on the slabs (device resident)
+    mixed = None
+    if mg.peer is not None and not args.no_mixed:
+        def f_rows(row0, nrows, NN):
+            g = torch.Generator(device="cuda").manual_seed(777 + rank)
+            return 1e-3 * torch.randn((nrows, NN), generator=g, device="cuda", dtype=torch.float64)
+
+        mg.fill_local64(f_rows)
+        mg.SolveMixed(n_iter=1)  # warm-up
+        mg.fill_local64(f_rows)
+        barrier()
+        t0 = time.perf_counter()
+        hm = mg.SolveMixed(EPS=1e-8 * mg_r0(mg), max_cycles=60)
+        torch.cuda.synchronize()
+        tm = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        mixed = {"cycles_to_1e-8_rel": len(hm), "ms": 1e3 * float(tm.item()), "final_rel_residual": hm[-1] / mg.r0,
+                 "what": "1e-3 * randn right-hand side, u0 = 0; iterate / residual fp64 on the slabs, V-cycle fp32; "
+                         "host checks the all-reduced norm every cycle"}
     xname = ("halo rows stored straight into the neighbours' ghost rows over NVLink peer memory, one exchange kernel "
              "per step, no NCCL on the data path") if mg.peer is not None else "NCCL send/recv halo exchange"
     if rank == 0:
         line = {"metric": METRIC, "value": cycles_per_s * dof / 1e9, "unit": "GDOF/s", "n_gpus": world, "steps": steps,
                 "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "v_cycles_per_s": cycles_per_s,
-                "config": {"workload": f"iso Poisson {N}x{N}, V(1,1), {L} levels, single RHS partitioned into {world} "
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "v_cycles_per_s": cycles_per_s, "mixed_precision_solve": mixed,
+                "config": {"workload": (f"two-phase circle {args.prop} " if prop else "iso ") +
+                                       f"Poisson {N}x{N}, V(1,1), {L} levels, single RHS partitioned into {world} "
                                        f"row slabs ({xname}, levels N<2049 replicated), f=0 model problem; "
                                        f"{dof / world / 1e6:.1f} MDOF per GPU (N=1 runs 16.8 MDOF)",
                            "n": n, "levels": L, "nu": [1, 1], "batch": 1, "first_replicated_level": mg.part.ld,
@@ -600,6 +625,7 @@ def main():
     ap.add_argument("--loader", default="tma", choices=["tma", "cpasync"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--prop", default="", help="N > 1 only: conductivities a,b of a two-phase circle inclusion (e.g. 1,20)")
     ap.add_argument("--no-mixed", action="store_true", help="skip the fp64 defect-correction time-to-tolerance run")
     ap.add_argument("--n-multi", type=int, default=0, help="grid intervals for the row-slab run at N > 1 (default by N)")
     args = ap.parse_args()

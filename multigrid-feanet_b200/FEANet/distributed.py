@@ -83,29 +83,25 @@ def halo_exchange(arr, lev, rank, world, group=None):
             recv.copy_(rb)
 
 
-class PeerSlabMemory:
-    """Slab arrays + exchange mailbox of one rank in a block the other ranks of the node map through cudaIpc
-    (mgfea.PeerBlock), and the exchange steps over it (mgfea_p2p_exchange): the ranks store their boundary rows straight
-    into the neighbours' ghost rows over NVLink, one kernel per step, no collective library on the data path.
-
-    The layout is identical on every rank (arrays sized for the largest slab), so a peer's address of any row is
-    base[q] + offset(array) + (global row - row0 of rank q) * pitch.
-    """
+class SlabExchangePlan:
+    """Pure host logic of the peer exchange: the byte layout of a rank's block (identical on every rank, arrays sized
+    for the largest slab) and, per exchange step, WHAT goes WHERE -- copy jobs as (source offset, destination rank,
+    destination offset, bytes), the flags to raise in the targets' mailboxes, the flags to wait for, the CTA count.
+    No CUDA here, so tests/test_distributed_cpu.py checks every rank's plans against each other."""
     # mailbox (bytes): flags written by the neighbours / by every rank, partial-sum slots, this rank's step counters
     FLAG_UP, FLAG_DOWN, ALL_FLAGS, SLOTS, SEQ_NB, SEQ_ALL, ERR, PARTIAL, TOTAL, MAILBOX = 0, 16, 64, 256, 512, 528, 544, 576, 592, 4096
+    MAX_PEERS = 8
 
-    def __init__(self, part, group=None):
-        import mgfea
-
-        self.mg, self.part, self.group = mgfea, part, group
+    def __init__(self, part, pitch_for):
+        self.part = part
         world, rank, ld = part.world, part.rank, part.ld
-        if world > mgfea.XCHG_MAX_PEERS:
-            raise mgfea.MgfeaError(f"peer exchange supports up to {mgfea.XCHG_MAX_PEERS} ranks")
+        if world > self.MAX_PEERS:
+            raise ValueError(f"peer exchange supports up to {self.MAX_PEERS} ranks")
         self.parts = [part if q == rank else SlabPartition(part.n, part.L, world, q, part.dist_min_n) for q in range(world)]
         off, self.off, self.pitch = self.MAILBOX, {}, {}
         for l in range(ld + 1):
             N = part.levels[l]["N"]
-            self.pitch[l] = mgfea.pitch_for(N)
+            self.pitch[l] = pitch_for(N)
             rows = max(p.levels[l]["nrows"] for p in self.parts)
             size = (rows * self.pitch[l] * 4 + 255) // 256 * 256
             for name in (("u", "u_alt", "f") if l < ld else ("f",)):
@@ -115,7 +111,66 @@ class PeerSlabMemory:
                 for name in ("u64", "f64"):
                     self.off[(name, l)] = off
                     off += 2 * size
-        self.block = mgfea.PeerBlock(off)
+        self.nbytes = off
+
+    @staticmethod
+    def esize(name):
+        return 8 if name.endswith("64") else 4
+
+    def plan(self, halos, gather=False, reduce=False):
+        """jobs [(src_off, dst_rank, dst_off, nbytes)], signals [(rank, flag_off)], waits [flag_off], seq_off, grid,
+        red = (src_off, dst_off, n, stride) or None"""
+        part, rank, world = self.part, self.part.rank, self.part.world
+        jobs = []
+        for name, l in halos:  # GHOST boundary rows of my owned range -> the neighbours' ghost rows
+            lev, rowb, off = part.levels[l], self.pitch[l] * self.esize(name), self.off[(name, l)]
+            for q, first in ((rank - 1, lev["own0"]), (rank + 1, lev["own1"] - GHOST)):
+                if 0 <= q < world:
+                    jobs.append((off + (first - lev["row0"]) * rowb, q,
+                                 off + (first - self.parts[q].levels[l]["row0"]) * rowb, GHOST * rowb))
+        if gather:  # my owned rows of the first replicated level's right-hand side -> every peer
+            ld = part.ld
+            per, rowb, off = (part.n // 2 ** ld) // world, self.pitch[ld] * 4, self.off[("f", ld)]
+            jobs += [(off + rank * per * rowb, q, off + rank * per * rowb, per * rowb) for q in range(world) if q != rank]
+        red = None
+        if reduce:  # my partial sum -> slot [rank] of every mailbox (mine included); summed in rank order after the wait
+            jobs += [(self.PARTIAL, q, self.SLOTS + 16 * rank, 16) for q in range(world)]
+            red = (self.SLOTS, self.TOTAL, world, 16)
+        if gather or reduce:
+            signals = [(q, self.ALL_FLAGS + 16 * rank) for q in range(world) if q != rank]
+            waits = [self.ALL_FLAGS + 16 * q for q in range(world) if q != rank]
+            seq = self.SEQ_ALL
+        else:
+            signals, waits, seq = [], [], self.SEQ_NB
+            if rank > 0:
+                signals.append((rank - 1, self.FLAG_DOWN))
+                waits.append(self.FLAG_UP)
+            if rank < world - 1:
+                signals.append((rank + 1, self.FLAG_UP))
+                waits.append(self.FLAG_DOWN)
+        # CTAs of the step: a function of the step alone (NOT of the rank): the flags count the pushing CTAs.  About one
+        # 16-byte chunk per thread for the halo rows, more CTAs when whole coarse slabs travel
+        halo_chunks = sum(GHOST * self.pitch[l] * self.esize(nm) // 16 for nm, l in halos) * 2
+        gather_chunks = ((part.n // 2 ** part.ld) // world) * self.pitch[part.ld] * 4 // 16 * (world - 1) if gather else 0
+        grid = int(min(64, max(1, (halo_chunks + gather_chunks // 4 + 255) // 256)))
+        return dict(jobs=jobs, signals=signals, waits=waits, seq=seq, grid=grid, red=red)
+
+
+class PeerSlabMemory(SlabExchangePlan):
+    """Slab arrays + exchange mailbox of one rank in a block the other ranks of the node map through cudaIpc
+    (mgfea.PeerBlock), and the exchange steps over it (mgfea_p2p_exchange): the ranks store their boundary rows straight
+    into the neighbours' ghost rows over NVLink, one kernel per step, no collective library on the data path.
+
+    The layout is identical on every rank (SlabExchangePlan), so a peer's address of any row is
+    base[q] + offset(array) + (global row - row0 of rank q) * pitch.
+    """
+
+    def __init__(self, part, group=None):
+        import mgfea
+
+        super().__init__(part, mgfea.pitch_for)
+        self.mg, self.group = mgfea, group
+        self.block = mgfea.PeerBlock(self.nbytes)
         self.bases = None
         self.partial = self.block.tensor(self.PARTIAL, (2,), torch.float64)  # [0]: this rank's interior sum of squares
         self.total = self.block.tensor(self.TOTAL, (1,), torch.float64)      # all-rank sum (same bits on every rank)
@@ -133,54 +188,22 @@ class PeerSlabMemory:
         return self.block.tensor(self.off[(name, l)], (1, lev["nrows"], self.pitch[l]), dtype)
 
     def _build(self, halos, gather, reduce):
-        mg, part, rank, world = self.mg, self.part, self.part.rank, self.part.world
-        x, j = mg.Xchg(), 0
-
-        def job(src, dst, nbytes):
-            nonlocal j
-            x.src[j], x.dst[j], x.bytes[j] = src, dst, nbytes
-            j += 1
-
-        me = self.bases[rank]
-        for name, l in halos:  # GHOST boundary rows of my owned range -> the neighbours' ghost rows
-            lev, rowb, off = part.levels[l], self.pitch[l] * (8 if name.endswith("64") else 4), self.off[(name, l)]
-            for q, first in ((rank - 1, lev["own0"]), (rank + 1, lev["own1"] - GHOST)):
-                if 0 <= q < world:
-                    job(me + off + (first - lev["row0"]) * rowb,
-                        self.bases[q] + off + (first - self.parts[q].levels[l]["row0"]) * rowb, GHOST * rowb)
-        all_step = gather or reduce
-        if gather:  # my owned rows of the first replicated level's right-hand side -> every peer
-            ld = part.ld
-            per, rowb, off = (part.n // 2 ** ld) // world, self.pitch[ld] * 4, self.off[("f", ld)]
-            for q in range(world):
-                if q != rank:
-                    job(me + off + rank * per * rowb, self.bases[q] + off + rank * per * rowb, per * rowb)
-        if reduce:  # my partial sum -> slot [rank] of every mailbox (mine included); summed in rank order after the wait
-            for q in range(world):
-                job(me + self.PARTIAL, self.bases[q] + self.SLOTS + 16 * rank, 16)
-            x.red_src, x.red_dst, x.nred, x.red_stride = me + self.SLOTS, me + self.TOTAL, world, 16
-        ns = nw = 0
-        if all_step:
-            for q in range(world):
-                if q != rank:
-                    x.signal[ns], x.wait[nw] = self.bases[q] + self.ALL_FLAGS + 16 * rank, me + self.ALL_FLAGS + 16 * q
-                    ns, nw = ns + 1, nw + 1
-            x.seq = me + self.SEQ_ALL
-        else:
-            if rank > 0:
-                x.signal[ns], x.wait[nw] = self.bases[rank - 1] + self.FLAG_DOWN, me + self.FLAG_UP
-                ns, nw = ns + 1, nw + 1
-            if rank < world - 1:
-                x.signal[ns], x.wait[nw] = self.bases[rank + 1] + self.FLAG_UP, me + self.FLAG_DOWN
-                ns, nw = ns + 1, nw + 1
-            x.seq = me + self.SEQ_NB
-        x.njobs, x.nsignal, x.nwait, x.err = j, ns, nw, me + self.ERR
+        """resolve a plan into the mgfea_xchg descriptor of this rank (addresses in the mapped blocks)"""
+        mg, me = self.mg, self.bases[self.part.rank]
+        pl = self.plan(halos, gather, reduce)
+        x = mg.Xchg()
+        for j, (so, q, do, nb) in enumerate(pl["jobs"]):
+            x.src[j], x.dst[j], x.bytes[j] = me + so, self.bases[q] + do, nb
+        for i, (q, fo) in enumerate(pl["signals"]):
+            x.signal[i] = self.bases[q] + fo
+        for i, fo in enumerate(pl["waits"]):
+            x.wait[i] = me + fo
+        x.njobs, x.nsignal, x.nwait = len(pl["jobs"]), len(pl["signals"]), len(pl["waits"])
+        x.seq, x.err, x.grid = me + pl["seq"], me + self.ERR, pl["grid"]
+        if pl["red"] is not None:
+            so, do, n, stride = pl["red"]
+            x.red_src, x.red_dst, x.nred, x.red_stride = me + so, me + do, n, stride
         x.mode = mg.XCHG_PUSH | mg.XCHG_WAIT
-        # CTAs of the step: a function of the step alone (NOT of the rank): the flags count the pushing CTAs.  About one
-        # 16-byte chunk per thread for the halo rows, more CTAs when whole coarse slabs travel
-        halo_chunks = sum(GHOST * self.pitch[l] * (8 if nm.endswith("64") else 4) // 16 for nm, l in halos) * 2
-        gather_chunks = ((part.n // 2 ** part.ld) // world) * self.pitch[part.ld] * 4 // 16 * (world - 1) if gather else 0
-        x.grid = int(min(64, max(1, (halo_chunks + gather_chunks // 4 + 255) // 256)))
         return x
 
     def step(self, halos, gather=False, reduce=False):
@@ -311,6 +334,8 @@ class SlabMultigrid:
             self.f = [self.ops.alloc(l) for l in range(ld)]
         self.residuals = []
         self._graph = None
+        self._graph64 = None
+        self._mixed_steps = 0
         self._graph_out = None
         self._graph_err = None
         # the exchange of the pre-smoothed u is only needed by the up leg of the same level: it runs on a side stream
@@ -535,38 +560,77 @@ class SlabMultigrid:
             dst.zero_()
             dst[0, :, :N].copy_(src[rows], non_blocking=True)
 
-    def SolveMixed(self, n_iter=None, EPS=None, max_cycles=200):
+    def fill_local64(self, fn_f):
+        """fp64 problem from a per-rank generator: u0 = 0, f rows [own0, own1) = fn_f(own0, nrows, N) (float64 device
+        tensor); the ghost rows of f come from the neighbours"""
+        if self.peer is None:
+            raise self.ops.mg.MgfeaError("SolveMixed on slabs needs the peer-memory exchange")
+        lev = self.part.levels[0]
+        N = lev["N"]
+        self.u64, self.f64 = self.peer.array("u64", 0), self.peer.array("f64", 0)
+        self.u64.zero_()
+        self.f64.zero_()
+        o0, o1 = lev["own0"] - lev["row0"], lev["own1"] - lev["row0"]
+        self.f64[0, o0:o1, :N].copy_(fn_f(lev["own0"], o1 - o0, N))
+        self.peer.step((("f64", 0),))
+
+    def SolveMixed(self, n_iter=None, EPS=None, max_cycles=200, use_graph=True):
         """Multigrid.Solve semantics on the fp64 problem set by set_problem64: every step is one slab V-cycle (fp32, zero
         guess) on the fp64 residual.  Returns the fp64 interior residual 2-norms after each cycle; `self.u64` holds the
         local rows of the solution (gather_solution64 assembles it)."""
-        mg, ops, peer = self.ops.mg, self.ops, self.peer
+        peer = self.peer
         if n_iter is None:
             n_iter = 0
         elif EPS is None:
             EPS = math.inf
-        lev = self.part.levels[0]
-        g = ops._grid(0, self.f[0])
-        sl = ops._slab(0)
-
-        def defect():
-            peer.step((("u64", 0),))  # 4 ghost rows of the iterate: the defect is also formed on 3 ghost rows per side
-            mg.check(mg.lib().mgfea_slab_defect_f64(ctypes.byref(g), ctypes.byref(sl), self.u64.data_ptr(),
-                                                    self.f64.data_ptr(), self.f[0].data_ptr(), peer.partial.data_ptr(), 1,
-                                                    mg.stream_ptr()))
-            peer.step((), reduce=True)
-            return float(torch.sqrt(peer.total.sum()).item())
-
-        self.r0 = defect()
+        self._defect64()
+        self.r0 = float(torch.sqrt(peer.total.sum()).item())
         res, hist = self.r0, []
         while (res > EPS or len(hist) < n_iter) and len(hist) < max_cycles:
-            self._cycle_peer(want_norm=False, zero_guess=True)  # e = V-cycle(0, r) -> u[0]
-            mg.check(mg.lib().mgfea_slab_correct_f64(ctypes.byref(g), ctypes.byref(sl), self.u64.data_ptr(),
-                                                     self.u[0].data_ptr(), 1, mg.stream_ptr()))
-            res = defect()
+            # the first step runs eagerly (lazy one-time initialisation must not happen inside a capture)
+            if use_graph and self._graph64 is None and self._mixed_steps >= 1 and torch.cuda.is_available():
+                self._capture_graph64()
+            self._mixed_steps += 1
+            if self._graph64 is not None:
+                self._graph64.replay()
+            else:
+                self._mixed_iter()
+            res = float(torch.sqrt(peer.total.sum()).item())
             hist.append(res)
         peer.check()
         self.residuals = hist
         return hist
+
+    def _defect64(self):
+        """r = f64 - K u64 -> f[0] (owned rows + 3 ghost rows per side), all-rank interior sum of squares -> peer.total"""
+        mg, ops, peer = self.ops.mg, self.ops, self.peer
+        g, sl = ops._grid(0, self.f[0]), ops._slab(0)
+        peer.step((("u64", 0),))  # 4 ghost rows of the iterate
+        mg.check(mg.lib().mgfea_slab_defect_f64(ctypes.byref(g), ctypes.byref(sl), self.u64.data_ptr(), self.f64.data_ptr(),
+                                                self.f[0].data_ptr(), peer.partial.data_ptr(), 1, mg.stream_ptr()))
+        peer.step((), reduce=True)
+
+    def _mixed_iter(self):
+        """e = V-cycle(0, r) (fp32, slabs); u64 += e; new defect + norm"""
+        mg, ops = self.ops.mg, self.ops
+        self._cycle_peer(want_norm=False, zero_guess=True)
+        g, sl = ops._grid(0, self.f[0]), ops._slab(0)
+        mg.check(mg.lib().mgfea_slab_correct_f64(ctypes.byref(g), ctypes.byref(sl), self.u64.data_ptr(), self.u[0].data_ptr(),
+                                                 1, mg.stream_ptr()))
+        self._defect64()
+
+    def _capture_graph64(self):
+        """one defect-correction step (slab cycle + exchanges + fp64 kernels) as a CUDA graph; every rank captures after
+        the same number of eager steps, so the exchange counters stay aligned"""
+        try:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._mixed_iter()
+            self._graph64 = g
+        except Exception as e:  # noqa: BLE001
+            self._graph64, self._graph_err = None, repr(e)
+            raise
 
     def gather_solution64(self):
         """full fp64 solution on every rank (host tensor)"""

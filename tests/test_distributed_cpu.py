@@ -135,3 +135,102 @@ def test_partition_properties():
                 assert rows == list(range(N)), "owned rows must tile the level exactly once"
             assert all(not p.levels[ld]["dist"] for p in parts)
     assert GHOST >= 3
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# peer-memory exchange: the per-rank plans (FEANet.distributed.SlabExchangePlan, pure host logic) checked against each
+# other and executed on byte buffers -- what mgfea_p2p_exchange does with them on the GPUs
+def _plans(n, world, dist_min_n):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "multigrid-feanet_b200")]
+    import mgfea
+    from FEANet.distributed import SlabExchangePlan, SlabPartition
+
+    L = int(np.log2(n))
+    return [SlabExchangePlan(SlabPartition(n, L, world, r, dist_min_n), mgfea.pitch_for) for r in range(world)]
+
+
+@pytest.mark.parametrize("world,n,dist_min_n", [(2, 512, 129), (4, 1024, 257), (8, 16384, 2049), (8, 2048, 257)])
+def test_exchange_plans_are_consistent(world, n, dist_min_n):
+    from FEANet.distributed import GHOST
+
+    plans = _plans(n, world, dist_min_n)
+    ld = plans[0].part.ld
+    assert 0 < ld
+    assert all(p.off == plans[0].off and p.nbytes == plans[0].nbytes for p in plans)  # one layout for all ranks
+    steps = [((("u_alt", l), ("f", l + 1)), False, False) for l in range(ld - 1)] + [((("u_alt", ld - 1),), True, False)]
+    steps += [((("u", l),), False, l == 0) for l in range(ld - 1, -1, -1)] + [((("u64", 0),), False, False), ((), False, True)]
+    for halos, gather, reduce in steps:
+        pl = [p.plan(halos, gather, reduce) for p in plans]
+        assert len({q["grid"] for q in pl}) == 1 and 1 <= pl[0]["grid"] <= 64  # the flags count CTAs: same on every rank
+        # every flag a rank waits on is raised by exactly one rank, and nobody raises a flag that is not awaited
+        raised = {}
+        for r, q in enumerate(pl):
+            assert len(q["jobs"]) <= 16 and len(q["signals"]) <= 8 and len(q["waits"]) <= 8
+            for tgt, fo in q["signals"]:
+                assert (tgt, fo) not in raised
+                raised[(tgt, fo)] = r
+        awaited = {(r, fo) for r, q in enumerate(pl) for fo in q["waits"]}
+        assert set(raised) == awaited
+        for r, q in enumerate(pl):  # a rank that receives rows from another rank also waits for that rank
+            for so, tgt, do, nb in q["jobs"]:
+                assert nb % 16 == 0 and so % 16 == 0 and do % 16 == 0
+                if tgt != r:
+                    assert raised_by(raised, tgt, r)
+        # halo jobs land exactly in the target's ghost rows of the same array
+        for r, p in enumerate(plans):
+            for name, l in halos:
+                rowb = p.pitch[l] * p.esize(name)
+                for so, tgt, do, nb in pl[r]["jobs"]:
+                    if not (p.off[(name, l)] <= so < p.off[(name, l)] + p.part.levels[l]["nrows"] * rowb) or nb == 16:
+                        continue
+                    lt = plans[tgt].part.levels[l]
+                    g0 = (so - p.off[(name, l)]) // rowb + p.part.levels[l]["row0"]  # first global row sent
+                    assert nb == GHOST * rowb
+                    assert p.part.levels[l]["own0"] <= g0 and g0 + GHOST <= p.part.levels[l]["own1"]  # owned by sender
+                    t0 = (do - p.off[(name, l)]) // rowb + lt["row0"]
+                    assert t0 == g0 and (g0 + GHOST <= lt["own0"] or g0 >= lt["own1"])  # ghost rows of the target
+                    assert lt["row0"] <= g0 and g0 + GHOST <= lt["row0"] + lt["nrows"]
+    # gather: the replicated right-hand side is covered exactly once by the ranks' owned rows (last ring row stays zero)
+    pl = [p.plan((("u_alt", ld - 1),), True, False) for p in plans]
+    rowb, off = plans[0].pitch[ld] * 4, plans[0].off[("f", ld)]
+    nl = n // 2 ** ld
+    rows = np.zeros(nl + 1, int)
+    for r, q in enumerate(pl):
+        mine = [(so, nb) for so, tgt, do, nb in q["jobs"] if so >= off and so == do]
+        assert len(mine) == world - 1 and len({m for m in mine}) == 1
+        rows[(mine[0][0] - off) // rowb:(mine[0][0] - off + mine[0][1]) // rowb] += 1
+    assert (rows[:nl] == 1).all() and rows[nl] == 0
+
+
+def raised_by(raised, receiver, sender):
+    return any(tgt == receiver and src == sender for (tgt, _), src in raised.items())
+
+
+def test_exchange_plan_moves_the_right_rows():
+    """execute the halo jobs of every rank on byte buffers filled with (array id, global row) codes"""
+    from FEANet.distributed import GHOST
+
+    world, n, dmin = 4, 1024, 257
+    plans = _plans(n, world, dmin)
+    mem = [np.zeros(p.nbytes, np.uint8) for p in plans]
+    l, name = 1, "u_alt"
+    rowb = plans[0].pitch[l] * 4
+
+    def rows_view(r):
+        lev = plans[r].part.levels[l]
+        o = plans[r].off[(name, l)]
+        return mem[r][o:o + lev["nrows"] * rowb].view(np.float32).reshape(lev["nrows"], -1), lev
+
+    for r in range(world):  # owned rows carry their global row index, ghost rows -1
+        v, lev = rows_view(r)
+        v[:] = -1
+        for g in range(lev["own0"], lev["own1"]):
+            v[g - lev["row0"]] = g
+    for r in range(world):
+        for so, tgt, do, nb in plans[r].plan(((name, l),))["jobs"]:
+            mem[tgt][do:do + nb] = mem[r][so:so + nb]
+    for r in range(world):
+        v, lev = rows_view(r)
+        for i in range(lev["nrows"]):
+            g = lev["row0"] + i
+            assert (v[i] == g).all(), (r, g)
