@@ -197,7 +197,7 @@ class Multigrid():
         eng.set_f(self.grids[0].f)
         res = eng.run(n_iter=args[0], EPS=args[1], chunk=chunk, use_graph=use_graph)
         on_gpu = torch.is_tensor(self.initial_v) and self.initial_v.is_cuda
-        self.grids[0].v = eng.solution if on_gpu else eng.solution_to_host().clone()
+        self.grids[0].v = eng.solution if on_gpu else eng.solution_to_host()
         self.engine = eng
         return res
 

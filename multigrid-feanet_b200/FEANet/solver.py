@@ -318,10 +318,11 @@ class VCycleEngine:
         return self.u[0].view
 
     def solution_to_host(self):
-        """D2H of the level-0 solution into a reusable PINNED host buffer (contiguous (B,1,N,N)); returns a copy-free
-        view of that buffer, valid until the next call."""
-        if getattr(self, "_host_out", None) is None:
-            self._host_out = torch.empty((self.B, 1, self.u[0].N, self.u[0].N), dtype=torch.float32).pin_memory()
-        self._host_out.copy_(self.u[0].view, non_blocking=True)
+        """D2H of the level-0 solution into a PINNED host tensor (contiguous (B,1,N,N)) that belongs to the caller.
+        torch's caching host allocator hands the same pinned block back once the previous result has been dropped, so a
+        solve loop pays neither a cudaHostAlloc nor a host-side copy per call, and a result the caller keeps is never
+        overwritten by a later solve."""
+        out = torch.empty((self.B, 1, self.u[0].N, self.u[0].N), dtype=torch.float32, pin_memory=True)
+        out.copy_(self.u[0].view, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return self._host_out
+        return out
