@@ -87,6 +87,12 @@ int mgfea_trace(unsigned long long *buf, int capacity);
 /* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
 uint64_t mgfea_launch_count(void);
 
+/* ---- setup ------------------------------------------------------------------------------------------- */
+/* pattern key map of MeshCenterInterface (FEANet/mesh.py:62-101: the reference loops nodes x elements, O(N^4)) in closed
+ * form on the device: keys[N][key_pitch] uint8 (key_pitch % 16 == 0, padding bytes 0); shape 0 = circle r=0.5,
+ * 1 = square half-width 0.5, anything else = single phase */
+int mgfea_pattern_keys(uint8_t *keys, int N, int key_pitch, int shape, void *stream);
+
 /* ---- layout ------------------------------------------------------------------------------------------ */
 /* contiguous [B][N][N] <-> padded [B][N][pitch]; pack zero-fills columns [N,pitch) */
 int mgfea_pack(const float *src, float *dst, int N, int pitch, int64_t plane, int B, void *stream);

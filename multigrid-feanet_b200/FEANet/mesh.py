@@ -44,7 +44,12 @@ class _LazyPatternMap(Mapping):
     (16 dense int64 maps of a 4097^2 grid would be 2 GB; the kernels use the uint8 key map instead)."""
 
     def __init__(self, keys_u8, npat):
-        self._keys, self._npat = keys_u8, npat
+        # keys_u8: the (N,N) uint8 key map, or an object whose ``pattern_keys`` attribute produces it on demand
+        self._src, self._npat = keys_u8, npat
+
+    @property
+    def _keys(self):
+        return self._src if isinstance(self._src, np.ndarray) else self._src.pattern_keys
 
     def __getitem__(self, k):
         if not (0 <= k < self._npat):
@@ -127,9 +132,11 @@ class MeshCenterInterface(_StructuredQuad):
         self.ref_pattern_dict = {k: list(v) for k, v in _REF_PATTERNS.items()}
         self.Ke = _element_stiffness()
         self.kernel_dict = {k: _node_kernel(self.a, self.Ke, p) for k, p in self.ref_pattern_dict.items()}
-        self._phase2d = self._element_phase(nnode_edge - 1, shape)
-        self.pattern_keys = self._node_keys(self._phase2d)
-        self.global_pattern_center = _LazyPatternMap(self.pattern_keys, 16)
+        # host copies of the element phases / node keys are built on first access: the kernels take the key map from
+        # mgfea_pattern_keys (device_pattern_keys), so a 16385^2 mesh costs no host-side 268M-element passes
+        self._phase2d_cache = None
+        self._keys_cache = None
+        self.global_pattern_center = _LazyPatternMap(self, 16)
         if outfile is not None:
             self.save_mesh(outfile)
 
@@ -159,6 +166,24 @@ class MeshCenterInterface(_StructuredQuad):
         keys = np.zeros((N, N), np.uint8)
         keys[1:-1, 1:-1] = lut[code]
         return keys
+
+    @property
+    def _phase2d(self):
+        if self._phase2d_cache is None:
+            self._phase2d_cache = self._element_phase(self.nnode_edge - 1, self.shape)
+        return self._phase2d_cache
+
+    @property
+    def pattern_keys(self):
+        if self._keys_cache is None:
+            self._keys_cache = self._node_keys(self._phase2d)
+        return self._keys_cache
+
+    def device_pattern_keys(self):
+        """the uint8 key map as a padded device tensor, generated by the setup kernel (no host pass)"""
+        import mgfea
+
+        return mgfea.device_pattern_keys(self.nnode_edge, self.shape)
 
     @property
     def phase(self):

@@ -37,16 +37,27 @@ class KNet(nn.Module):
             for pkey in self.kernel_dict:
                 self.net1.weight[pkey, 0] = ident
                 self.net2.weight[0, pkey] = torch.from_numpy(np.asarray(self.kernel_dict[pkey]))
-        self._keys_np = getattr(mesh, "pattern_keys", None)
-        if self._keys_np is None and self.n_channel > 1:
-            # duck-typed reference-style mesh: rebuild the key map from its one-hot maps
-            k = np.zeros(self.nnode_edge * self.nnode_edge, np.uint8)
-            for pkey in self.kernel_dict:
-                k[np.asarray(mesh.global_pattern_center[pkey]).reshape(-1) != 0] = pkey
-            self._keys_np = k.reshape(self.nnode_edge, self.nnode_edge)
+        self._keys_np_cache = None
         self._keys_dev = None
         self._ktab = mgfea.DeviceTable()
         self._global_pattern = None
+
+    @property
+    def _keys_np(self):
+        """host uint8 key map (None for single-pattern meshes), built on first use"""
+        if self.n_channel == 1:
+            return None
+        if self._keys_np_cache is None:
+            mesh = self._mesh
+            k = getattr(mesh, "pattern_keys", None)
+            if k is None:
+                # duck-typed reference-style mesh: rebuild the key map from its one-hot maps
+                k = np.zeros(self.nnode_edge * self.nnode_edge, np.uint8)
+                for pkey in self.kernel_dict:
+                    k[np.asarray(mesh.global_pattern_center[pkey]).reshape(-1) != 0] = pkey
+                k = k.reshape(self.nnode_edge, self.nnode_edge)
+            self._keys_np_cache = k
+        return self._keys_np_cache
 
     # -- reference attribute: (1, C, N, N) fp32 one-hot pattern masks (model.py:32-35); built only when asked for
     @property
@@ -71,10 +82,11 @@ class KNet(nn.Module):
 
     # -- device-side description shared with JacobiBlock and the V-cycle drivers
     def keys_dev(self):
-        if self._keys_np is None:
+        if self.n_channel == 1:
             return None
         if self._keys_dev is None:
-            self._keys_dev = mgfea.pack_keys(self._keys_np)
+            gen = getattr(self._mesh, "device_pattern_keys", None)  # closed-form meshes: setup kernel, no host pass
+            self._keys_dev = gen() if gen is not None else mgfea.pack_keys(self._keys_np)
         return self._keys_dev
 
     def ktab_dev(self):

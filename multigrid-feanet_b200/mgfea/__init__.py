@@ -30,7 +30,7 @@ EXPORTS = [
     "mgfea_slab_smooth_residual_restrict", "mgfea_slab_prolong_correct_smooth",
     "mgfea_peer_alloc", "mgfea_peer_free", "mgfea_peer_export", "mgfea_peer_open", "mgfea_peer_close",
     "mgfea_p2p_exchange", "mgfea_trace", "mgfea_prolong_correct_smooth_norm",
-    "mgfea_defect_f64", "mgfea_correct_f64", "mgfea_slab_defect_f64", "mgfea_slab_correct_f64",
+    "mgfea_defect_f64", "mgfea_correct_f64", "mgfea_slab_defect_f64", "mgfea_slab_correct_f64", "mgfea_pattern_keys",
 ]
 
 
@@ -136,6 +136,7 @@ def lib():
         L.mgfea_correct_f64.argtypes = [G, vp, vp, vp, i32, vp]
         L.mgfea_slab_defect_f64.argtypes = [G, ctypes.POINTER(Slab), vp, vp, vp, vp, i32, vp]
         L.mgfea_slab_correct_f64.argtypes = [G, ctypes.POINTER(Slab), vp, vp, i32, vp]
+        L.mgfea_pattern_keys.argtypes = [vp, i32, i32, i32, vp]
         L.mgfea_restrict_channels.argtypes = [vp, vp, vp, i32, i32, i32, vp]
         L.mgfea_prolong_channels.argtypes = [vp, vp, vp, i32, i32, i32, vp]
         L.mgfea_residual_norm.argtypes = [G, vp, vp, vp, vp, vp, i32, vp]
@@ -253,6 +254,15 @@ def pack_keys(keys_u8) -> torch.Tensor:
     kp = (N + 127) // 128 * 128
     out = torch.zeros((N, kp), dtype=torch.uint8, device=dev)
     out[:, :N] = k.to(dev)
+    return out
+
+
+def device_pattern_keys(N: int, shape: int) -> torch.Tensor:
+    """[N][key_pitch] uint8 key map of the two-phase plate generated on the device (mgfea_pattern_keys)"""
+    dev = require_cuda()
+    kp = (N + 127) // 128 * 128
+    out = torch.empty((N, kp), dtype=torch.uint8, device=dev)
+    check(lib().mgfea_pattern_keys(out.data_ptr(), N, kp, int(shape), stream_ptr()))
     return out
 
 

@@ -504,6 +504,33 @@ __global__ void prolong_channels_kernel(const float *__restrict__ eFC, float *__
     }
 }
 
+// Setup path: pattern key of every node of the two-phase plate in closed form (FEANet/mesh.py:62-101 --
+// the reference loops over all nodes x all elements, O(N^4)).  Element (r,c) is phase 1 iff its centroid lies strictly
+// inside the inclusion: circle 4((2c+1-n)^2 + (2r+1-n)^2) < n^2, square 2|2c+1-n| < n and 2|2r+1-n| < n (integers);
+// node pattern [e1,e2,e3,e4] = elements (i-1,j),(i-1,j-1),(i,j-1),(i,j); ring nodes keep key 0 (mesh.py:81-82).
+__device__ __forceinline__ int elem_phase_dev(int shape, long long n, long long r, long long c) {
+    const long long tc = 2 * c + 1 - n, tr = 2 * r + 1 - n;
+    if (shape == 0) return (4 * (tc * tc + tr * tr) < n * n) ? 1 : 0;
+    if (shape == 1) return (2 * (tc < 0 ? -tc : tc) < n && 2 * (tr < 0 ? -tr : tr) < n) ? 1 : 0;
+    return 0;
+}
+__global__ void pattern_keys_kernel(unsigned char *keys, int N, int key_pitch, int shape) {
+    // key of pattern code (e1<<3 | e2<<2 | e3<<1 | e4): the reference's ref_pattern_dict (mesh.py:23-26) inverted
+    const unsigned char lut[16] = {0, 2, 3, 6, 5, 10, 8, 14, 4, 9, 11, 15, 7, 13, 12, 1};
+    const long long total = (long long)N * key_pitch;
+    const long long n = N - 1;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t / key_pitch), j = (int)(t - (long long)i * key_pitch);
+        unsigned char k = 0;
+        if (i >= 1 && j >= 1 && i <= N - 2 && j <= N - 2) {
+            const int code = (elem_phase_dev(shape, n, i - 1, j) << 3) | (elem_phase_dev(shape, n, i - 1, j - 1) << 2) |
+                             (elem_phase_dev(shape, n, i, j - 1) << 1) | elem_phase_dev(shape, n, i, j);
+            k = lut[code];
+        }
+        keys[t] = k;
+    }
+}
+
 // =========================================================================================================
 // host side
 // =========================================================================================================
@@ -1396,6 +1423,16 @@ int mgfea_trace(unsigned long long *buf, int capacity) {
 }
 int mgfea_set_loader(int use_tma) { return g_use_tma.exchange(use_tma ? 1 : 0); }
 uint64_t mgfea_launch_count(void) { return g_launches.load(); }
+
+int mgfea_pattern_keys(uint8_t *keys, int N, int key_pitch, int shape, void *stream) {
+    if (!keys || N < 3 || key_pitch < N) return MGFEA_EINVAL;
+    if (key_pitch & 15) return MGFEA_EALIGN;
+    const long long total = (long long)N * key_pitch;
+    int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    pattern_keys_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(keys, N, key_pitch, shape);
+    g_launches.fetch_add(1);
+    return (int)cudaGetLastError();
+}
 
 int mgfea_pack(const float *src, float *dst, int N, int pitch, int64_t plane, int B, void *stream) {
     if (!src || !dst || N < 1 || pitch < N || B < 1) return MGFEA_EINVAL;

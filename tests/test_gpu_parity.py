@@ -742,3 +742,24 @@ def test_jacobi_omega_not_power_of_two(O):
     u0 = rs.standard_normal((1, 1, n + 1, n + 1)).astype(np.float32)
     f = 0.01 * rs.standard_normal((1, n + 1, n + 1)).astype(np.float32)
     engine_vs_oracle(O, jacs, levels, O.CycleCfg(), {}, u0, f, ncyc=2, name="omega 0.8")
+
+
+# ------------------------------------------------------------------------------------------ setup path on the device (8f.3)
+@pytest.mark.parametrize("shape", [0, 1])
+def test_device_pattern_keys(O, shape):
+    """mgfea_pattern_keys against the reference's own key maps (tests/golden/mesh.npz, produced by the unmodified
+    MeshCenterInterface), the oracle and the host closed form -- bit-exact, incl. the zero padding bytes"""
+    import mgfea
+    from FEANet.mesh import MeshCenterInterface
+
+    M = np.load(os.path.join(G, "mesh.npz"))
+    for n in (4, 8, 16, 32, 64):
+        k = host(mgfea.device_pattern_keys(n + 1, shape))
+        assert np.array_equal(k[:, :n + 1], M[f"keys_n{n}_s{shape}"]), n
+        assert (k[:, n + 1:] == 0).all()
+    for n in (128, 1000 + 24, 4096):
+        k = host(mgfea.device_pattern_keys(n + 1, shape))
+        assert np.array_equal(k[:, :n + 1], O.pattern_keys(n + 1, shape)), n
+        mesh = MeshCenterInterface(2, [1, 20], n + 1, shape=shape)
+        assert np.array_equal(k[:, :n + 1], mesh.pattern_keys)
+        assert np.array_equal(host(mesh.device_pattern_keys()), k)

@@ -56,10 +56,8 @@ u2 = O.jacobi(uc, f, lv[0].keys, lv[0].ktab, lv[0].invd)
 report("up u2", eng.u[0].view.cpu().numpy()[0, 0], u2[0])
 print("norm", float(ss.item()), O.sumsq_interior(O.residual(u2, f, lv[0].keys, lv[0].ktab)))
 
-# ---- which rounding does the kernel use at a mismatching inclusion node?  (Jacobi update from u0)
-mgfea.check(mgfea.lib().mgfea_smooth_residual_restrict(
-    ctypes.byref(g0), eng.u_alt[0].ptr if False else None, eng.u[0].ptr, eng.f[0].ptr, 1, 0, None, 0, eng.f[1].ptr,
-    eng.f[1].pitch, eng.f[1].plane, rt.data_ptr(), 1, 1, 4.0, None, 1, mgfea.stream_ptr())) if False else None
+# ---- which rounding does the kernel use at a mismatching inclusion node?  (Jacobi update from u0; this is how the
+# FFMA2 contraction of the packed update was found: the kernel matched `fused`, the oracle `unfused`)
 eng.set_u(torch.from_numpy(u0))
 mgfea.check(mgfea.lib().mgfea_smooth_residual_restrict(
     ctypes.byref(g0), eng.u[0].ptr, eng.u_alt[0].ptr, eng.f[0].ptr, 1, 0, None, 0, eng.f[1].ptr,
