@@ -1851,7 +1851,7 @@ static int defect_f64(const mgfea_grid *g, const mgfea_slab *sl, const double *u
     }
     p.nbx = (g->pitch / 2 + F64_TX - 1) / F64_TX;
     p.nby = (p.yhi - p.ylo + F64_TY - 1) / F64_TY;
-    if (p.nby > 65535 || B > 65535) return MGFEA_EUNSUPPORTED;
+    if (B > 65535) return MGFEA_EUNSUPPORTED;
     DeviceScratch *scr = nullptr;
     int rc = get_scratch((size_t)p.nbx * p.nby * B, &scr);
     if (rc) return rc;
@@ -1860,7 +1860,11 @@ static int defect_f64(const mgfea_grid *g, const mgfea_slab *sl, const double *u
     p.sumsq = sumsq;
     p.hist = hist;
     p.ctl = ctl;
-    const dim3 grid((unsigned)p.nbx, (unsigned)p.nby, (unsigned)B), block(F64_TX, F64_TY);
+    // persistent blocks: about 8 per SM over all samples, each walking over its sample's tiles
+    long long gx = ((long long)scr->num_sms * 8 + B - 1) / B;
+    if (gx > (long long)p.nbx * p.nby) gx = (long long)p.nbx * p.nby;
+    if (gx < 1) gx = 1;
+    const dim3 grid((unsigned)gx, 1u, (unsigned)B), block(F64_TX, F64_TY);
     trace_stamp((cudaStream_t)stream);
     if (g->keys)
         mg_defect_f64_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(p);

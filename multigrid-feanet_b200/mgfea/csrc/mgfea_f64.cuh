@@ -56,55 +56,62 @@ __global__ void __launch_bounds__(F64_TX *F64_TY) mg_defect_f64_kernel(const F64
     __syncthreads();
     if (solve_done) return;
     const int N = p.N, b = blockIdx.z;
-    const int x = (blockIdx.x * F64_TX + threadIdx.x) * 2, y = p.ylo + blockIdx.y * F64_TY + threadIdx.y;
     const double *ub = p.u + (long long)b * p.plane - (long long)p.row0 * p.pitch;  // indexed by GLOBAL row below
     double part = 0.0;
-    if (y < p.yhi && x < p.pitch) {
-        double r0 = 0.0, r1 = 0.0;
-        const bool rin = (y >= 1 && y <= N - 2);
-        if (rin && x <= N - 2) {  // at least one of the two columns may be interior
-            double acc0 = 0.0, acc1 = 0.0;
+    // persistent blocks: a block walks over the sample's 64 x 8 tiles with stride gridDim.x and reports ONE partial sum
+    // (one fence + one ticket per block; with a block per tile the 33k tickets of a 4097^2 level dominated the kernel)
+    const int ntile = p.nbx * p.nby;
+    for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+        const int by = tile / p.nbx, bx = tile - by * p.nbx;
+        const int x = (bx * F64_TX + threadIdx.x) * 2, y = p.ylo + by * F64_TY + threadIdx.y;
+        if (y < p.yhi && x < p.pitch) {
+            double r0 = 0.0, r1 = 0.0;
+            const bool rin = (y >= 1 && y <= N - 2);
+            if (rin && x <= N - 2) {  // at least one of the two columns may be interior
+                double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                const int yy = y - 1 + d;  // 0 .. N-1
-                const double *row = ub + (long long)yy * p.pitch;
-                // columns x-1 .. x+2 (x is even; x-1 >= -1, x+2 <= pitch+1): guard the two outer ones
-                const double2 c = *reinterpret_cast<const double2 *>(row + x);
-                const double l = (x >= 1) ? row[x - 1] : 0.0;
-                const double rr = (x + 2 < p.pitch) ? row[x + 2] : 0.0;
-                const double v[4] = {l, c.x, c.y, rr};
-                int k[4] = {0, 0, 0, 0};
-                if (KEYS) {
-                    const unsigned char *kr = p.keys + (long long)yy * p.key_pitch;
+                for (int d = 0; d < 3; ++d) {
+                    const int yy = y - 1 + d;  // 0 .. N-1
+                    const double *row = ub + (long long)yy * p.pitch;
+                    // columns x-1 .. x+2 (x is even; x-1 >= -1, x+2 <= pitch+1): guard the two outer ones
+                    const double2 c = *reinterpret_cast<const double2 *>(row + x);
+                    const double l = (x >= 1) ? row[x - 1] : 0.0;
+                    const double rr = (x + 2 < p.pitch) ? row[x + 2] : 0.0;
+                    const double v[4] = {l, c.x, c.y, rr};
+                    int k[4] = {0, 0, 0, 0};
+                    if (KEYS) {
+                        const unsigned char *kr = p.keys + (long long)yy * p.key_pitch;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int xx = x - 1 + q;
-                        k[q] = (xx >= 0 && xx < N) ? kr[xx] : 0;
+                        for (int q = 0; q < 4; ++q) {
+                            const int xx = x - 1 + q;
+                            k[q] = (xx >= 0 && xx < N) ? kr[xx] : 0;
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        acc0 = fma(tab[9 * k[q] + 3 * d + q], v[q], acc0);
+                        acc1 = fma(tab[9 * k[q + 1] + 3 * d + q], v[q + 1], acc1);
                     }
                 }
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    acc0 = fma(tab[9 * k[q] + 3 * d + q], v[q], acc0);
-                    acc1 = fma(tab[9 * k[q + 1] + 3 * d + q], v[q + 1], acc1);
-                }
+                const double2 fv =
+                    *reinterpret_cast<const double2 *>(p.f + (long long)b * p.plane + (long long)(y - p.row0) * p.pitch + x);
+                if (x >= 1) r0 = fv.x - acc0;
+                if (x + 1 <= N - 2) r1 = fv.y - acc1;
             }
-            const double2 fv = *reinterpret_cast<const double2 *>(p.f + (long long)b * p.plane + (long long)(y - p.row0) * p.pitch + x);
-            if (x >= 1) r0 = fv.x - acc0;
-            if (x + 1 <= N - 2) r1 = fv.y - acc1;
+            *reinterpret_cast<float2 *>(p.r + (long long)b * p.plane + (long long)(y - p.row0) * p.pitch + x) =
+                make_float2((float)r0, (float)r1);
+            if (y >= p.own0 && y < p.own1) part += r0 * r0 + r1 * r1;
         }
-        *reinterpret_cast<float2 *>(p.r + (long long)b * p.plane + (long long)(y - p.row0) * p.pitch + x) =
-            make_float2((float)r0, (float)r1);
-        if (y >= p.own0 && y < p.own1) part = r0 * r0 + r1 * r1;
     }
     // ---- block partial -> per-sample sum by the last block (deterministic order), convergence control
     part = warp_sum_f64(part);
     if (threadIdx.x == 0) red[threadIdx.y] = part;
     __syncthreads();
-    const int per = p.nbx * p.nby;
+    const int per = gridDim.x;  // partials per sample
     if (tid == 0) {
         double s = 0.0;
         for (int w = 0; w < F64_TY; ++w) s += red[w];
-        p.partials[(long long)b * per + blockIdx.y * p.nbx + blockIdx.x] = s;
+        p.partials[(long long)b * per + blockIdx.x] = s;
         __threadfence();
         const unsigned int ticket = atomicAdd(p.counter, 1u);
         lastflag = (ticket == (unsigned int)(per * p.B) - 1u) ? 1 : 0;
