@@ -240,8 +240,10 @@ __device__ __forceinline__ void run_tile(TileCtx &c, Tables &T, const RegW &W, c
     }
 }
 
-template <bool KEYS, bool GBC>
-__global__ void __launch_bounds__(NTHREADS, MGFEA_MINBLOCKS) mg_tile_kernel(const __grid_constant__ TileMaps maps,
+// MINB: resident CTAs per SM the register budget is cut for.  Programs whose shared-memory carve-up admits only two
+// CTAs (HNet temporaries) get the 128-register build (no spills) instead of the 85-register one.
+template <bool KEYS, bool GBC, int MINB = MGFEA_MINBLOCKS>
+__global__ void __launch_bounds__(NTHREADS, MINB) mg_tile_kernel(const __grid_constant__ TileMaps maps,
                                                            const TileParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     Tables &T = *reinterpret_cast<Tables *>(smem);
@@ -728,6 +730,7 @@ struct Knobs {
     int stream_r = 0;         // rows per strip (0 = auto)
     int stream_packed = 1;    // 1: FFMA2 (fma.rn.f32x2) streaming kernels, 0: scalar FFMA
     int stream_keys = 0;      // 1: two-phase levels also stream (see stream_eligible)
+    int tile_minb2 = 1;       // 1: tile programs limited to <= 2 CTAs per SM by shared memory use the 128-register build
     int mid_min_n = 66;       // coarse levels with mid_min_n <= N <= mid_max_n use the latency-oriented mid kernels
     int mid_max_n = 513;      // (mid_max_n = 0 disables them; at 1025 the streaming DOWN kernel wins: profiles/)
     int mid_max_n_up = 1025;  // the up leg stays ahead one level longer
@@ -744,6 +747,7 @@ struct Knobs {
         if (const char *e = getenv("MGFEA_STREAM_R")) stream_r = atoi(e);
         if (const char *e = getenv("MGFEA_STREAM_PACKED")) stream_packed = atoi(e);
         if (const char *e = getenv("MGFEA_STREAM_KEYS")) stream_keys = atoi(e);
+        if (const char *e = getenv("MGFEA_TILE_MINB2")) tile_minb2 = atoi(e);
         if (const char *e = getenv("MGFEA_THREADS")) threads = atoi(e);
         threads = 256;
         if (th < 8 || th > 64 || (th & 1)) th = 32;
@@ -755,21 +759,27 @@ static const Knobs &knobs() {
     return k;
 }
 
-template <bool KEYS, bool GBC>
-static cudaError_t launch_tile(const TileMaps &maps, const TileParams &p, int grid, int threads, size_t smem,
-                               cudaStream_t st) {
+template <bool KEYS, bool GBC, int MINB>
+static cudaError_t launch_tile_(const TileMaps &maps, const TileParams &p, int grid, size_t smem, cudaStream_t st) {
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(mg_tile_kernel<KEYS, GBC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(mg_tile_kernel<KEYS, GBC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              232448);
         if (e != cudaSuccess) return e;
         configured = 232448;
     }
-    (void)threads;
-    cudaError_t le = launch_pdl(mg_tile_kernel<KEYS, GBC>, grid, NTHREADS, smem, st, maps, p);
+    cudaError_t le = launch_pdl(mg_tile_kernel<KEYS, GBC, MINB>, grid, NTHREADS, smem, st, maps, p);
     if (le != cudaSuccess) return le;
     g_launches.fetch_add(1);
     return cudaGetLastError();
+}
+template <bool KEYS, bool GBC>
+static cudaError_t launch_tile(const TileMaps &maps, const TileParams &p, int grid, int threads, size_t smem,
+                               cudaStream_t st) {
+    (void)threads;
+    const bool two = (232448 / smem) <= 2 && knobs().tile_minb2;  // at most two CTAs fit anyway: take the registers
+    return two ? launch_tile_<KEYS, GBC, 2>(maps, p, grid, smem, st)
+               : launch_tile_<KEYS, GBC, MGFEA_MINBLOCKS>(maps, p, grid, smem, st);
 }
 
 static int check_field(const void *p, int pitch, long long plane) {

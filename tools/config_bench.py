@@ -94,3 +94,18 @@ if which in ("cfg3bil", "all"):
     h = eng.run(n_iter=8)
     report("cfg3bil: two-phase circle 1:20, 4097^2, 12 levels, V(1,1) jac, FW restriction + bilinear prolongation",
            eng, n, L, B, 1, [x / r0 for x in h])
+
+for tag, n in (("cfg4_1gpu", 8192), ("cfg5_1gpu", 16384)):
+    if which in (tag, "all", "big"):
+        # configs 4 / 5 on ONE GPU (the row-slab numbers at 2/4/8 GPUs come from bench.py --gpus N): f = 0 model problem
+        L, B = int(np.log2(n)), 1
+        prob = Multigrid(n)
+        eng = prob._engine(1, 1, 0, B=1)
+        g = torch.Generator(device="cuda").manual_seed(123)
+        eng.set_u(1.2e5 * torch.rand((1, 1, n + 1, n + 1), generator=g, device="cuda") + 1.3e5)
+        eng.set_f(torch.zeros(1, 1, n + 1, n + 1, device="cuda"))
+        r0 = float(torch.sqrt(eng.residual_sumsq().sum()).item())
+        h = eng.run(n_iter=8)
+        report(f"{tag}: iso Poisson {n + 1}^2, {L} levels, V(1,1), single RHS, 1 GPU", eng, n, L, B, 0, [x / r0 for x in h])
+        del eng, prob
+        torch.cuda.empty_cache()
