@@ -777,7 +777,8 @@ template <bool KEYS, bool GBC>
 static cudaError_t launch_tile(const TileMaps &maps, const TileParams &p, int grid, int threads, size_t smem,
                                cudaStream_t st) {
     (void)threads;
-    const bool two = (232448 / smem) <= 2 && knobs().tile_minb2;  // at most two CTAs fit anyway: take the registers
+    // at most two CTAs fit anyway: take the registers (MGFEA_TILE_MINB2=2 forces the 128-register build everywhere)
+    const bool two = ((232448 / smem) <= 2 && knobs().tile_minb2) || knobs().tile_minb2 == 2;
     return two ? launch_tile_<KEYS, GBC, 2>(maps, p, grid, smem, st)
                : launch_tile_<KEYS, GBC, MGFEA_MINBLOCKS>(maps, p, grid, smem, st);
 }
