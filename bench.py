@@ -88,9 +88,9 @@ class ClockSampler:
 
 def ncu_traffic(kernel_prefix, grid=None):
     """DRAM bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full` summary
-    (profiles/r01_ncu_full_stream2_s7.json, captured with tools/cycle_profile.py on the same 4097^2 workload)"""
+    (profiles/r01_ncu_full_stream2_final.json, captured with tools/cycle_profile.py on the same 4097^2 workload)"""
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_stream2_s7.json")))
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_stream2_final.json")))
         for name, d in prof.items():
             if name.startswith(kernel_prefix) and (grid is None or f"({grid}," in name):
                 mb = float(d["dram__bytes_read.sum"].split()[0]) + float(d["dram__bytes_write.sum"].split()[0])
@@ -314,14 +314,14 @@ def run_ours(args):
     alg_up = 4 * (2 * M0 + M1 + 3 * M0)         # prolong->correct (v_c,u -> u) + post-smooth (u,f -> u)
     alg_upn = alg_up + 4 * 2 * M0               # + convergence norm (u,f)
     # the dominant kernel = the longest launch of the cycle
-    kname, kms, kalg = "mg_stream2_kernel<1, 0> level-0 up leg (prolong+correct+smooth+residual norm)", ms_upn, alg_upn
-    traffic = ncu_traffic("mg_stream2_kernel<1, 0>", 280) if n == 4096 else None
+    kname, kms, kalg = "mg_stream2_kernel<1, 0, 0> level-0 up leg (prolong+correct+smooth+residual norm)", ms_upn, alg_upn
+    traffic = ncu_traffic("mg_stream2_kernel<1, 0", 280) if n == 4096 else None
     ach = kalg / (kms * 1e-3) / 1e9
     balg = algorithmic_bytes_per_cycle(n, L)
     cyc_ms = ms / steps
     cyc_ach = balg / (cyc_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                "traffic_source": "profiles/r01_ncu_full_stream2_s7.json (ncu --set full, same workload)" if traffic else None,
+                "traffic_source": "profiles/r01_ncu_full_stream2_final.json (ncu --set full, same workload)" if traffic else None,
                 "note": "achieved = algorithmic bytes (SURVEY 8d: every logical operator reads its inputs and writes its "
                         "outputs once) / measured time; the fused kernel moves only `traffic` bytes through DRAM, so "
                         "achieved may exceed the copy-bandwidth peak; traffic / time is the DRAM rate actually sustained",
@@ -329,7 +329,7 @@ def run_ours(args):
                 "kernel": kname, "kernel_ms": kms, "algorithmic_bytes_per_launch": kalg, "peak_source": peak_src,
                 "other_kernels": {"down_leg": {"ms": ms_down, "algorithmic_bytes": alg_down,
                                                "achieved": alg_down / (ms_down * 1e-3) / 1e9,
-                                               "traffic": ncu_traffic("mg_stream2_kernel<0, 0>", 280) if n == 4096 else None},
+                                               "traffic": ncu_traffic("mg_stream2_kernel<0, 0", 280) if n == 4096 else None},
                                   "up_leg_without_norm": {"ms": ms_up, "algorithmic_bytes": alg_up,
                                                           "achieved": alg_up / (ms_up * 1e-3) / 1e9}},
                 "cycle": {"algorithmic_bytes": balg, "ms": cyc_ms, "achieved": cyc_ach, "frac": cyc_ach / peak}}
