@@ -367,7 +367,9 @@ def run_ours(args):
     r0 = float(torch.sqrt(eng.residual_sumsq().sum()).item())
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    hist = eng.run(EPS=1e-8 * r0, chunk=4)
+    # convergence is evaluated on the device and cycles past it are no-ops, so the host may enqueue a generous chunk
+    # and synchronise once (the reference synchronises with .item() after every cycle)
+    hist = eng.run(EPS=1e-8 * r0, chunk=16)
     torch.cuda.synchronize()
     t_tol = time.perf_counter() - t0
 
