@@ -211,6 +211,8 @@ int mgfea_p2p_exchange(const mgfea_xchg *x, void *stream);
  * mgfea_defect_f64: r (fp32, 0 on the ring) and sumsq[b] = sum over interior nodes of (f - K u)^2 in fp64; with ctl
  * it is the residual history / stopping rule of the solve, like mgfea_residual_norm.
  * mgfea_correct_f64: u += (double) e on interior nodes (no-op once ctl->done is set). */
+/* padded fp32 field -> padded fp64 field (same pitch / plane counts); zero_ring clears the Dirichlet ring on the way */
+int mgfea_widen_f64(const float *src, double *dst, int N, int pitch, int64_t plane, int B, int zero_ring, void *stream);
 int mgfea_defect_f64(const mgfea_grid *g, const double *u, const double *f, float *r, double *sumsq, mgfea_ctl *ctl,
                      double *hist, int B, void *stream);
 int mgfea_correct_f64(const mgfea_grid *g, double *u, const float *e, const mgfea_ctl *ctl, int B, void *stream);

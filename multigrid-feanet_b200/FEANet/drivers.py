@@ -217,8 +217,9 @@ class Multigrid():
                                max_cycles=self.max_cycles, compute_norm=False, zero_guess=True)
             self._engines[key] = eng
         N = self.n + 1
-        u0 = torch.as_tensor(self.initial_v).reshape(1, 1, N, N)
-        f = torch.as_tensor(self.grids[0].f).reshape(1, 1, N, N)
+        u0, f = torch.as_tensor(self.initial_v), torch.as_tensor(self.grids[0].f)
+        u0 = u0 if u0.dim() == 4 else u0.reshape(1, 1, N, N)  # (4-D tensors are passed on as they are: our own padded
+        f = f if f.dim() == 4 else f.reshape(1, 1, N, N)      # views are then used in place)
         on_host = not u0.is_cuda
         res = eng.run_mixed(u0, f, n_iter=n_iter, EPS=EPS, chunk=chunk, use_graph=use_graph)
         sol = eng.solution64

@@ -226,7 +226,9 @@ class VCycleEngine:
             self._graph64 = None
 
     def _load64(self, dst, x, zero_ring):
-        x = torch.as_tensor(x)
+        """(B,1,N,N) problem data -> padded fp64 buffer.  fp32 input (the reference's dtype) goes through the padded fp32
+        layout (in place for our own strided views) and ONE widening kernel; fp64 input is copied as is."""
+        x = x0 = torch.as_tensor(x)
         while x.dim() < 4:
             x = x[None]
         N = self.u[0].N
@@ -234,12 +236,17 @@ class VCycleEngine:
             x = x.expand(self.B, -1, -1, -1)
         if tuple(x.shape) != (self.B, 1, N, N):
             raise mgfea.MgfeaError(f"field shape {tuple(x.shape)} does not match level ({self.B},1,{N},{N})")
-        dst[:, :, :N].copy_(x[:, 0].to(dtype=torch.float64), non_blocking=True)
-        if zero_ring:  # the first reset_boundary of the reference's sweep (default Dirichlet ring)
-            dst[:, 0, :] = 0
-            dst[:, N - 1, :] = 0
-            dst[:, :, 0] = 0
-            dst[:, :, N - 1:] = 0
+        if x.dtype == torch.float64:
+            dst[:, :, :N].copy_(x[:, 0], non_blocking=True)
+            if zero_ring:  # the first reset_boundary of the reference's sweep (default Dirichlet ring)
+                dst[:, 0, :] = 0
+                dst[:, N - 1, :] = 0
+                dst[:, :, 0] = 0
+                dst[:, :, N - 1:] = 0
+            return
+        own = x0.dim() == 4 and x0.shape[0] == self.B and x0.dtype == torch.float32  # possibly one of our padded views
+        fld = mgfea.as_field(x0 if own else x.to(dtype=torch.float32), self.dev)
+        check(lib().mgfea_widen_f64(fld.ptr, dst.data_ptr(), N, fld.pitch, fld.plane, self.B, int(zero_ring), stream_ptr()))
 
     def _mixed_step(self, use_ctl=True):
         """e = V-cycle(0, r) in fp32; u64 += e; r = f64 - K u64 (fp64, rounded to fp32 into the cycle's rhs) + norm"""

@@ -1908,6 +1908,17 @@ static int correct_f64(const mgfea_grid *g, const mgfea_slab *sl, double *u, con
     return (int)cudaGetLastError();
 }
 
+int mgfea_widen_f64(const float *src, double *dst, int N, int pitch, int64_t plane, int B, int zero_ring, void *stream) {
+    if (!src || !dst || N < 3 || pitch < N || B < 1) return MGFEA_EINVAL;
+    if ((pitch & 3) || (plane & 3) || (reinterpret_cast<uintptr_t>(src) & 7u) || (reinterpret_cast<uintptr_t>(dst) & 15u))
+        return MGFEA_EALIGN;
+    const long long total = (long long)B * N * (pitch / 2);
+    int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    mg_widen_f64_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, N, pitch, plane, B, zero_ring);
+    g_launches.fetch_add(1);
+    return (int)cudaGetLastError();
+}
+
 int mgfea_defect_f64(const mgfea_grid *g, const double *u, const double *f, float *r, double *sumsq, mgfea_ctl *ctl,
                      double *hist, int B, void *stream) {
     return defect_f64(g, nullptr, u, f, r, sumsq, ctl, hist, B, stream);

@@ -177,4 +177,28 @@ __global__ void __launch_bounds__(256) mg_correct_f64_kernel(double *u, const fl
     }
 }
 
+// padded fp32 field -> padded fp64 field (same pitch / plane counts); zero_ring: the Dirichlet ring of the iterate is
+// cleared on the way (the reference's first reset_boundary)
+__global__ void __launch_bounds__(256) mg_widen_f64_kernel(const float *src, double *dst, int N, int pitch, long long plane,
+                                                          int B, int zero_ring) {
+    const int half = pitch >> 1;
+    const long long total = (long long)B * N * half;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int xp = (int)(i % half);
+        const long long ry = i / half;
+        const int y = (int)(ry % N), x = 2 * xp;
+        const long long o = (ry / N) * plane + (long long)y * pitch + x;
+        const float2 v = *reinterpret_cast<const float2 *>(src + o);
+        double2 w = make_double2((double)v.x, (double)v.y);
+        if (x >= N) w.x = 0.0;
+        if (x + 1 >= N) w.y = 0.0;
+        if (zero_ring) {
+            const bool rr = (y == 0 || y == N - 1);
+            if (rr || x == 0 || x == N - 1) w.x = 0.0;
+            if (rr || x + 1 == N - 1) w.y = 0.0;
+        }
+        *reinterpret_cast<double2 *>(dst + o) = w;
+    }
+}
+
 }  // namespace mgfea
