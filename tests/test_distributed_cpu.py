@@ -234,3 +234,44 @@ def test_exchange_plan_moves_the_right_rows():
         for i in range(lev["nrows"]):
             g = lev["row0"] + i
             assert (v[i] == g).all(), (r, g)
+
+
+@pytest.mark.parametrize("world,n,dist_min_n", [(2, 512, 129), (4, 1024, 257), (8, 16384, 2049), (8, 2048, 257), (1, 256, 129)])
+def test_slab_partition_invariants(world, n, dist_min_n):
+    """every row of every distributed level has exactly one owner, boundaries are even (fine row 2I and coarse row I
+    share a rank), ghost rows stay inside the domain, levels below the threshold are replicated"""
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "multigrid-feanet_b200")]
+    from FEANet.distributed import GHOST, SlabPartition
+
+    L = int(np.log2(n))
+    parts = [SlabPartition(n, L, world, r, dist_min_n) for r in range(world)]
+    ld = parts[0].ld
+    assert all(p.ld == ld for p in parts)
+    for l in range(L):
+        N = n // 2 ** l + 1
+        levs = [p.levels[l] for p in parts]
+        if l >= ld:
+            assert all(not v["dist"] and v["own0"] == 0 and v["own1"] == N and v["nrows"] == N for v in levs)
+            continue
+        assert N >= dist_min_n and all(v["dist"] for v in levs)
+        owner = np.zeros(N, int)
+        for r, v in enumerate(levs):
+            assert v["own0"] % 2 == 0 and (v["own1"] % 2 == 0 or v["own1"] == N)
+            assert v["row0"] == max(0, v["own0"] - GHOST) and v["row0"] + v["nrows"] == min(N, v["own1"] + GHOST)
+            owner[v["own0"]:v["own1"]] += 1
+            if l + 1 < ld:  # coarse rows I = own0/2 .. live on the same rank
+                c = parts[r].levels[l + 1]
+                assert c["own0"] == v["own0"] // 2 and (c["own1"] == v["own1"] // 2 or c["own1"] == (N - 1) // 2 + 1)
+        assert (owner == 1).all()
+
+
+def test_bench_algorithmic_bytes_match_survey():
+    """64 B per fine DOF per V(1,1) cycle = 1.0745 GB at 4097^2; 4.30 GB at 8193^2 and at 1025^2 x 64"""
+    sys.path[:0] = [ROOT]
+    import bench
+
+    b = bench.algorithmic_bytes_per_cycle(4096, 12)
+    assert abs(b / 4097 ** 2 - 64) < 0.1 and abs(b / 1e9 - 1.0745) < 1e-3
+    assert abs(bench.algorithmic_bytes_per_cycle(8192, 13) / 1e9 - 4.30) < 0.01
+    assert abs(bench.algorithmic_bytes_per_cycle(1024, 8, B=64) / 1e9 - 4.30) < 0.02
+    assert bench.algorithmic_bytes_per_cycle(4096, 12, key_bytes=1) > b
