@@ -1129,7 +1129,10 @@ static int run_program_(const Program &pr, cudaStream_t st) {
     // profiles/r01_th_sweep_cfg3.log), so among TH in {knob, knob-4, knob-8} take the one with the most resident CTAs
     const bool hj = (pr.nsweeps > 0 && pr.smoother == MGFEA_SMOOTH_HJACOBI);
     int TH = knobs().th;
-    p.nstages = knobs().stages;
+    // keyed Jacobi programs stall on their tile loads (ncu: long_scoreboard on top, profiles/
+    // r01_ncu_full_tile_keys_cfg3jac.json): double-buffer them (0.366 -> 0.352 ms/cycle on config 3 / Jacobi); the HNet
+    // programs have no shared memory to spare for a second stage (0.632 -> 0.788 with it)
+    p.nstages = (keys && !hj && getenv("MGFEA_STAGES") == nullptr) ? 2 : knobs().stages;
     size_t smem = 0;
     if ((keys || hj) && getenv("MGFEA_TH") == nullptr) {
         int best_th = TH, best_ctas = 0;
