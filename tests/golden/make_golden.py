@@ -349,11 +349,185 @@ def gen_solve():
     print("solve fixtures written")
 
 
+# ---------------------------------------------------------------------------------------------------------
+# fp64 noise bands for the histories that had none, and BASELINE config 3 through the unmodified reference
+# ---------------------------------------------------------------------------------------------------------
+def closed_form_keys(N, shape=0):
+    """pattern key per node of the two-phase plate in integer arithmetic; asserted below against the
+    reference's own MeshCenterInterface before it is used to feed the reference classes at sizes its O(N^4) setup
+    cannot reach"""
+    n = N - 1
+    c = 2 * np.arange(n) + 1 - n
+    if shape == 0:
+        ph = (4 * (c[None, :] ** 2 + c[:, None] ** 2) < n * n).astype(np.int64)
+    else:
+        ph = ((2 * np.abs(c[None, :]) < n) & (2 * np.abs(c[:, None]) < n)).astype(np.int64)
+    pe = np.zeros((n + 2, n + 2), np.int64)
+    pe[1:-1, 1:-1] = ph  # pe[r+1, c+1] = phase of element (r, c)
+    i, j = np.meshgrid(np.arange(N), np.arange(N), indexing="ij")
+    e1, e2, e3, e4 = pe[i, j + 1], pe[i, j], pe[i + 1, j], pe[i + 1, j + 1]  # (i-1,j), (i-1,j-1), (i,j-1), (i,j)
+    ref = {0: [0, 0, 0, 0], 1: [1, 1, 1, 1], 2: [0, 0, 0, 1], 3: [0, 0, 1, 0], 4: [1, 0, 0, 0], 5: [0, 1, 0, 0],
+           6: [0, 0, 1, 1], 7: [1, 1, 0, 0], 8: [0, 1, 1, 0], 9: [1, 0, 0, 1], 10: [0, 1, 0, 1], 11: [1, 0, 1, 0],
+           12: [1, 1, 1, 0], 13: [1, 1, 0, 1], 14: [0, 1, 1, 1], 15: [1, 0, 1, 1]}
+    lut = np.zeros(16, np.int64)
+    for k, p in ref.items():
+        lut[p[0] * 8 + p[1] * 4 + p[2] * 2 + p[3]] = k
+    keys = lut[e1 * 8 + e2 * 4 + e3 * 2 + e4]
+    keys[0, :] = keys[-1, :] = 0
+    keys[:, 0] = keys[:, -1] = 0
+    return keys.astype(np.uint8)
+
+
+def _to_double(grid):
+    grid.Knet.double()
+    grid.Knet.global_pattern = grid.Knet.global_pattern.double()
+    grid.jac.geometry_idx = grid.jac.geometry_idx.double()
+    grid.jac.boundary_value = grid.jac.boundary_value.double()
+    grid.jac.d_mat = grid.jac.d_mat.double()
+    grid.v = grid.v.double()
+    grid.f = grid.f.double()
+    grid.fnet.double()
+
+
+def gen_bands():
+    import torch.nn.functional as F_
+
+    out = {}
+    # ---- MM_Interface_error (quirk variant), fp64
+    nsI = H.notebook_namespace("MM_Interface_error.ipynb", [0, 1, 2])
+    prob = nsI["Multigrid"](64)
+    for g in prob.grids.values():
+        _to_double(g)
+    prob.grids[0].f = prob.grids[0].fnet(torch.ones(1, 1, 65, 65, dtype=torch.float64))
+
+    def Restrict(f):
+        k = torch.asarray([[1, 2, 1], [2, 4, 2], [1, 2, 1]], dtype=torch.float64) / 16.0
+        return F_.pad(F_.conv2d(f[:, :, 1:-1, 1:-1], k.view(1, 1, 3, 3), stride=2), (1, 1, 1, 1), "constant", 0)
+
+    prob.Restrict = Restrict
+    prob.grids[0].v = torch.zeros((1, 1, 65, 65), dtype=torch.float64)
+    rl = []
+    with torch.no_grad():
+        for _ in range(14):
+            prob.rec_V_cycle(0, prob.grids[0].v, prob.grids[0].f)
+            r = prob.grids[0].f - prob.grids[0].Knet(prob.grids[0].v)
+            rl.append(torch.sqrt(torch.sum(r[:, :, 1:-1, 1:-1] ** 2)).item())
+    out["interface_quirk_n64"] = dict(res64=rl)
+    print("interface_quirk fp64", rl[:2], rl[-1])
+
+    # ---- M-FEANet-mg_test MultiGrid on the IsoPoisson 33^2 samples, fp64
+    bi, bv, rhs, uex = H.read_h5_contiguous(os.path.join(H.REF, "Data/IsoPoisson/poisson2d_33x33.h5"), (100, 33, 33))
+    nsT = H.notebook_namespace("M-FEANet-mg_test.ipynb", [1, 2, 3, 4, 5, 18, 19, 20])
+    sd = torch.load(os.path.join(H.REF, "Model/learn_iterator/iso_poisson/iso_poisson_33x33.pth"), weights_only=True)
+    for mode in ("jac", "hjac"):
+        for k in range(3):
+            n = 32
+            hnet = nsT["HNet"](3)
+            hnet.load_state_dict(sd)
+            hnet.double()
+            mg = nsT["MultiGrid"](n=n, hnet=hnet, P=nsT["linear_tensor_P"], mode=mode)
+            mg.conv.double()
+            mg.deconv.double()
+            for it in mg.iterators.values():
+                _to_double(it.grid)
+            # the fp32 run casts the dataset to fp32 first: same inputs here, widened
+            f_mg = torch.from_numpy(rhs[k].astype(np.float32)).double().reshape(1, 1, n + 1, n + 1)
+            bidx = torch.from_numpy(bi[k].astype(np.float32)).double().reshape(1, 1, n + 1, n + 1)
+            bval = torch.from_numpy(bv[k].astype(np.float32)).double().reshape(1, 1, n + 1, n + 1)
+            u_mg = torch.zeros((1, 1, n + 1, n + 1), dtype=torch.float64)
+            want = len(json.load(open(os.path.join(OUT, "solve_histories.json")))[f"mgtest_{mode}_s{k}"]["res"])
+            with torch.no_grad():
+                mg(u_mg, f_mg, bidx, bval, 1)
+                r = mg.f - mg.iterators[0].grid.Knet(mg.u0)
+                rl = [torch.norm(r[:, :, 1:-1, 1:-1].clone(), dim=(2, 3)).item()]
+                while len(rl) < want:
+                    u_mg = mg.Step(u_mg, mg.f)
+                    r = mg.f - mg.iterators[0].grid.Knet(u_mg)
+                    rl.append(torch.norm(r[:, :, 1:-1, 1:-1].clone(), dim=(2, 3)).item())
+            out[f"mgtest_{mode}_s{k}"] = dict(res64=rl)
+            print("mgtest fp64", mode, k, rl[:2], rl[-1])
+
+    # ---- BASELINE config 3: two-phase circle 1:100, 16-channel linear R/P, w = [4, 1], F = ones, u0 = 0, through the
+    #      UNMODIFIED FEANet/multigrid.py MultiGrid.iterate (n_iter shim) fed with a closed-form duck-typed mesh (the
+    #      reference's MeshCenterInterface is O(N^4)); 'hjac': each level's Relax is the unmodified mg_test
+    #      HJacIterator.HRelax with the shipped iso_poisson_33x33.pth weights (SURVEY 8d config 3)
+    M = H.load_reference_multigrid_module()
+    from FEANet.mesh import MeshCenterInterface as RefMesh
+
+    PROP = [1, 100]
+    kd = RefMesh(2, PROP, 9).kernel_dict  # the 16 x (3x3) table is size independent: the reference builds it
+    for n in (8, 16, 32):  # the closed form against the reference's own key maps
+        m = RefMesh(2, PROP, n + 1)
+        assert np.array_equal(keys_of(m), closed_form_keys(n + 1, 0)), n
+
+    class FastMesh:
+        def __init__(self, size, prop, nnode_edge, shape=0):
+            self.nnode_edge = int(nnode_edge)
+            self.kernel_dict = kd
+            k = closed_form_keys(self.nnode_edge, shape).reshape(-1)
+            self.global_pattern_center = {key: (k == key).astype(int) for key in kd}
+
+    HJ = nsT["HJacIterator"]
+
+    def make(n, mode, double):
+        hnet = nsT["HNet"](3)
+        hnet.load_state_dict(sd)
+
+        class HGrid(M.SingleGrid):
+            def Relax(self, v, f, k):
+                if not hasattr(self, "_it"):
+                    self._it = HJ(n=self.n, hnet=hnet, grid=self)
+                return self._it.HRelax(v, f, k)
+
+        saved = M.MeshCenterInterface, M.SingleGrid
+        M.MeshCenterInterface = FastMesh
+        if mode == "hjac":
+            M.SingleGrid = HGrid
+        try:
+            P4 = torch.tensor([[1, 2, 1], [2, 4, 2], [1, 2, 1]], dtype=torch.float32) / 4.0
+            R16 = torch.tensor([[1, 2, 1], [2, 4, 2], [1, 2, 1]], dtype=torch.float32) / 16.0
+            mg = M.MultiGrid(n, R16, P4, torch.tensor([4.0, 1.0]))
+        finally:
+            M.MeshCenterInterface, M.SingleGrid = saved
+        if double:
+            hnet.double()
+            mg.double()
+            for g in mg.grids.values():
+                _to_double(g)
+        return mg
+
+    for n, ncyc in ((64, 10), (256, 8)):
+        for mode in ("jac", "hjac"):
+            rec = {}
+            for double in (False, True):
+                t0 = time.time()
+                mg = make(n, mode, double)
+                dt = torch.float64 if double else torch.float32
+                with torch.no_grad():
+                    f = mg.grids[0].fnet(torch.ones(1, 1, n + 1, n + 1, dtype=dt))
+                    x = torch.zeros(1, 1, n + 1, n + 1, dtype=dt)
+                    r = f - mg.grids[0].Knet(x)
+                    r0 = torch.norm(r[:, :, 1:-1, 1:-1], dim=(2, 3)).item()
+                    rl = []
+                    for _ in range(ncyc):
+                        x = mg.iterate(x, f)
+                        r = f - mg.grids[0].Knet(x)
+                        rl.append(torch.norm(r[:, :, 1:-1, 1:-1], dim=(2, 3)).item())
+                rec["res64" if double else "res"] = rl
+                rec["r0_64" if double else "r0"] = r0
+                print("cfg3", n, mode, "fp64" if double else "fp32", "%.1fs" % (time.time() - t0), r0, rl)
+            out[f"cfg3_{mode}_n{n}"] = dict(n=n, prop=PROP, mode=mode, w=[4.0, 1.0], **rec)
+    json.dump(out, open(os.path.join(OUT, "bands.json"), "w"), indent=1)
+    print("bands.json written")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["mesh", "ops", "solve"]
+    which = sys.argv[1:] or ["mesh", "ops", "solve", "bands"]
     if "mesh" in which:
         gen_mesh()
     if "ops" in which:
         gen_ops()
     if "solve" in which:
         gen_solve()
+    if "bands" in which:
+        gen_bands()

@@ -7,12 +7,14 @@ import numpy as np
 import pytest
 
 from oracle import oracle as O
+from tolerance import check_band
 
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 OPS = np.load(os.path.join(G, "ops.npz"))
 MESH = np.load(os.path.join(G, "mesh.npz"))
 ARR = np.load(os.path.join(G, "solve_arrays.npz"))
 HIST = json.load(open(os.path.join(G, "solve_histories.json")))
+BANDS = json.load(open(os.path.join(G, "bands.json")))  # fp64 runs of the reference (noise bands) + config 3
 
 SIZES = (9, 17, 33)
 TAGS = {"iso": (None, None), "c20": ([1, 20], 0), "s100": ([1, 100], 1)}
@@ -195,13 +197,11 @@ def test_interface_quirk_history():
     f = O.conv3x3(np.ones((1, n + 1, n + 1), np.float32), O.load_vector_weights(2.0 / n))
     u, res = O.solve(levels, cfg, np.zeros((n + 1, n + 1), np.float32), f, EPS=5e-5)
     assert len(res) == len(h["res"]) == 14
-    rel = np.abs(np.array(res) - np.array(h["res"])) / np.array(h["res"])
-    # this 1:20 problem amplifies fp32 noise: the reference run here differs from the outputs recorded in the
-    # notebook by 4.5e-6 (cycle 1) .. 1.5e-2 (cycle 14).  Same envelope for the oracle: 2e-5 * 2^k, capped at 2e-2.
-    band = np.minimum(2e-5 * 2.0 ** np.arange(len(res)), 2e-2)
-    assert (rel <= band).all(), (rel, band)
+    # this 1:20 problem amplifies fp32 noise (the reference run here differs from the outputs recorded in the notebook
+    # by 4.5e-6 at cycle 1 .. 1.5e-2 at cycle 14): tolerance = the reference's own recorded fp32-vs-fp64 drift
+    check_band(res, h["res"], BANDS["interface_quirk_n64"]["res64"], "interface quirk")
     nb = np.array(h["notebook_recorded"])
-    assert (np.abs(np.array(res) - nb) / nb <= band * 2).all()
+    assert (np.abs(np.array(res) - nb) / nb <= 2 * np.minimum(2e-5 * 2.0 ** np.arange(len(res)), 2e-2)).all()
 
 
 @pytest.mark.parametrize("mode", ["jac", "hjac"])
@@ -221,10 +221,7 @@ def test_mgtest_histories(mode, k):
         u = O.vcycle(levels, cfg, u, f)
         res.append(float(O.residual_norm(levels, u, f)[0]))
     assert len(res) == len(h["res"]), (len(res), len(h["res"]))
-    ref = np.array(h["res"])
-    rel = np.abs(np.array(res) - ref) / ref
-    tol = np.where(ref / ref[0] > 1e-3, 2e-5, np.where(ref / ref[0] > 1e-4, 1e-3, 0.5))
-    assert (rel <= tol).all(), (rel, tol)
+    check_band(res, h["res"], BANDS[f"mgtest_{mode}_s{k}"]["res64"], f"mgtest {mode} {k}")
     close(u, ARR[f"mgtest_{mode}_s{k}_u"][:, 0], rtol=2e-5)
 
 
@@ -246,6 +243,30 @@ def test_committed_multigrid_iterate(tag):
         ref = np.array(h["res"][it])
         assert (np.abs(got - ref) / ref < 3e-5 * 4 ** it).all(), (it, got, ref)
     close(x, ARR[f"iterate_{tag}_u"][:, 0], rtol=1e-4)
+
+
+@pytest.mark.parametrize("mode", ["jac", "hjac"])
+@pytest.mark.parametrize("n", [64, 256])
+def test_config3_histories(mode, n):
+    """BASELINE config 3 (two-phase circle 1:100, keys + 16-channel linear R/P, w = [4, 1], Jacobi / learned HNet
+    smoother) against the UNMODIFIED FEANet/multigrid.py MultiGrid.iterate fed with a closed-form mesh
+    (tests/golden/make_golden.py gen_bands).  Faithful includes the reference's failure: at n = 256 the Jacobi cycle
+    STALLS near 3 r0 (rediscretised coarse operators + linear R/P across a 1:100 interface), and so must we."""
+    b = BANDS[f"cfg3_{mode}_n{n}"]
+    levels = O.make_levels(n, None, prop=b["prop"], shape=0)
+    R, P = np.repeat(O.FW16, 16, 0), np.repeat(O.LIN4, 16, 0)
+    cfg = O.CycleCfg(smoother=mode, hw=OPS["hnet_w"], prolong="table", rtab=R, r_scale=b["w"][0], ptab=P,
+                     p_scale=b["w"][1])
+    f = O.conv3x3(np.ones((1, n + 1, n + 1), np.float32), O.load_vector_weights(2.0 / n))
+    u = np.zeros((1, n + 1, n + 1), np.float32)
+    assert abs(float(O.residual_norm(levels, u, f)[0]) - b["r0"]) <= 1e-6 * b["r0"]
+    res = []
+    for _ in range(len(b["res"])):
+        u = O.vcycle(levels, cfg, u, f)
+        res.append(float(O.residual_norm(levels, u, f)[0]))
+    check_band(res, b["res"], b["res64"], f"config 3 {mode} n={n}")
+    if n == 256 and mode == "jac":
+        assert min(res[3:]) > 2.0 * b["r0"], "the reference stalls here; a converging history is NOT parity"
 
 
 def test_feanet_torch_matches_reference_histories():
