@@ -299,9 +299,6 @@ class CudaSlabOps:
         """one V-cycle from a zero guess on the replicated levels; rhs / result live in the engine's level-0 buffers"""
         self.coarse.cycle()
 
-    def full_cycle_single(self, u, f):
-        raise NotImplementedError
-
 
 class SlabMultigrid:
     """V(1,1) solver for the iso Poisson problem on row slabs.  `ops` supplies the local operators."""
@@ -529,10 +526,37 @@ class SlabMultigrid:
             peer.step((("u", l),), reduce=(want_norm and l == 0))
         return peer.total if want_norm else None
 
+    def _sync_ranks(self):
+        """Order every rank's LOCAL writes to its slab arrays (set_problem / fill_local / zero_(), ghost rows included)
+        before any peer starts storing into those ghost rows: a neighbour that runs ahead would otherwise have its pushed
+        rows wiped by this rank's own initialisation while the flag still counts the push."""
+        if self.world > 1:
+            if torch.cuda.is_available():
+                torch.cuda.current_stream().synchronize()
+            dist.barrier(group=self.group)
+
+    def close(self):
+        """drop the captured graphs and unmap / free the peer block (IPC mappings do not go away with the Python object)"""
+        self._graph = self._graph64 = None
+        if getattr(self.ops, "coarse", None) is not None:
+            self.ops.coarse._graph = None
+        if self.peer is not None:
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+            if self.world > 1:
+                dist.barrier(group=self.group)  # nobody may still be storing into a block that is about to be freed
+            self.u = self.u_alt = self.f = []
+            self.peer.partial = self.peer.total = self.peer.err = None
+            self.ops._sumsq = None
+            self.ops.coarse = None
+            self.peer.block.close()
+            self.peer = None
+
     def exchange_initial(self):
         """ghost rows of the level-0 iterate and right-hand side (after set_problem / fill_local)"""
         if self.part.ld == 0:
             return
+        self._sync_ranks()
         if self.peer is not None:
             self.peer.step((("u", 0), ("f", 0)))
         else:
@@ -572,6 +596,7 @@ class SlabMultigrid:
         self.f64.zero_()
         o0, o1 = lev["own0"] - lev["row0"], lev["own1"] - lev["row0"]
         self.f64[0, o0:o1, :N].copy_(fn_f(lev["own0"], o1 - o0, N))
+        self._sync_ranks()  # the zero fill above covers the ghost rows the neighbours are about to store into
         self.peer.step((("f64", 0),))
 
     def SolveMixed(self, n_iter=None, EPS=None, max_cycles=200, use_graph=True):
@@ -583,6 +608,7 @@ class SlabMultigrid:
             n_iter = 0
         elif EPS is None:
             EPS = math.inf
+        self._sync_ranks()  # set_problem64 / fill_local64 wrote ghost rows locally; peers push into them next
         self._defect64()
         self.r0 = float(torch.sqrt(peer.total.sum()).item())
         res, hist = self.r0, []
