@@ -237,8 +237,10 @@ def _replay(eng, k, zero_ctl):
         done += c
 
 
-def time_engine(eng, steps, warm=3, repeats=REPEATS):
-    """median over `repeats` of CUDA-event timed blocks of `steps` graph-replayed cycles (ms per cycle, all blocks)"""
+def time_engine(eng, steps, warm=3, repeats=REPEATS, reset=None):
+    """median over `repeats` of CUDA-event timed blocks of `steps` graph-replayed cycles (ms per cycle, all blocks);
+    `reset` (untimed) restores the initial iterate before every block: configurations on which the reference algorithm
+    diverges would otherwise overflow, and a solve that has gone to inf / NaN stops doing work (device-side guard)"""
     import torch
 
     eng.refresh()
@@ -250,6 +252,8 @@ def time_engine(eng, steps, warm=3, repeats=REPEATS):
     out = []
     for _ in range(repeats):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if reset is not None:
+            reset()
         eng.ctl.copy_(zero, non_blocking=True)
         a.record()
         _replay(eng, steps, zero)
@@ -259,9 +263,11 @@ def time_engine(eng, steps, warm=3, repeats=REPEATS):
     return float(np.median(out)), out
 
 
-def config_entry(name, eng, n, L, B, key_bytes, hist, steps=20):
+def config_entry(name, eng, n, L, B, key_bytes, hist, steps=20, reset=None):
     peak, _ = hbm_peak()
-    ms, runs = time_engine(eng, steps)
+    if reset is not None:
+        reset()
+    ms, runs = time_engine(eng, steps, reset=reset)
     balg = algorithmic_bytes_per_cycle(n, L, B=B, key_bytes=key_bytes)
     dof = (n + 1) ** 2 * B
     return {"config": name, "ms_per_cycle": ms, "ms_runs": runs, "v_cycles_per_s": 1e3 / ms,
@@ -311,7 +317,8 @@ def secondary_configs(which):
             out[tag] = config_entry(f"config 3: two-phase circle 1:100, 4097^2, 12 levels, V(1,1), "
                                     f"{'learned HNet' if smoother == 'hjac' else 'Jacobi'} smoother, 16-ch linear R/P, "
                                     "w=[4,1], F=ones; the reference algorithm itself diverges at this depth (DESIGN 5, "
-                                    "tests/golden/bands.json cfg3_*): throughput per cycle", eng, n, L, B, 1, hist)
+                                    "tests/golden/bands.json cfg3_*): throughput per cycle", eng, n, L, B, 1, hist,
+                                    steps=10, reset=lambda: eng.u[0].zero_())
             del eng, grids
             torch.cuda.empty_cache()
     for tag, n in (("cfg4_1gpu", 8192), ("cfg5_1gpu", 16384)):
@@ -326,8 +333,9 @@ def secondary_configs(which):
         r0 = float(torch.sqrt(eng.residual_sumsq().sum()).item())
         hist = [x / r0 for x in eng.run(n_iter=8)]
         out["cfg5_two_phase_1gpu"] = config_entry("config 5 on 1 GPU: two-phase circle 1:20, 16385^2, 14 levels, V(1,1) "
-                                                  "Jacobi, full weighting + bilinear prolongation, F=ones", eng, n, L,
-                                                  1, 1, hist, steps=10)
+                                                  "Jacobi, full weighting + bilinear prolongation, F=ones (the "
+                                                  "reference algorithm diverges at this depth)", eng, n, L,
+                                                  1, 1, hist, steps=10, reset=lambda: eng.u[0].zero_())
         del eng, grids
         torch.cuda.empty_cache()
     return out
