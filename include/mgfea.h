@@ -199,7 +199,7 @@ typedef struct mgfea_xchg {
     const double *red_src; /* optional: after the wait, *red_dst = sum of nred doubles spaced red_stride bytes apart */
     double *red_dst;
     int32_t nred, red_stride;
-    int32_t grid;    /* CTAs of this step, 1..64: MUST be the same on every rank (a flag counts the pushing CTAs) */
+    int32_t grid;    /* CTAs of this step, 1..512: MUST be the same on every rank (a flag counts the pushing CTAs) */
     int32_t pad_;
 } mgfea_xchg;
 int mgfea_p2p_exchange(const mgfea_xchg *x, void *stream);
@@ -222,6 +222,10 @@ int mgfea_correct_f64(const mgfea_grid *g, double *u, const float *e, const mgfe
 int mgfea_slab_defect_f64(const mgfea_grid *g, const mgfea_slab *s, const double *u, const double *f, float *r,
                           double *sumsq, int B, void *stream);
 int mgfea_slab_correct_f64(const mgfea_grid *g, const mgfea_slab *s, double *u, const float *e, int B, void *stream);
+/* the same defect written on the owned rows and on `ext` rows per side (the deep-halo slab cycle computes its ghost rows
+ * redundantly instead of exchanging them: FEANet/distributed.py); u must be valid on ext + 1 rows per side */
+int mgfea_slab_defect_f64_ext(const mgfea_grid *g, const mgfea_slab *s, int ext, const double *u, const double *f,
+                              float *r, double *sumsq, int B, void *stream);
 
 /* ---- whole V-cycle ----------------------------------------------------------------------------------- */
 typedef struct mgfea_cycle_cfg {

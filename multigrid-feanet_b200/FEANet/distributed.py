@@ -19,31 +19,59 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-GHOST = 4  # ghost rows per side: the fused legs read 3 rows above / 2 below their owned range (streaming kernels)
+GHOST = 4  # margin rows kept beyond the redundantly computed range: the fused legs stream 3 rows above / 2 below it
+
+
+def halo_depths(ld):
+    """Communication-avoiding deep halos.  With `ld` distributed levels a rank computes, besides its owned rows, `a[l]`
+    extra rows per side of the down leg of level l and `y[l]` of the up leg REDUNDANTLY (bit-identical to what the
+    neighbour computes for the same rows), so that no level needs a halo exchange inside the cycle:
+
+      up leg     y[0] = 0; y[l] = 2: level l-1 prolongs from coarse rows own +- (y[l-1]/2 + 1)
+      down leg   the last distributed level only feeds the gathered replicated right-hand side: a[ld-1] = 4 (>= y + 1,
+                 the rows of the pre-smoothed iterate its own up leg reads); level l must produce the coarse right-hand
+                 side on own_{l+1} +- (a[l+1] + 2) (residual + restriction stencils), i.e. a[l] = 2 a[l+1] + 4
+
+    Per cycle only TWO exchange steps remain: the gather of the first replicated right-hand side, and after the finest
+    up leg the push of a[0] + GHOST rows of the new iterate together with the all-reduce of the residual norm.
+    Returns (a, y, G): G[l] = a[l] + GHOST ghost rows per side are held in memory."""
+    a = [0] * ld
+    for l in range(ld - 1, -1, -1):
+        a[l] = 4 if l == ld - 1 else 2 * a[l + 1] + 4
+    y = [0 if l == 0 else 2 for l in range(ld)]
+    return a, y, [v + GHOST for v in a]
 
 
 class SlabPartition:
-    """Host-side description of which global rows of every level a rank owns / holds."""
+    """Host-side description of which global rows of every level a rank owns / holds / computes."""
 
     def __init__(self, n, L, world, rank, dist_min_n=2049):
         self.n, self.L, self.world, self.rank, self.dist_min_n = n, L, world, rank, dist_min_n
+        # number of distributed levels: the size threshold, then as many as leave every rank at least G[l] owned rows
+        ld = 0
+        if world > 1:
+            while ld < L and (n // 2 ** ld + 1) >= dist_min_n and (n // 2 ** ld) % (2 * world) == 0:
+                ld += 1
+            while ld > 0 and any((n // 2 ** l) // world < g for l, g in enumerate(halo_depths(ld)[2])):
+                ld -= 1
+        a, y, G = halo_depths(ld)
         self.levels = []
         for l in range(L):
             nl = n // (2 ** l)
             N = nl + 1
-            distributed = (world > 1) and (N >= dist_min_n) and (nl % (2 * world) == 0) and (nl // world >= 2 * GHOST)
-            if l > 0 and not self.levels[-1]["dist"]:
-                distributed = False
-            if distributed:
+            if l < ld:
                 per = nl // world
                 own0 = rank * per
                 own1 = (rank + 1) * per + (1 if rank == world - 1 else 0)
-                row0 = max(0, own0 - GHOST)
-                row1 = min(N, own1 + GHOST)
+                row0 = max(0, own0 - G[l])
+                row1 = min(N, own1 + G[l])
+                lev = dict(N=N, dist=True, own0=own0, own1=own1, row0=row0, nrows=row1 - row0, G=G[l],
+                           dn0=max(0, own0 - a[l]), dn1=min(N, own1 + a[l]), up0=max(0, own0 - y[l]),
+                           up1=min(N, own1 + y[l]))
             else:
-                own0, own1, row0, row1 = 0, N, 0, N
-            self.levels.append(dict(N=N, dist=distributed, own0=own0, own1=own1, row0=row0, nrows=row1 - row0))
-        self.ld = next((l for l, v in enumerate(self.levels) if not v["dist"]), L)  # first replicated level
+                lev = dict(N=N, dist=False, own0=0, own1=N, row0=0, nrows=N, G=0, dn0=0, dn1=N, up0=0, up1=N)
+            self.levels.append(lev)
+        self.ld = ld  # first replicated level
         if self.ld == L and world > 1:
             raise ValueError("the coarsest levels must be replicated: lower dist_min_n or use fewer ranks")
 
@@ -62,13 +90,13 @@ def halo_exchange(arr, lev, rank, world, group=None):
     """refresh the ghost rows of a local slab array (B=1: [1][nrows][pitch]) from the neighbouring ranks"""
     if world == 1 or not lev["dist"]:
         return
-    r0, own0, own1 = lev["row0"], lev["own0"], lev["own1"]
+    r0, own0, own1, G = lev["row0"], lev["own0"], lev["own1"], lev["G"]
     a = arr[0]
     pairs = []  # (send view, recv view, peer)
     if rank > 0:  # neighbour above (smaller row indices)
-        pairs.append((a[own0 - r0: own0 - r0 + GHOST], a[own0 - r0 - GHOST: own0 - r0], rank - 1))
+        pairs.append((a[own0 - r0: own0 - r0 + G], a[own0 - r0 - G: own0 - r0], rank - 1))
     if rank < world - 1:  # neighbour below
-        pairs.append((a[own1 - r0 - GHOST: own1 - r0], a[own1 - r0: own1 - r0 + GHOST], rank + 1))
+        pairs.append((a[own1 - r0 - G: own1 - r0], a[own1 - r0: own1 - r0 + G], rank + 1))
     stage = _staged(arr, group)
     ops, bufs = [], []
     for send, recv, peer in pairs:
@@ -122,12 +150,12 @@ class SlabExchangePlan:
         red = (src_off, dst_off, n, stride) or None"""
         part, rank, world = self.part, self.part.rank, self.part.world
         jobs = []
-        for name, l in halos:  # GHOST boundary rows of my owned range -> the neighbours' ghost rows
+        for name, l in halos:  # G boundary rows of my owned range -> the neighbours' ghost rows
             lev, rowb, off = part.levels[l], self.pitch[l] * self.esize(name), self.off[(name, l)]
-            for q, first in ((rank - 1, lev["own0"]), (rank + 1, lev["own1"] - GHOST)):
+            for q, first in ((rank - 1, lev["own0"]), (rank + 1, lev["own1"] - lev["G"])):
                 if 0 <= q < world:
                     jobs.append((off + (first - lev["row0"]) * rowb, q,
-                                 off + (first - self.parts[q].levels[l]["row0"]) * rowb, GHOST * rowb))
+                                 off + (first - self.parts[q].levels[l]["row0"]) * rowb, lev["G"] * rowb))
         if gather:  # my owned rows of the first replicated level's right-hand side -> every peer
             ld = part.ld
             per, rowb, off = (part.n // 2 ** ld) // world, self.pitch[ld] * 4, self.off[("f", ld)]
@@ -150,9 +178,9 @@ class SlabExchangePlan:
                 waits.append(self.FLAG_DOWN)
         # CTAs of the step: a function of the step alone (NOT of the rank): the flags count the pushing CTAs.  About one
         # 16-byte chunk per thread for the halo rows, more CTAs when whole coarse slabs travel
-        halo_chunks = sum(GHOST * self.pitch[l] * self.esize(nm) // 16 for nm, l in halos) * 2
+        halo_chunks = sum(part.levels[l]["G"] * self.pitch[l] * self.esize(nm) // 16 for nm, l in halos) * 2
         gather_chunks = ((part.n // 2 ** part.ld) // world) * self.pitch[part.ld] * 4 // 16 * (world - 1) if gather else 0
-        grid = int(min(64, max(1, (halo_chunks + gather_chunks // 4 + 255) // 256)))
+        grid = int(min(296, max(1, (halo_chunks + gather_chunks // 4 + 255) // 256)))
         return dict(jobs=jobs, signals=signals, waits=waits, seq=seq, grid=grid, red=red)
 
 
@@ -272,14 +300,16 @@ class CudaSlabOps:
         g.plane = arr.shape[1] * arr.shape[2]
         return g
 
-    def _slab(self, l):
+    def _slab(self, l, leg="own"):
+        """rows held + rows COMPUTED by a leg: the owned rows, or the owned rows plus the deep-halo rows of that leg"""
         lev = self.part.levels[l]
-        return self.mg.Slab(lev["row0"], lev["nrows"], lev["own0"], lev["own1"])
+        lo, hi = {"own": ("own0", "own1"), "dn": ("dn0", "dn1"), "up": ("up0", "up1")}[leg]
+        return self.mg.Slab(lev["row0"], lev["nrows"], lev[lo], lev[hi])
 
     def down(self, l, u_in, u_out, f, fc):
         mg = self.mg
         g = self._grid(l, u_out)
-        s, sc = self._slab(l), self._slab(l + 1)
+        s, sc = self._slab(l, "dn"), self._slab(l + 1)
         mg.check(mg.lib().mgfea_slab_smooth_residual_restrict(
             ctypes.byref(g), ctypes.byref(s), u_in.data_ptr() if u_in is not None else None, u_out.data_ptr(),
             f.data_ptr(), fc.data_ptr(), ctypes.byref(sc), fc.shape[2], fc.shape[1] * fc.shape[2], self.rtab.data_ptr(),
@@ -288,7 +318,7 @@ class CudaSlabOps:
     def up(self, l, vc, u_in, u_out, f, want_norm):
         mg = self.mg
         g = self._grid(l, u_out)
-        s, sc = self._slab(l), self._slab(l + 1)
+        s, sc = self._slab(l, "up"), self._slab(l + 1)
         mg.check(mg.lib().mgfea_slab_prolong_correct_smooth(
             ctypes.byref(g), ctypes.byref(s), vc.data_ptr(), ctypes.byref(sc), vc.shape[2], vc.shape[1] * vc.shape[2],
             u_in.data_ptr(), u_out.data_ptr(), f.data_ptr(), self._sumsq.data_ptr() if want_norm else None, 1,
@@ -335,12 +365,6 @@ class SlabMultigrid:
         self._mixed_steps = 0
         self._graph_out = None
         self._graph_err = None
-        # the exchange of the pre-smoothed u is only needed by the up leg of the same level: it runs on a side stream
-        # with its own communicator so that it overlaps the coarser levels instead of delaying the next restriction
-        self._side_group, self._side_stream = None, None
-        if self.peer is None and self.world > 1 and torch.cuda.is_available() and dist.get_backend(group) == "nccl":
-            self._side_group = dist.new_group(ranks=list(range(self.world)), backend="nccl")
-            self._side_stream = torch.cuda.Stream()
 
     def _try_peer_memory(self):
         """collective: all ranks map each other's block, or all fall back to the NCCL exchange"""
@@ -468,23 +492,10 @@ class SlabMultigrid:
             return ops.coarse.sumsq.clone()
         if self.peer is not None:
             return self._cycle_peer(want_norm)
-        # ---- down leg on the slabs
-        side_done = [None] * ld
+        # ---- down leg on the slabs: no exchange, every level computes its deep-halo rows itself (halo_depths)
         for l in range(ld):
             fc = self.f[l + 1] if l + 1 < ld else ops.coarse_f()
             ops.down(l, self.u[l] if l == 0 else None, self.u_alt[l], self.f[l], fc)
-            if self._side_stream is not None:
-                ev = torch.cuda.Event()
-                ev.record()
-                with torch.cuda.stream(self._side_stream):
-                    self._side_stream.wait_event(ev)
-                    halo_exchange(self.u_alt[l], p.levels[l], self.rank, self.world, self._side_group)
-                    side_done[l] = torch.cuda.Event()
-                    side_done[l].record()
-            else:
-                halo_exchange(self.u_alt[l], p.levels[l], self.rank, self.world, self.group)
-            if l + 1 < ld:
-                halo_exchange(self.f[l + 1], p.levels[l + 1], self.rank, self.world, self.group)
         # ---- replicated coarse levels
         self._allgather_coarse_f()
         ops.coarse_cycle()
@@ -492,10 +503,8 @@ class SlabMultigrid:
         ss = None
         for l in range(ld - 1, -1, -1):
             vc = self.u[l + 1] if l + 1 < ld else ops.coarse_u()
-            if side_done[l] is not None:
-                torch.cuda.current_stream().wait_event(side_done[l])
             ss = ops.up(l, vc, self.u_alt[l], self.u[l], self.f[l], want_norm and l == 0)
-            halo_exchange(self.u[l], p.levels[l], self.rank, self.world, self.group)
+        halo_exchange(self.u[0], p.levels[0], self.rank, self.world, self.group)  # the only halo exchange of the cycle
         if want_norm:
             tot = ss.clone()
             if self.world > 1:
@@ -508,22 +517,26 @@ class SlabMultigrid:
             return tot
         return None
 
-    def _cycle_peer(self, want_norm=True, zero_guess=False):
-        """the same cycle with every exchange done by peer stores (PeerSlabMemory.step): 2 * ld kernels, no NCCL.
-        Buffer discipline (what makes overwriting a neighbour's ghost rows safe without a second handshake): the step
-        after down(l) pushes u_alt[l] / f[l+1], the step after up(l) pushes u[l] -- never an array that the kernel
-        running between two consecutive steps reads."""
+    def _cycle_peer(self, want_norm=True, zero_guess=False, push_u=True):
+        """the same cycle with the two exchanges done by peer stores (PeerSlabMemory.step), no NCCL: the gather of the first
+        replicated right-hand side after the last down leg, and after the finest up leg the push of the G[0] boundary rows
+        of the new iterate into the neighbours' ghost rows together with the all-reduce of the residual norm.
+        Overwriting a neighbour's ghost rows needs no second handshake: u[0]'s ghost rows are read by down(0) only, and a
+        rank reaches its next push of u[0] only after the gather of the NEXT cycle, which every rank enters after its
+        down(0).  The gathered right-hand side is read by the coarse cycle only, and the next gather follows the push /
+        reduce step that every rank enters after its coarse cycle."""
         ops, ld, peer = self.ops, self.part.ld, self.peer
         for l in range(ld):
             last = l == ld - 1
             ops.down(l, self.u[l] if (l == 0 and not zero_guess) else None, self.u_alt[l], self.f[l],
                      ops.coarse_f() if last else self.f[l + 1])
-            peer.step((("u_alt", l),) if last else (("u_alt", l), ("f", l + 1)), gather=last)
+        peer.step((), gather=True)
         ops.coarse_cycle()
         for l in range(ld - 1, -1, -1):
             vc = self.u[l + 1] if l + 1 < ld else ops.coarse_u()
             ops.up(l, vc, self.u_alt[l], self.u[l], self.f[l], want_norm and l == 0)
-            peer.step((("u", l),), reduce=(want_norm and l == 0))
+        if push_u or want_norm:
+            peer.step((("u", 0),) if push_u else (), reduce=want_norm)
         return peer.total if want_norm else None
 
     def _sync_ranks(self):
@@ -631,15 +644,18 @@ class SlabMultigrid:
         """r = f64 - K u64 -> f[0] (owned rows + 3 ghost rows per side), all-rank interior sum of squares -> peer.total"""
         mg, ops, peer = self.ops.mg, self.ops, self.peer
         g, sl = ops._grid(0, self.f[0]), ops._slab(0)
-        peer.step((("u64", 0),))  # 4 ghost rows of the iterate
-        mg.check(mg.lib().mgfea_slab_defect_f64(ctypes.byref(g), ctypes.byref(sl), self.u64.data_ptr(), self.f64.data_ptr(),
-                                                self.f[0].data_ptr(), peer.partial.data_ptr(), 1, mg.stream_ptr()))
+        lev = self.part.levels[0]
+        peer.step((("u64", 0),))  # G[0] ghost rows of the iterate
+        # the zero-guess down leg of level 0 reads its right-hand side on the deep-halo rows + 2
+        mg.check(mg.lib().mgfea_slab_defect_f64_ext(ctypes.byref(g), ctypes.byref(sl), lev["G"] - 2, self.u64.data_ptr(),
+                                                    self.f64.data_ptr(), self.f[0].data_ptr(), peer.partial.data_ptr(), 1,
+                                                    mg.stream_ptr()))
         peer.step((), reduce=True)
 
     def _mixed_iter(self):
         """e = V-cycle(0, r) (fp32, slabs); u64 += e; new defect + norm"""
         mg, ops = self.ops.mg, self.ops
-        self._cycle_peer(want_norm=False, zero_guess=True)
+        self._cycle_peer(want_norm=False, zero_guess=True, push_u=False)  # the correction is used on the owned rows only
         g, sl = ops._grid(0, self.f[0]), ops._slab(0)
         mg.check(mg.lib().mgfea_slab_correct_f64(ctypes.byref(g), ctypes.byref(sl), self.u64.data_ptr(), self.u[0].data_ptr(),
                                                  1, mg.stream_ptr()))

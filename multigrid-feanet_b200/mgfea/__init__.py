@@ -31,7 +31,7 @@ EXPORTS = [
     "mgfea_peer_alloc", "mgfea_peer_free", "mgfea_peer_export", "mgfea_peer_open", "mgfea_peer_close",
     "mgfea_p2p_exchange", "mgfea_trace", "mgfea_prolong_correct_smooth_norm",
     "mgfea_defect_f64", "mgfea_correct_f64", "mgfea_slab_defect_f64", "mgfea_slab_correct_f64", "mgfea_pattern_keys",
-    "mgfea_widen_f64",
+    "mgfea_widen_f64", "mgfea_slab_defect_f64_ext",
 ]
 
 
@@ -137,6 +137,7 @@ def lib():
         L.mgfea_correct_f64.argtypes = [G, vp, vp, vp, i32, vp]
         L.mgfea_slab_defect_f64.argtypes = [G, ctypes.POINTER(Slab), vp, vp, vp, vp, i32, vp]
         L.mgfea_slab_correct_f64.argtypes = [G, ctypes.POINTER(Slab), vp, vp, i32, vp]
+        L.mgfea_slab_defect_f64_ext.argtypes = [G, ctypes.POINTER(Slab), i32, vp, vp, vp, vp, i32, vp]
         L.mgfea_pattern_keys.argtypes = [vp, i32, i32, i32, vp]
         L.mgfea_widen_f64.argtypes = [vp, vp, i32, i32, i64, i32, i32, vp]
         L.mgfea_restrict_channels.argtypes = [vp, vp, vp, i32, i32, i32, vp]

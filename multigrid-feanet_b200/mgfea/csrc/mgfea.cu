@@ -835,7 +835,6 @@ static int run_stream(const Program &pr, cudaStream_t st) {
     }
     if (R < 2) R = 2;
     R &= ~1;
-    p.R = R;
     p.Nc = (g->N - 1) / 2 + 1;
     if (pr.slab) {
         if (pr.own0 < 0 || pr.own1 > g->N || pr.own0 >= pr.own1 || (pr.own0 & 1) || pr.nrloc < 1) return MGFEA_EINVAL;
@@ -846,7 +845,20 @@ static int run_stream(const Program &pr, cudaStream_t st) {
         p.own1 = pr.own1;
         p.crow0 = pr.crow0;
         p.nrc = pr.nrc;
-        p.nry = (pr.own1 - pr.own0) / R;
+        // the computed range of a slab (owned rows + the redundantly computed deep-halo rows) is not a power of two:
+        // balance the strips instead of leaving the remainder to the last one
+        if (knobs().stream_r <= 0) {
+            const int rows = pr.own1 - pr.own0;
+            const double slots = (double)scr->num_sms * 2 * ST_WARPS;
+            double rt = (double)rows * p.ntx * pr.B / slots;
+            if (rt < 2.0) rt = 2.0;
+            int nry = (int)((double)rows / rt + 0.5);
+            if (nry < 1) nry = 1;
+            R = (rows + nry - 1) / nry;
+            R = (R + 1) & ~1;
+            if (R < 2) R = 2;
+        }
+        p.nry = (pr.own1 - pr.own0 + R - 1) / R;  // the last strip takes what is left (<= R rows)
     } else {
         p.row0 = 0;
         p.nrloc = g->N;
@@ -856,6 +868,7 @@ static int run_stream(const Program &pr, cudaStream_t st) {
         p.nrc = p.Nc;
         p.nry = (g->N - 1) / R;
     }
+    p.R = R;
     if (p.nry < 1) p.nry = 1;
     p.nstrips = p.ntx * p.nry;
     const long long total = (long long)p.nstrips * pr.B;
@@ -1805,7 +1818,7 @@ int mgfea_p2p_exchange(const mgfea_xchg *x, void *stream) {
             return MGFEA_EALIGN;
         total += x->bytes[j];
     }
-    if (x->grid < 1 || x->grid > 64) return MGFEA_EINVAL;
+    if (x->grid < 1 || x->grid > 512) return MGFEA_EINVAL;
     XchgParams p;
     p.x = *x;
     static long long clocks_per_s = 0;
@@ -1827,7 +1840,7 @@ int mgfea_p2p_exchange(const mgfea_xchg *x, void *stream) {
 }
 
 /* ---- fp64 defect correction (mgfea_f64.cuh) -------------------------------------------------------------- */
-static int defect_f64(const mgfea_grid *g, const mgfea_slab *sl, const double *u, const double *f, float *r,
+static int defect_f64(const mgfea_grid *g, const mgfea_slab *sl, int ext, const double *u, const double *f, float *r,
                       double *sumsq, mgfea_ctl *ctl, double *hist, int B, void *stream) {
     if (!g || !u || !f || !r || B < 1 || g->N < 3) return MGFEA_EINVAL;
     if (g->bc_idx) return MGFEA_EUNSUPPORTED;  // the correction equation has the homogeneous default ring
@@ -1855,8 +1868,9 @@ static int defect_f64(const mgfea_grid *g, const mgfea_slab *sl, const double *u
         p.row0 = sl->row0;
         p.own0 = sl->own0;
         p.own1 = sl->own1;
-        p.ylo = sl->own0 - 3 > 0 ? sl->own0 - 3 : 0;
-        p.yhi = sl->own1 + 3 < g->N ? sl->own1 + 3 : g->N;
+        if (ext < 0) return MGFEA_EINVAL;
+        p.ylo = sl->own0 - ext > 0 ? sl->own0 - ext : 0;
+        p.yhi = sl->own1 + ext < g->N ? sl->own1 + ext : g->N;
         if ((p.ylo > 0 && p.ylo - 1 < sl->row0) || (p.yhi < g->N && p.yhi + 1 > sl->row0 + sl->nrows)) return MGFEA_EINVAL;
     } else {
         p.row0 = 0;
@@ -1924,7 +1938,7 @@ int mgfea_widen_f64(const float *src, double *dst, int N, int pitch, int64_t pla
 
 int mgfea_defect_f64(const mgfea_grid *g, const double *u, const double *f, float *r, double *sumsq, mgfea_ctl *ctl,
                      double *hist, int B, void *stream) {
-    return defect_f64(g, nullptr, u, f, r, sumsq, ctl, hist, B, stream);
+    return defect_f64(g, nullptr, 0, u, f, r, sumsq, ctl, hist, B, stream);
 }
 int mgfea_correct_f64(const mgfea_grid *g, double *u, const float *e, const mgfea_ctl *ctl, int B, void *stream) {
     return correct_f64(g, nullptr, u, e, ctl, B, stream);
@@ -1932,7 +1946,12 @@ int mgfea_correct_f64(const mgfea_grid *g, double *u, const float *e, const mgfe
 int mgfea_slab_defect_f64(const mgfea_grid *g, const mgfea_slab *s, const double *u, const double *f, float *r,
                           double *sumsq, int B, void *stream) {
     if (!s) return MGFEA_EINVAL;
-    return defect_f64(g, s, u, f, r, sumsq, nullptr, nullptr, B, stream);
+    return defect_f64(g, s, 3, u, f, r, sumsq, nullptr, nullptr, B, stream);
+}
+int mgfea_slab_defect_f64_ext(const mgfea_grid *g, const mgfea_slab *s, int ext, const double *u, const double *f,
+                              float *r, double *sumsq, int B, void *stream) {
+    if (!s) return MGFEA_EINVAL;
+    return defect_f64(g, s, ext, u, f, r, sumsq, nullptr, nullptr, B, stream);
 }
 int mgfea_slab_correct_f64(const mgfea_grid *g, const mgfea_slab *s, double *u, const float *e, int B, void *stream) {
     if (!s) return MGFEA_EINVAL;
