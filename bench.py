@@ -731,6 +731,7 @@ def run_multi(args):
     rank = int(os.environ["RANK"])
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    numa = mgfea.bind_to_gpu_numa(local)  # pinned host buffers of the e2e leg land on the GPU's own NUMA node
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = size_for(world, args.n_multi)
     N = n + 1
@@ -885,7 +886,7 @@ def run_multi(args):
                                         f"{dof / world / 1e6:.1f} MDOF per GPU; value = median of 5 timed blocks",
                            "n": n, "levels": L, "nu": [1, 1], "batch": 1, "first_replicated_level": ld,
                            "cuda_graph": bool(graphed), "graph_error": graph_err, "exchange": exchange,
-                           "peer_error": peer_err,
+                           "peer_error": peer_err, "numa_node_rank0": numa,
                            "l2": "inputs larger than L2 per GPU at level 0; no explicit flush"},
                 "clocks": clocks,
                 "e2e": {"value": args.e2e_cycles * dof / e2e_dt / 1e9, "unit": "GDOF/s",

@@ -171,6 +171,26 @@ int mgfea_slab_prolong_correct_smooth(const mgfea_grid *g, const mgfea_slab *s, 
                                       int pitch_c, int64_t plane_c, const float *u_in, float *u_out, const float *f,
                                       double *sumsq, int B, void *stream);
 
+/* The same up leg with the halo push FUSED into the kernel (north_star: exchange overlapped with the sweep): the strips
+ * that produce the first / last `rows` owned rows store them also straight into the neighbours' ghost rows (peer-mapped
+ * memory, mgfea_peer_open), and the last such strip raises a flag in the neighbour's mailbox (one increment per launch and
+ * direction).  A following mgfea_p2p_exchange step with wait2 = this rank's own flags makes the next kernel see complete
+ * ghost rows.  up / dn: address of the element (GLOBAL row 0, column 0) of the neighbour's array in this process (may lie
+ * before the mapped block; only rows the neighbour holds are touched), NULL = no neighbour on that side.
+ * ctl (optional, read only): when ctl->done is set the kernel returns without storing, pushing or signalling -- the
+ * solution of a converged slab solve stays what it was (the rule itself is evaluated by the reduce step, mgfea_xchg.ctl). */
+typedef struct mgfea_slab_push {
+    float *up, *dn;
+    uint32_t *flag_up, *flag_dn; /* in the neighbours' mailboxes */
+    uint32_t *ticket;            /* 2 zeroed words in local device memory, left at 0 by every launch */
+    int32_t rows;                /* boundary rows to push per side (the receiver's ghost depth) */
+    int32_t own0, own1;          /* the rank's owned global rows */
+} mgfea_slab_push;
+int mgfea_slab_prolong_correct_smooth_push(const mgfea_grid *g, const mgfea_slab *s, const float *vc,
+                                           const mgfea_slab *sc, int pitch_c, int64_t plane_c, const float *u_in,
+                                           float *u_out, const float *f, double *sumsq, const mgfea_slab_push *push,
+                                           const mgfea_ctl *ctl, int B, void *stream);
+
 /* ---- peer memory: halo exchange over NVLink without a collective library ----------- */
 /* The reference has no distributed code; these entries carry the row-slab exchange of FEANet/distributed.py.  Slab
  * arrays and one mailbox per rank are allocated with mgfea_peer_alloc, exported as 64-byte handles that the host side
@@ -200,7 +220,17 @@ typedef struct mgfea_xchg {
     double *red_dst;
     int32_t nred, red_stride;
     int32_t grid;    /* CTAs of this step, 1..512: MUST be the same on every rank (a flag counts the pushing CTAs) */
-    int32_t pad_;
+    int32_t nwait2;  /* optional second flag set, raised ONCE per launch by the neighbours' fused-push kernels
+                        (mgfea_slab_prolong_correct_smooth_push): wait until each has reached *seq2 + 1, advance *seq2 */
+    const uint32_t *wait2[2];
+    uint32_t *seq2;
+    /* optional device-side stopping rule of the row-slab solve (all ranks reduce the same total in the same order, so
+     * they all take the same decision): when ctl->done is set the whole step is skipped; otherwise, after the reduction,
+     * hist[ctl->cycle] = total (while ctl->cycle < hist_cap), ctl->cycle++, and the mgfea_ctl rule is evaluated */
+    mgfea_ctl *ctl;
+    double *hist;
+    int32_t hist_cap;
+    int32_t pad2_;
 } mgfea_xchg;
 int mgfea_p2p_exchange(const mgfea_xchg *x, void *stream);
 

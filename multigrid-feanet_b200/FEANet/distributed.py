@@ -118,6 +118,9 @@ class SlabExchangePlan:
     No CUDA here, so tests/test_distributed_cpu.py checks every rank's plans against each other."""
     # mailbox (bytes): flags written by the neighbours / by every rank, partial-sum slots, this rank's step counters
     FLAG_UP, FLAG_DOWN, ALL_FLAGS, SLOTS, SEQ_NB, SEQ_ALL, ERR, PARTIAL, TOTAL, MAILBOX = 0, 16, 64, 256, 512, 528, 544, 576, 592, 4096
+    # fused halo push of the finest up leg (mgfea_slab_prolong_correct_smooth_push): flags raised ONCE per launch by the
+    # neighbour's kernel, this rank's expected value, and the two local ticket words
+    FUSE_UP, FUSE_DOWN, SEQ_FUSE, TICKET = 32, 48, 560, 608
     MAX_PEERS = 8
 
     def __init__(self, part, pitch_for):
@@ -234,12 +237,53 @@ class PeerSlabMemory(SlabExchangePlan):
         x.mode = mg.XCHG_PUSH | mg.XCHG_WAIT
         return x
 
-    def step(self, halos, gather=False, reduce=False):
-        """one exchange step (a single kernel on the current stream); every rank must issue the same sequence"""
-        key = (tuple(halos), gather, reduce)
+    def fused_waits(self):
+        """(flag offsets this rank waits on after a fused push of its neighbours, seq offset): the neighbour ABOVE pushes
+        its last rows DOWN into this rank's upper ghost rows and raises FUSE_DOWN here, and vice versa"""
+        rank, world = self.part.rank, self.part.world
+        return ([self.FUSE_DOWN] if rank > 0 else []) + ([self.FUSE_UP] if rank < world - 1 else []), self.SEQ_FUSE
+
+    def push_desc(self, name="u", l=0):
+        """mgfea_slab_push for this rank's finest up leg: where the first / last G owned rows of `name` go"""
+        mg, part = self.mg, self.part
+        rank, world, lev = part.rank, part.world, part.levels[l]
+        rowb = self.pitch[l] * self.esize(name)
+        d = mg.SlabPush()
+        if rank > 0:  # element (global row 0, column 0) of the upper neighbour's array, in this process
+            q = rank - 1
+            d.up = self.bases[q] + self.off[(name, l)] - self.parts[q].levels[l]["row0"] * rowb
+            d.flag_up = self.bases[q] + self.FUSE_UP
+        if rank < world - 1:
+            q = rank + 1
+            d.dn = self.bases[q] + self.off[(name, l)] - self.parts[q].levels[l]["row0"] * rowb
+            d.flag_dn = self.bases[q] + self.FUSE_DOWN
+        d.ticket = self.bases[rank] + self.TICKET
+        d.rows, d.own0, d.own1 = lev["G"], lev["own0"], lev["own1"]
+        return d
+
+    def step(self, halos, gather=False, reduce=False, fused=False, ctl=None):
+        """one exchange step (a single kernel on the current stream); every rank must issue the same sequence.
+        fused: also wait for the flags of the neighbours' fused-push kernels (their finest up leg of this cycle);
+        ctl = (mgfea_ctl address, history address, capacity): device-side stopping rule on the reduced total"""
+        key = (tuple(halos), gather, reduce, fused, ctl)
         x = self._steps.get(key)
         if x is None:
-            x = self._steps[key] = self._build(halos, gather, reduce)
+            if halos or gather or reduce:
+                x = self._build(halos, gather, reduce)
+            else:  # wait-only step
+                x = self.mg.Xchg()
+                x.err, x.grid, x.mode = self.bases[self.part.rank] + self.ERR, 1, 0
+            if fused:
+                waits, seq = self.fused_waits()
+                me = self.bases[self.part.rank]
+                for i, fo in enumerate(waits):
+                    x.wait2[i] = me + fo
+                x.nwait2, x.seq2 = len(waits), me + seq
+            if ctl is not None:
+                x.ctl, x.hist, x.hist_cap = ctl
+            self._steps[key] = x
+        if x.mode == 0 and x.nwait2 == 0:
+            return
         self.mg.check(self.mg.lib().mgfea_p2p_exchange(ctypes.byref(x), self.mg.stream_ptr()))
 
     def check(self):
@@ -315,14 +359,16 @@ class CudaSlabOps:
             f.data_ptr(), fc.data_ptr(), ctypes.byref(sc), fc.shape[2], fc.shape[1] * fc.shape[2], self.rtab.data_ptr(),
             1, 4.0, None, 1, mg.stream_ptr()))
 
-    def up(self, l, vc, u_in, u_out, f, want_norm):
+    def up(self, l, vc, u_in, u_out, f, want_norm, push=None, ctl=None):
+        """push: mgfea.SlabPush -- the kernel also stores its boundary rows into the neighbours' ghost rows (fused halo);
+        ctl: device address of the solve's mgfea_ctl (read only: a converged solve is left untouched)"""
         mg = self.mg
         g = self._grid(l, u_out)
         s, sc = self._slab(l, "up"), self._slab(l + 1)
-        mg.check(mg.lib().mgfea_slab_prolong_correct_smooth(
+        mg.check(mg.lib().mgfea_slab_prolong_correct_smooth_push(
             ctypes.byref(g), ctypes.byref(s), vc.data_ptr(), ctypes.byref(sc), vc.shape[2], vc.shape[1] * vc.shape[2],
-            u_in.data_ptr(), u_out.data_ptr(), f.data_ptr(), self._sumsq.data_ptr() if want_norm else None, 1,
-            mg.stream_ptr()))
+            u_in.data_ptr(), u_out.data_ptr(), f.data_ptr(), self._sumsq.data_ptr() if want_norm else None,
+            ctypes.byref(push) if push is not None else None, ctl, 1, mg.stream_ptr()))
         return self._sumsq if want_norm else None
 
     def coarse_cycle(self):
@@ -359,6 +405,14 @@ class SlabMultigrid:
             self.u = [self.ops.alloc(l) for l in range(ld)]
             self.u_alt = [self.ops.alloc(l) for l in range(ld)]
             self.f = [self.ops.alloc(l) for l in range(ld)]
+        # halo push fused into the finest up leg (MGFEA_FUSED_PUSH=0: separate exchange kernel after it)
+        self.fused_push = self.peer is not None and os.environ.get("MGFEA_FUSED_PUSH", "1") != "0"
+        self._push0 = self.peer.push_desc("u", 0) if self.fused_push else None
+        if self.peer is not None:  # mgfea_ctl + residual history of the device-side stopping rule (free-running by default)
+            self.max_cycles = 256
+            self.ctl = torch.zeros(8, dtype=torch.int32, device=self.ops.dev)
+            self.hist = torch.zeros(self.max_cycles, dtype=torch.float64, device=self.ops.dev)
+            self._ctl_set(0, -1.0, 2 ** 31 - 1)
         self.residuals = []
         self._graph = None
         self._graph64 = None
@@ -532,11 +586,18 @@ class SlabMultigrid:
                      ops.coarse_f() if last else self.f[l + 1])
         peer.step((), gather=True)
         ops.coarse_cycle()
+        fuse = push_u and self.fused_push
+        # device-side stopping rule (Solve): the finest up leg and the final step do nothing once the solve is done, so
+        # cycles enqueued past convergence leave the solution alone; all ranks reduce the same total -> same decision
+        ctl = (self.ctl.data_ptr(), self.hist.data_ptr(), self.hist.shape[0]) if (want_norm and not zero_guess) else None
         for l in range(ld - 1, -1, -1):
             vc = self.u[l + 1] if l + 1 < ld else ops.coarse_u()
-            ops.up(l, vc, self.u_alt[l], self.u[l], self.f[l], want_norm and l == 0)
-        if push_u or want_norm:
-            peer.step((("u", 0),) if push_u else (), reduce=want_norm)
+            ops.up(l, vc, self.u_alt[l], self.u[l], self.f[l], want_norm and l == 0,
+                   push=self._push0 if (fuse and l == 0) else None, ctl=ctl[0] if (ctl and l == 0) else None)
+        if fuse:  # the rows are already on their way (stored by the up leg itself): wait for the neighbours' flags
+            peer.step((), reduce=want_norm, fused=True, ctl=ctl)
+        elif push_u or want_norm:
+            peer.step((("u", 0),) if push_u else (), reduce=want_norm, ctl=ctl)
         return peer.total if want_norm else None
 
     def _sync_ranks(self):
@@ -691,18 +752,43 @@ class SlabMultigrid:
             dist.all_gather(out, chunk, group=self.group)
         return torch.cat([o[:per] for o in out[:-1]] + [out[-1][: per + 1]], dim=0)
 
-    def Solve(self, n_iter=None, EPS=None, max_cycles=200):
-        """Multigrid.Solve semantics (MM_Model_convergence.ipynb cell 3): cycles while (res > EPS or n < n_iter)"""
+    def _ctl_set(self, min_cycles, eps2, max_cycles):
+        c = self.ops.mg.Ctl()
+        c.cycle, c.done, c.min_cycles, c.max_cycles, c.conv_rule, c.eps2 = 0, 0, int(min_cycles), int(max_cycles), 0, eps2
+        self.ctl.copy_(torch.from_numpy(np.frombuffer(bytes(c), dtype=np.int32).copy()))
+
+    def Solve(self, n_iter=None, EPS=None, max_cycles=200, chunk=4):
+        """Multigrid.Solve semantics (MM_Model_convergence.ipynb cell 3): cycles while (res > EPS or n < n_iter).
+        Peer path: the loop condition is evaluated on the device by the all-reduce step (identical on every rank); the host
+        enqueues `chunk` cycles (graph replays once captured) per synchronisation, cycles past convergence are no-ops on the
+        solution.  NCCL fallback: one host synchronisation per cycle like the reference's .item()."""
         if n_iter is None:
             n_iter = 0
         elif EPS is None:
             EPS = math.inf
-        res, hist = 1.0, []
         self.exchange_initial()
-        while (res > EPS or len(hist) < n_iter) and len(hist) < max_cycles:
-            res = float(torch.sqrt(self.cycle().sum()).item())
-            hist.append(res)
-        if self.peer is not None:
-            self.peer.check()
+        if self.peer is None or self.part.ld == 0:
+            res, hist = 1.0, []
+            while (res > EPS or len(hist) < n_iter) and len(hist) < max_cycles:
+                res = float(torch.sqrt(self.cycle().sum()).item())
+                hist.append(res)
+            self.residuals = hist
+            return hist
+        cap = min(max_cycles, self.max_cycles)
+        if n_iter > cap:
+            raise self.ops.mg.MgfeaError(f"n_iter={n_iter} exceeds the history capacity {cap}")
+        self._ctl_set(n_iter, float(EPS) ** 2 if math.isfinite(EPS) else 1.7e308, cap)
+        if n_iter > 0 and not math.isfinite(EPS):
+            chunk = n_iter  # fixed cycle count: one synchronisation at the end
+        done = False
+        while not done:
+            for _ in range(chunk):
+                self.cycle()
+            c = self.ctl.cpu()
+            done = bool(c[1].item())
+        ncyc = int(c[0].item())
+        hist = [float(math.sqrt(v)) for v in self.hist[:ncyc].cpu().numpy()]
+        self._ctl_set(0, -1.0, 2 ** 31 - 1)  # back to free-running for cycle() users
+        self.peer.check()
         self.residuals = hist
         return hist

@@ -694,6 +694,7 @@ struct Program {
     int ignore_keys = 0;
     // row-slab partition (mgfea_slab_*): local arrays hold global rows [row0, row0+nrloc); owned rows [own0, own1)
     int slab = 0, row0 = 0, nrloc = 0, own0 = 0, own1 = 0, crow0 = 0, nrc = 0;
+    const mgfea_slab_push *push = nullptr;  // fused halo push (finest slab up leg)
 };
 
 static inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
@@ -905,19 +906,41 @@ static int run_stream(const Program &pr, cudaStream_t st) {
         p.prolong_seq = (g->N <= 33);
         p.want_norm = (pr.out_mode == OUT_NORM);
     }
+    if (pr.push) {
+        const mgfea_slab_push &ps = *pr.push;
+        if (mode != 1 || !pr.slab || pr.B != 1 || ps.rows < 1 || !ps.ticket || ps.own0 < pr.own0 || ps.own1 > pr.own1 ||
+            ps.own1 - ps.own0 < ps.rows || (ps.up && !ps.flag_up) || (ps.dn && !ps.flag_dn))
+            return MGFEA_EINVAL;
+        p.push_up = ps.up;
+        p.push_dn = ps.dn;
+        p.push_rows = ps.rows;
+        p.pown0 = ps.own0;
+        p.pown1 = ps.own1;
+        p.push_ticket = ps.ticket;
+        p.push_flag_up = ps.flag_up;
+        p.push_flag_dn = ps.flag_dn;
+        for (int ry = 0; ry < p.nry; ++ry) {  // strips that hold boundary rows (the kernel's own test, per strip row)
+            const int y0 = p.own0 + ry * R, y1 = (ry == p.nry - 1) ? p.own1 : y0 + R;
+            if (ps.up && y0 < ps.own0 + ps.rows && y1 > ps.own0) p.npush_up += p.ntx;
+            if (ps.dn && y1 > ps.own1 - ps.rows && y0 < ps.own1) p.npush_dn += p.ntx;
+        }
+    }
     if ((rc = get_scratch((size_t)total, &scr))) return rc;
     p.partials = scr->tile_partials;
     p.counter = scr->counter;
     p.sumsq = pr.sumsq;
     p.hist = pr.hist;
     p.ctl = pr.ctl;
-    const size_t smem = (size_t)ST_WARPS * ST_RING_F4 * 32 * 16 + (keys ? (size_t)ST_WARPS * ST_KDEPTH * 32 * 4 : 0);
+    p.ctl_ro = pr.slab ? 1 : 0;
+    const bool pk = knobs().stream_packed != 0;
+    const int ring_f4 = pk ? st2_ring_f4(mode, keys) : ST_RING_F4;  // the packed down leg keeps a 12-row ring
+    const size_t smem = (size_t)ST_WARPS * ring_f4 * 32 * 16 + (keys ? (size_t)ST_WARPS * ST_KDEPTH * 32 * 4 : 0);
     long long ctas = (total + ST_WARPS - 1) / ST_WARPS;
     const long long maxc = (long long)scr->num_sms * 2;
     const int grid = (int)(ctas < maxc ? ctas : maxc);
     static bool configured = false;
     if (!configured) {
-        const int big = (int)((size_t)ST_WARPS * ST_RING_F4 * 32 * 16 + (size_t)ST_WARPS * ST_KDEPTH * 32 * 4);
+        const int big = (int)((size_t)ST_WARPS * st2_ring_f4(0, false) * 32 * 16 + (size_t)ST_WARPS * ST_KDEPTH * 32 * 4);
         cudaFuncSetAttribute(mg_stream_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         cudaFuncSetAttribute(mg_stream_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         cudaFuncSetAttribute(mg_stream_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
@@ -927,9 +950,10 @@ static int run_stream(const Program &pr, cudaStream_t st) {
         cudaFuncSetAttribute(mg_stream2_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         cudaFuncSetAttribute(mg_stream2_kernel<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         cudaFuncSetAttribute(mg_stream2_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(mg_stream2_kernel<1, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(mg_stream2_kernel<1, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         configured = true;
     }
-    const bool pk = knobs().stream_packed != 0;
     if (keys && !pk) return MGFEA_EUNSUPPORTED;
     if (mode == 0) {
         if (pr.u_in) {
@@ -941,6 +965,10 @@ static int run_stream(const Program &pr, cudaStream_t st) {
             else if (pk) launch_pdl(mg_stream2_kernel<0, true, false>, grid, ST_WARPS * 32, smem, st, p);
             else launch_pdl(mg_stream_kernel<0, true>, grid, ST_WARPS * 32, smem, st, p);
         }
+    } else if (pr.push) {
+        if (!pk) return MGFEA_EUNSUPPORTED;
+        if (keys) launch_pdl(mg_stream2_kernel<1, false, true, true>, grid, ST_WARPS * 32, smem, st, p);
+        else launch_pdl(mg_stream2_kernel<1, false, false, true>, grid, ST_WARPS * 32, smem, st, p);
     } else {
         if (keys) launch_pdl(mg_stream2_kernel<1, false, true>, grid, ST_WARPS * 32, smem, st, p);
         else if (pk) launch_pdl(mg_stream2_kernel<1, false, false>, grid, ST_WARPS * 32, smem, st, p);
@@ -1745,9 +1773,10 @@ int mgfea_slab_smooth_residual_restrict(const mgfea_grid *g, const mgfea_slab *s
     return rc;
 }
 
-int mgfea_slab_prolong_correct_smooth(const mgfea_grid *g, const mgfea_slab *s, const float *vc, const mgfea_slab *sc,
-                                      int pitch_c, int64_t plane_c, const float *u_in, float *u_out, const float *f,
-                                      double *sumsq, int B, void *stream) {
+int mgfea_slab_prolong_correct_smooth_push(const mgfea_grid *g, const mgfea_slab *s, const float *vc,
+                                           const mgfea_slab *sc, int pitch_c, int64_t plane_c, const float *u_in,
+                                           float *u_out, const float *f, double *sumsq, const mgfea_slab_push *push,
+                                           const mgfea_ctl *ctl, int B, void *stream) {
     Program pr;
     int rc = slab_common(pr, g, s, sc);
     if (rc) return rc;
@@ -1762,11 +1791,20 @@ int mgfea_slab_prolong_correct_smooth(const mgfea_grid *g, const mgfea_slab *s, 
     pr.plane_c = plane_c;
     pr.out_mode = sumsq ? OUT_NORM : OUT_NONE;
     pr.sumsq = sumsq;
+    pr.push = push;
+    pr.ctl = const_cast<mgfea_ctl *>(ctl);  // read only on slabs (StreamParams.ctl_ro)
     if ((rc = check_field(u_out, g->pitch, g->plane)) || (rc = check_field(f, g->pitch, g->plane))) return rc;
     trace_stamp((cudaStream_t)stream);
     rc = run_stream(pr, (cudaStream_t)stream);
     trace_stamp((cudaStream_t)stream);
     return rc;
+}
+
+int mgfea_slab_prolong_correct_smooth(const mgfea_grid *g, const mgfea_slab *s, const float *vc, const mgfea_slab *sc,
+                                      int pitch_c, int64_t plane_c, const float *u_in, float *u_out, const float *f,
+                                      double *sumsq, int B, void *stream) {
+    return mgfea_slab_prolong_correct_smooth_push(g, s, vc, sc, pitch_c, plane_c, u_in, u_out, f, sumsq, nullptr, nullptr, B,
+                                                  stream);
 }
 
 /* ---- peer memory + exchange (mgfea_p2p.cuh) -------------------------------------------------------------- */
@@ -1808,8 +1846,10 @@ int mgfea_peer_close(void *ptr) { return ptr ? (int)cudaIpcCloseMemHandle(ptr) :
 
 int mgfea_p2p_exchange(const mgfea_xchg *x, void *stream) {
     if (!x || x->njobs < 0 || x->njobs > MGFEA_XCHG_MAX_JOBS || x->nsignal < 0 || x->nsignal > MGFEA_XCHG_MAX_PEERS ||
-        x->nwait < 0 || x->nwait > MGFEA_XCHG_MAX_PEERS || !(x->mode & (MGFEA_XCHG_PUSH | MGFEA_XCHG_WAIT)))
+        x->nwait < 0 || x->nwait > MGFEA_XCHG_MAX_PEERS || x->nwait2 < 0 || x->nwait2 > 2 ||
+        (!(x->mode & (MGFEA_XCHG_PUSH | MGFEA_XCHG_WAIT)) && x->nwait2 == 0))
         return MGFEA_EINVAL;
+    if (x->nwait2 > 0 && !x->seq2) return MGFEA_EINVAL;
     if ((x->mode & MGFEA_XCHG_WAIT) && !x->seq) return MGFEA_EINVAL;
     unsigned long long total = 0;
     for (int j = 0; j < x->njobs; ++j) {

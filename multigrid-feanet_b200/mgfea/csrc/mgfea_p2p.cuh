@@ -20,6 +20,7 @@
 #include <stdint.h>
 
 #include "../../../include/mgfea.h"
+#include "mgfea_ptx.cuh"
 
 namespace mgfea {
 
@@ -41,6 +42,7 @@ constexpr int XCHG_THREADS = 256;
 
 __global__ void __launch_bounds__(XCHG_THREADS) p2p_exchange_kernel(const XchgParams p) {
     const mgfea_xchg &x = p.x;
+    if (x.ctl != nullptr && ld_volatile_s32(&x.ctl->done) != 0) return;  // converged: every rank skips the step
     if (x.mode & MGFEA_XCHG_PUSH) {
         // ---- copy jobs: 16-byte chunks, grid-stride within each job (coalesced peer stores)
         const long long gtid = (long long)blockIdx.x * XCHG_THREADS + threadIdx.x;
@@ -68,12 +70,12 @@ __global__ void __launch_bounds__(XCHG_THREADS) p2p_exchange_kernel(const XchgPa
             for (int s = 0; s < x.nsignal; ++s) red_relaxed_sys_add_u32(x.signal[s], 1u);
         }
     }
-    if (!(x.mode & MGFEA_XCHG_WAIT) || blockIdx.x != 0 || threadIdx.x != 0) return;
+    if ((!(x.mode & MGFEA_XCHG_WAIT) && x.nwait2 <= 0) || blockIdx.x != 0 || threadIdx.x != 0) return;
     // ---- CTA 0 waits for the ranks that push to this one: each of their `x.grid` CTAs increments the flag once
-    const unsigned int expect = *x.seq + (unsigned int)x.grid;
+    const unsigned int expect = (x.mode & MGFEA_XCHG_WAIT) ? *x.seq + (unsigned int)x.grid : 0u;
     const bool dead = (x.err != nullptr) && (*x.err != 0);  // after one timeout do not wait again (fail fast on the host)
     const long long t0 = clock64();
-    for (int w = 0; w < x.nwait && !dead; ++w) {
+    for (int w = 0; w < ((x.mode & MGFEA_XCHG_WAIT) ? x.nwait : 0) && !dead; ++w) {
         while ((int)(ld_acquire_sys_u32(x.wait[w]) - expect) < 0) {
             if (clock64() - t0 > p.timeout_clocks) {
                 if (x.err) *x.err = 1 + w;
@@ -81,13 +83,38 @@ __global__ void __launch_bounds__(XCHG_THREADS) p2p_exchange_kernel(const XchgPa
             }
         }
     }
-    *x.seq = expect;
+    if (x.mode & MGFEA_XCHG_WAIT) *x.seq = expect;
+    // ---- second flag set: raised once per launch by the neighbours' fused-push kernels
+    if (x.nwait2 > 0) {
+        const unsigned int expect2 = *x.seq2 + 1u;
+        for (int w = 0; w < x.nwait2 && !dead; ++w) {
+            while ((int)(ld_acquire_sys_u32(x.wait2[w]) - expect2) < 0) {
+                if (clock64() - t0 > p.timeout_clocks) {
+                    if (x.err) *x.err = 17 + w;
+                    break;
+                }
+            }
+        }
+        *x.seq2 = expect2;
+    }
     // ---- optional reduction of the slots the peers filled (fixed rank order: identical result on every rank)
     if (x.nred > 0 && x.red_dst != nullptr) {
         double s = 0.0;
         for (int i = 0; i < x.nred; ++i) s += __ldcg(reinterpret_cast<const double *>(
                                                reinterpret_cast<const unsigned char *>(x.red_src) + (size_t)i * x.red_stride));
         *x.red_dst = s;
+        if (x.ctl != nullptr) {  // Multigrid.Solve's loop condition on the all-rank total (same bits on every rank)
+            mgfea_ctl *c = x.ctl;
+            const int cyc = c->cycle;
+            if (x.hist != nullptr && cyc < x.hist_cap) x.hist[cyc] = s;
+            c->cycle = cyc + 1;
+            bool done = false;
+            if (c->eps2 >= 0.0 && cyc + 1 >= c->min_cycles && s <= c->eps2) done = true;
+            if (cyc + 1 >= c->max_cycles) done = true;
+            if (!(s == s) || s > 1.7e308) done = true;
+            if (done) c->done = 1;
+            __threadfence();
+        }
     }
 }
 

@@ -26,6 +26,26 @@ constexpr int ST_TWI = BW - 8; // interior columns per strip (HX = 4)
 constexpr int ST_RING_F4 = 2 * ST_DEPTH + ST_DEPTH / 2;  // float4 units per lane: u ring, f ring, coarse float2 ring
 constexpr int ST_KDEPTH = 3 * ST_DEPTH;                  // key-word ring depth in rows (KEYS kernels only)
 
+// mg_stream2_kernel: ring depth in rows.  The down leg of single-pattern levels keeps 12 rows (two halves of 6, the
+// unroll factor, so slots stay compile-time) and prefetches 9 rows ahead: with 6 rows / 3 ahead only ~49 KB per SM were
+// in flight, less than HBM latency x bandwidth asks for (ncu: long_scoreboard was the top stall).  The up leg (coarse
+// ring) and the keyed kernels (key ring) have no shared memory to spare at 2 CTAs per SM and stay at 6.
+__host__ __device__ constexpr int st2_ring_rows(int mode, bool keys) { return (mode == 0 && !keys) ? 12 : ST_DEPTH; }
+__host__ __device__ constexpr int st2_ring_f4(int mode, bool keys) {  // float4 units per lane
+    return 2 * st2_ring_rows(mode, keys) + (mode == 1 ? ST_DEPTH / 2 : 0);
+}
+__device__ __forceinline__ void st_global_v4_pred(float *p, float a, float b, float c, float d, bool ok) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q st.global.v4.f32 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(p),
+        "f"(a), "f"(b), "f"(c), "f"(d), "r"((int)ok)
+        : "memory");
+}
+__device__ __forceinline__ void st_global_v2_pred(float *p, float a, float b, bool ok) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q st.global.v2.f32 [%0], {%1, %2};\n\t}" ::"l"(p), "f"(a),
+                 "f"(b), "r"((int)ok)
+                 : "memory");
+}
+
 struct StreamParams {
     int N, B, pitch;
     long long plane;
@@ -59,6 +79,16 @@ struct StreamParams {
     double *sumsq;
     double *hist;
     void *ctl;
+    // fused halo push (mg_stream2_kernel<.., PUSH>: the finest up leg of the row-slab cycle).  The strips that produce the
+    // `push_rows` first / last rows of the owned range [pown0, pown1) store them ALSO straight into the neighbours' ghost
+    // rows over NVLink (push_up / push_dn: peer-mapped address of GLOBAL row 0, column 0 of the neighbour's array; NULL:
+    // no neighbour), so the transfer overlaps the sweep.  Every pushing strip takes a ticket when its stores are fenced;
+    // the last of the npush_* strips raises the flag in the neighbour's mailbox once (release, system scope).
+    float *push_up, *push_dn;
+    int push_rows, pown0, pown1, npush_up, npush_dn;
+    unsigned int *push_ticket;  // 2 local words (up, dn), left at 0
+    unsigned int *push_flag_up, *push_flag_dn;
+    int ctl_ro;  // row slabs: `ctl` is only read (done flag); the stopping rule belongs to the all-reduce step
 };
 
 __device__ __forceinline__ double warp_sum_d(double v) {
@@ -584,7 +614,7 @@ __device__ __noinline__ void stencil_rows_keys(const float *tab, const float *in
 // i.e. twice per strip that crosses the inclusion).  Blocks that touch the interface run a general variant whose
 // stencils look every weight up by the source node's key (out of line, so the fast path's code and registers are
 // those of the iso kernel).
-template <int MODE, bool ZERO_INIT, bool KEYS = false>
+template <int MODE, bool ZERO_INIT, bool KEYS = false, bool PUSH = false>
 __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const StreamParams p) {
     extern __shared__ __align__(16) unsigned char st_smem[];
     __shared__ double red[ST_WARPS];
@@ -621,11 +651,14 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
     const int solve_done = (p.ctl != nullptr) ? ld_volatile_s32(&reinterpret_cast<const Ctl *>(p.ctl)->done) : 0;
 
     // ---- per-lane prefetch ring: [slot][lane] float4 for u and for f, float2 for the coarse row (up leg)
-    float4 *ring_u = reinterpret_cast<float4 *>(st_smem) + warp * (ST_RING_F4 * 32);
-    float4 *ring_f = ring_u + ST_DEPTH * 32;
-    float2 *ring_c = reinterpret_cast<float2 *>(ring_f + ST_DEPTH * 32);
-    // key words: 12 rows deep (the residual stage looks back further than the 6-row data ring keeps its rows)
-    unsigned int *ring_k = reinterpret_cast<unsigned int *>(st_smem + ST_WARPS * ST_RING_F4 * 32 * 16) + warp * (ST_KDEPTH * 32);
+    constexpr int RD = st2_ring_rows(MODE, KEYS);  // ring depth (rows): 6, or two halves of 6
+    constexpr int PD = RD - 3;                     // prefetch distance: rows k-2 .. k stay in the ring (f is re-read)
+    constexpr int RF4 = st2_ring_f4(MODE, KEYS);
+    float4 *ring_u = reinterpret_cast<float4 *>(st_smem) + warp * (RF4 * 32);
+    float4 *ring_f = ring_u + RD * 32;
+    float2 *ring_c = reinterpret_cast<float2 *>(ring_f + RD * 32);
+    // key words: 18 rows deep (the residual stage looks back further than the 6-row data ring keeps its rows)
+    unsigned int *ring_k = reinterpret_cast<unsigned int *>(st_smem + ST_WARPS * RF4 * 32 * 16) + warp * (ST_KDEPTH * 32);
 
     const int total = p.nstrips * p.B;
     for (int s = blockIdx.x * ST_WARPS + warp; s < total; s += gridDim.x * ST_WARPS) {
@@ -722,13 +755,21 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
         };
 #pragma unroll
         if (KEYS) fetch_keys(0);  // block 0's keys travel with the first row
-        for (int k = 0; k < ST_DEPTH - 3; ++k) prefetch(std::true_type{}, k);
+        for (int k = 0; k < PD; ++k) prefetch(std::true_type{}, k);  // at k0 = 0 the ring row of streamed row k is k
         if (solve_done) break;
 
         // rotating windows (indices are compile-time after unrolling by 6)
         RP A[3];   // input rows (u0, or corrected u for the up leg): a-2, a-1, a
         RP Bw[3];  // smoothed rows: a-3, a-2, a-1
-        R6 C[3];   // residual rows (down leg): a-4, a-3, a-2
+        float racc0 = 0.f, racc1 = 0.f;  // restriction chains of the lane's two coarse columns (down leg), fed row by row
+        // running store pointers: row a0 - 1 of u_out / coarse row y0/2 - 3 of fc at step 0, advanced as the rows go by
+        float *st_u = uo + (long long)(a0 - 1 - p.row0) * p.pitch;
+        // fused halo push: does this strip produce boundary rows a neighbour needs?
+        const bool s_up = PUSH && p.push_up != nullptr && y0 < p.pown0 + p.push_rows && y1 > p.pown0;
+        const bool s_dn = PUSH && p.push_dn != nullptr && y1 > p.pown1 - p.push_rows && y0 < p.pown1;
+        float *st_pu = PUSH ? p.push_up + (long long)(a0 - 1) * p.pitch + gx : nullptr;
+        float *st_pd = PUSH ? p.push_dn + (long long)(a0 - 1) * p.pitch + gx : nullptr;
+        float *st_c = (MODE == 0) ? fco + (long long)((y0 >> 1) - 3 - p.crow0) * p.pitch_c : nullptr;
         float vt[3] = {0.f, 0.f, 0.f};  // coarse row floor(a/2) at coarse columns cxl, cxl+1, cxl+2 (up leg)
         double part = 0.0;
         if (MODE == 1 && (a0 & 1) && a0 >= 1) {  // the strip starts on an odd row: fetch its upper coarse row directly
@@ -747,15 +788,22 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
             constexpr bool GUARD = decltype(guard_tag)::value;
             constexpr bool EDGE = decltype(edge_tag)::value;
             constexpr bool KEYED = decltype(keyed_tag)::value;
+            // ring row of streamed row k0 + d (d compile-time): a 12-row ring is two halves of 6, `hc` = the half that
+            // holds rows k0 .. k0+5 (k0 is a multiple of 6), so every slot is a run-time half base + a constant
+            const int hc = (RD == 12) ? ((k0 / 6) & 1) * 6 : 0, ho = (RD == 12) ? 6 - hc : 0;
+            auto ring_row = [&](int d) {
+                if (RD == 12) return d < 0 ? ho + 6 + d : (d < 6 ? hc + d : (d < 12 ? ho + d - 6 : hc + d - 12));
+                return (d + 12) % 6;
+            };
 #pragma unroll
             for (int ph = 0; ph < 6; ++ph) {
                 const int k = k0 + ph;
                 if (GUARD && k >= K) break;
                 const int a = a0 + k;
                 if (KEYS && ph == 0) fetch_keys(k0 + 6);  // next block's keys, same commit group as row k0+3
-                prefetch(pf_tag, (ph + ST_DEPTH - 3) % ST_DEPTH);  // rows k-2..k stay in the ring (f is re-read)
-                asm volatile("cp.async.wait_group %0;" ::"n"(ST_DEPTH - 3) : "memory");
-                const int slot = ph * 32 + lane;
+                prefetch(pf_tag, ring_row(ph + PD));  // rows k-2..k stay in the ring (f is re-read)
+                asm volatile("cp.async.wait_group %0;" ::"n"(PD) : "memory");
+                const int slot = ring_row(ph) * 32 + lane;
                 float4 uv = ZERO_INIT ? make_float4(0.f, 0.f, 0.f, 0.f) : ring_u[slot];
                 const bool arow_in = !EDGE || (a >= 1 && a <= N - 2);
                 if (MODE == 1) {
@@ -820,7 +868,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
                     } else {
                         stencil_rows2(kw2, t, m, bq, klo, khi);
                     }
-                    const ulonglong2 ff = *reinterpret_cast<const ulonglong2 *>(&ring_f[((ph + ST_DEPTH - 1) % ST_DEPTH) * 32 + lane]);
+                    const ulonglong2 ff = *reinterpret_cast<const ulonglong2 *>(&ring_f[ring_row(ph - 1) * 32 + lane]);
                     // u + inv * (f - K u) with TWO roundings (reference: separate mul and add).  ptxas contracts
                     // mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (measured: the result then carries the fused rounding,
                     // visible as soon as omega/d is not a power of two), so the sum is written as fma(p, 1, u) = fl(p + u):
@@ -839,7 +887,13 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
                         o3 = om.w;
                     }
                     const bool st_ok = lane_int && (!GUARD || (y >= y0 && y < y1)) && (!EDGE || (cdom & 1u));
-                    if (st_ok) st_global_v4(uo + (long long)(y - p.row0) * p.pitch, make_float4(o0, o1, o2, o3));
+                    st_global_v4_pred(st_u, o0, o1, o2, o3, st_ok);  // predicated: no branch around the store
+                    if (PUSH) {  // the same row into the neighbour's ghost rows (peer store over NVLink)
+                        st_global_v4_pred(st_pu, o0, o1, o2, o3,
+                                          st_ok && s_up && (unsigned)(y - p.pown0) < (unsigned)p.push_rows);
+                        st_global_v4_pred(st_pd, o0, o1, o2, o3,
+                                          st_ok && s_dn && (unsigned)(p.pown1 - 1 - y) < (unsigned)p.push_rows);
+                    }
                     Bw[(ph + 2) % 3] = widen2(o0, o1, o2, o3);
                     // ---- residual row a-2
                     if (!GUARD || k >= 4) {
@@ -856,7 +910,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
                         } else {
                             stencil_rows2(kw2, Bw[(ph + 0) % 3], Bw[(ph + 1) % 3], Bw[(ph + 2) % 3], rlo, rhi);
                         }
-                        const ulonglong2 f2 = *reinterpret_cast<const ulonglong2 *>(&ring_f[((ph + ST_DEPTH - 2) % ST_DEPTH) * 32 + lane]);
+                        const ulonglong2 f2 = *reinterpret_cast<const ulonglong2 *>(&ring_f[ring_row(ph - 2) * 32 + lane]);
                         rlo = sub2(f2.x, rlo);
                         rhi = sub2(f2.y, rhi);
                         float4 r;
@@ -875,48 +929,53 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
                                 part += (double)s4;
                             }
                         } else {
-                            R6 rr;
-                            rr.a[0] = __shfl_up_sync(0xffffffffu, r.w, 1);
-                            rr.a[1] = r.x;
-                            rr.a[2] = r.y;
-                            rr.a[3] = r.z;
-                            rr.a[4] = r.w;
-                            rr.a[5] = 0.0f;
-                            C[(ph + 2) % 3] = rr;
-                            // ---- coarse row (a-3)/2 when a-3 is even (k even since y0 is even)
-                            if ((ph & 1) == 0 && (!GUARD || k >= 6)) {
-                                const int yc = a - 3;
-                                if (!GUARD || (yc >= y0 && yc < y1)) {
-                                    const R6 &ct = C[(ph + 0) % 3], &cm = C[(ph + 1) % 3], &cb = C[(ph + 2) % 3];
-                                    float o2[2];
-#pragma unroll
-                                    for (int h = 0; h < 2; ++h) {
-                                        const int e = 2 * h;
-                                        float sacc = __fmul_rn(rw[0], ct.a[e]);
-                                        sacc = __fmaf_rn(rw[1], ct.a[e + 1], sacc);
-                                        sacc = __fmaf_rn(rw[2], ct.a[e + 2], sacc);
-                                        sacc = __fmaf_rn(rw[3], cm.a[e], sacc);
-                                        sacc = __fmaf_rn(rw[4], cm.a[e + 1], sacc);
-                                        sacc = __fmaf_rn(rw[5], cm.a[e + 2], sacc);
-                                        sacc = __fmaf_rn(rw[6], cb.a[e], sacc);
-                                        sacc = __fmaf_rn(rw[7], cb.a[e + 1], sacc);
-                                        sacc = __fmaf_rn(rw[8], cb.a[e + 2], sacc);
-                                        o2[h] = p.r_has_scale ? __fmul_rn(rscale, sacc) : sacc;
+                            // restriction, fed row by row in the chain's own order (row-major taps): no window of residual
+                            // rows.  Residual row a-2 is the bottom row of the coarse stencil centred on fine row a-3 and
+                            // the top row of the next one when it is odd (k even, y0 is even), the middle row otherwise.
+                            const float rl = __shfl_up_sync(0xffffffffu, r.w, 1);  // column 4l-1
+                            if ((ph & 1) == 0) {
+                                if (!GUARD || k >= 6) {
+                                    const int yc = a - 3;
+                                    float c0 = __fmaf_rn(rw[6], rl, racc0), c1 = __fmaf_rn(rw[6], r.y, racc1);
+                                    c0 = __fmaf_rn(rw[7], r.x, c0);
+                                    c1 = __fmaf_rn(rw[7], r.z, c1);
+                                    c0 = __fmaf_rn(rw[8], r.y, c0);
+                                    c1 = __fmaf_rn(rw[8], r.w, c1);
+                                    if (p.r_has_scale) {
+                                        c0 = __fmul_rn(rscale, c0);
+                                        c1 = __fmul_rn(rscale, c1);
                                     }
-                                    const int I = yc >> 1;
                                     if (EDGE) {
+                                        const int I = yc >> 1;
                                         const bool Iin = (I >= 1 && I <= p.Nc - 2);
-                                        o2[0] = (Iin && cxl >= 1 && cxl <= p.Nc - 2) ? o2[0] : 0.0f;
-                                        o2[1] = (Iin && cxl + 1 >= 1 && cxl + 1 <= p.Nc - 2) ? o2[1] : 0.0f;
+                                        c0 = (Iin && cxl >= 1 && cxl <= p.Nc - 2) ? c0 : 0.0f;
+                                        c1 = (Iin && cxl + 1 >= 1 && cxl + 1 <= p.Nc - 2) ? c1 : 0.0f;
                                     }
-                                    if (fc_ok)
-                                        *reinterpret_cast<float2 *>(fco + (long long)(I - p.crow0) * p.pitch_c) =
-                                            make_float2(o2[0], o2[1]);
+                                    st_global_v2_pred(st_c, c0, c1, fc_ok && (!GUARD || (yc >= y0 && yc < y1)));
                                 }
+                                racc0 = __fmul_rn(rw[0], rl);
+                                racc1 = __fmul_rn(rw[0], r.y);
+                                racc0 = __fmaf_rn(rw[1], r.x, racc0);
+                                racc1 = __fmaf_rn(rw[1], r.z, racc1);
+                                racc0 = __fmaf_rn(rw[2], r.y, racc0);
+                                racc1 = __fmaf_rn(rw[2], r.w, racc1);
+                            } else {
+                                racc0 = __fmaf_rn(rw[3], rl, racc0);
+                                racc1 = __fmaf_rn(rw[3], r.y, racc1);
+                                racc0 = __fmaf_rn(rw[4], r.x, racc0);
+                                racc1 = __fmaf_rn(rw[4], r.z, racc1);
+                                racc0 = __fmaf_rn(rw[5], r.y, racc0);
+                                racc1 = __fmaf_rn(rw[5], r.w, racc1);
                             }
                         }
                     }
                 }
+                st_u += p.pitch;
+                if (PUSH) {
+                    st_pu += p.pitch;
+                    st_pd += p.pitch;
+                }
+                if (MODE == 0 && (ph & 1) == 0) st_c += p.pitch_c;
             }
         };
         using T_ = std::true_type;
@@ -929,13 +988,13 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
             } else {
                 block6(T_{}, F_{}, T_{}, F_{}, 0);
                 // steady state: no pipeline / store-range guards; prefetches unchecked while every prefetched row exists
-                for (k0 = 6; k0 + 5 <= K - 4 && k0 + 5 + ST_DEPTH - 1 < khi; k0 += 6) block6(F_{}, F_{}, F_{}, F_{}, k0);
+                for (k0 = 6; k0 + 5 <= K - 4 && k0 + 5 + PD < khi; k0 += 6) block6(F_{}, F_{}, F_{}, F_{}, k0);
                 for (; k0 + 5 <= K - 4; k0 += 6) block6(F_{}, F_{}, T_{}, F_{}, k0);
                 for (; k0 < K; k0 += 6) block6(T_{}, F_{}, T_{}, F_{}, k0);
             }
         } else {
             int prev_key = -2;  // uniform key of the previous block (-1: mixed, -2: no previous block)
-            asm volatile("cp.async.wait_group %0;" ::"n"(ST_DEPTH - 4) : "memory");  // block 0's keys (first group) are in
+            asm volatile("cp.async.wait_group %0;" ::"n"(PD - 1) : "memory");  // block 0's keys (first group) are in
             for (; k0 < K; k0 += 6) {
                 // one vote per block: do the 6 rows carry ONE pattern over the whole strip?
                 const unsigned int w0 = ring_k[(k0 % ST_KDEPTH) * 32 + lane];
@@ -962,7 +1021,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
                 }
                 if (edge) block6(T_{}, T_{}, T_{}, F_{}, k0);
                 else if (k0 == 0) block6(T_{}, F_{}, T_{}, F_{}, k0);
-                else if (k0 + 5 <= K - 4 && k0 + 5 + ST_DEPTH - 1 < khi) block6(F_{}, F_{}, F_{}, F_{}, k0);
+                else if (k0 + 5 <= K - 4 && k0 + 5 + PD < khi) block6(F_{}, F_{}, F_{}, F_{}, k0);
                 else if (k0 + 5 <= K - 4) block6(F_{}, F_{}, T_{}, F_{}, k0);
                 else block6(T_{}, F_{}, T_{}, F_{}, k0);
             }
@@ -971,6 +1030,24 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
         if (MODE == 1 && p.want_norm) {
             part = warp_sum_d(part);
             if (lane == 0) p.partials[s] = part;
+        }
+        if (PUSH && (s_up || s_dn)) {
+            // all lanes' peer stores precede lane 0's system-scope fence (warp barrier), the fence precedes the ticket;
+            // the strip that takes the last ticket publishes the flag: one remote increment per launch and direction
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_system();
+                if (s_up && atomicAdd(p.push_ticket, 1u) == (unsigned)p.npush_up - 1u) {
+                    p.push_ticket[0] = 0u;
+                    __threadfence_system();
+                    asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(p.push_flag_up) : "memory");
+                }
+                if (s_dn && atomicAdd(p.push_ticket + 1, 1u) == (unsigned)p.npush_dn - 1u) {
+                    p.push_ticket[1] = 0u;
+                    __threadfence_system();
+                    asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(p.push_flag_dn) : "memory");
+                }
+            }
         }
     }
 
@@ -989,7 +1066,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
         __syncthreads();
         if (lastflag) {
             __threadfence();
-            Ctl *ctl = reinterpret_cast<Ctl *>(p.ctl);
+            Ctl *ctl = p.ctl_ro ? nullptr : reinterpret_cast<Ctl *>(p.ctl);
             double tot = 0.0, mx = 0.0;
             for (int b = 0; b < p.B; ++b) {
                 double v = 0.0;

@@ -34,9 +34,10 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(mgfea.LevelBufs) == 24
     # sizes printed by gcc for include/mgfea.h (sizeof(mgfea_cycle_cfg), sizeof(mgfea_xchg), sizeof(mgfea_slab))
     assert ctypes.sizeof(mgfea.CycleCfg) == 104
-    assert ctypes.sizeof(mgfea.Xchg) == 576
-    assert ctypes.sizeof(mgfea.Slab) == 16
+    assert ctypes.sizeof(mgfea.Xchg) == 624
+    assert ctypes.sizeof(mgfea.Slab) == 16 and ctypes.sizeof(mgfea.SlabPush) == 56
     assert mgfea.CycleCfg.zero_guess.offset == 96 and mgfea.Xchg.grid.offset == 568 and mgfea.Xchg.seq.offset == 528
+    assert mgfea.Xchg.nwait2.offset == 572 and mgfea.Xchg.seq2.offset == 592
 
 
 def test_no_cpu_fallback():
