@@ -188,7 +188,16 @@ def bind_to_gpu_numa(device_index: Optional[int] = None) -> Optional[int]:
     try:
         dev = torch.cuda.current_device() if device_index is None else device_index
         pr = torch.cuda.get_device_properties(dev)
-        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        if hasattr(pr, "pci_bus_id"):
+            bdf = f"{getattr(pr, 'pci_domain_id', 0):04x}:{pr.pci_bus_id:02x}:{getattr(pr, 'pci_device_id', 0):02x}.0"
+        else:  # older torch: ask the driver (match by UUID, CUDA_VISIBLE_DEVICES may have renumbered the devices)
+            rows = subprocess.run(["nvidia-smi", "--query-gpu=uuid,pci.bus_id", "--format=csv,noheader"],
+                                  capture_output=True, text=True, timeout=10).stdout.strip().splitlines()
+            table = [tuple(c.strip() for c in r.split(",")) for r in rows]
+            uuid = str(getattr(pr, "uuid", ""))
+            hit = [b for u, b in table if uuid and uuid.replace("GPU-", "") in u] or [table[dev][1]]
+            dom, rest = hit[0].lower().split(":", 1)
+            bdf = f"{dom[-4:]}:{rest}"
         node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
         if node < 0:
             return None

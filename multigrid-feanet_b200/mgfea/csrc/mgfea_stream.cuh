@@ -767,8 +767,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
         // fused halo push: does this strip produce boundary rows a neighbour needs?
         const bool s_up = PUSH && p.push_up != nullptr && y0 < p.pown0 + p.push_rows && y1 > p.pown0;
         const bool s_dn = PUSH && p.push_dn != nullptr && y1 > p.pown1 - p.push_rows && y0 < p.pown1;
-        float *st_pu = PUSH ? p.push_up + (long long)(a0 - 1) * p.pitch + gx : nullptr;
-        float *st_pd = PUSH ? p.push_dn + (long long)(a0 - 1) * p.pitch + gx : nullptr;
+        const bool s_push = s_up || s_dn;
         float *st_c = (MODE == 0) ? fco + (long long)((y0 >> 1) - 3 - p.crow0) * p.pitch_c : nullptr;
         float vt[3] = {0.f, 0.f, 0.f};  // coarse row floor(a/2) at coarse columns cxl, cxl+1, cxl+2 (up leg)
         double part = 0.0;
@@ -888,10 +887,12 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
                     }
                     const bool st_ok = lane_int && (!GUARD || (y >= y0 && y < y1)) && (!EDGE || (cdom & 1u));
                     st_global_v4_pred(st_u, o0, o1, o2, o3, st_ok);  // predicated: no branch around the store
-                    if (PUSH) {  // the same row into the neighbour's ghost rows (peer store over NVLink)
-                        st_global_v4_pred(st_pu, o0, o1, o2, o3,
-                                          st_ok && s_up && (unsigned)(y - p.pown0) < (unsigned)p.push_rows);
-                        st_global_v4_pred(st_pd, o0, o1, o2, o3,
+                    if (PUSH && s_push) {  // warp-uniform: only the strips that hold boundary rows come here
+                        // the same row into the neighbour's ghost rows (peer stores over NVLink)
+                        float *pp = p.push_up + (long long)y * p.pitch + gx;
+                        st_global_v4_pred(pp, o0, o1, o2, o3, st_ok && s_up && (unsigned)(y - p.pown0) < (unsigned)p.push_rows);
+                        pp = p.push_dn + (long long)y * p.pitch + gx;
+                        st_global_v4_pred(pp, o0, o1, o2, o3,
                                           st_ok && s_dn && (unsigned)(p.pown1 - 1 - y) < (unsigned)p.push_rows);
                     }
                     Bw[(ph + 2) % 3] = widen2(o0, o1, o2, o3);
@@ -971,10 +972,6 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
                     }
                 }
                 st_u += p.pitch;
-                if (PUSH) {
-                    st_pu += p.pitch;
-                    st_pd += p.pitch;
-                }
                 if (MODE == 0 && (ph & 1) == 0) st_c += p.pitch_c;
             }
         };
@@ -1031,7 +1028,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
             part = warp_sum_d(part);
             if (lane == 0) p.partials[s] = part;
         }
-        if (PUSH && (s_up || s_dn)) {
+        if (PUSH && s_push) {
             // all lanes' peer stores precede lane 0's system-scope fence (warp barrier), the fence precedes the ticket;
             // the strip that takes the last ticket publishes the flag: one remote increment per launch and direction
             __syncwarp();
