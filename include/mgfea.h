@@ -257,6 +257,26 @@ int mgfea_slab_correct_f64(const mgfea_grid *g, const mgfea_slab *s, double *u, 
 int mgfea_slab_defect_f64_ext(const mgfea_grid *g, const mgfea_slab *s, int ext, const double *u, const double *f,
                               float *r, double *sumsq, int B, void *stream);
 
+/* ---- general per-element conductivity ---------------------------------------------------- */
+/* The reference's data model carries one conductivity per ELEMENT (`material`, Data/dataset.py:71-104) but its operator
+ * only knows the 16 two-phase patterns (FEANet/mesh.py:103-117).  These entries are that operator with the pattern lookup
+ * replaced by the element values: a = [N][pitch] fp32 (16-byte aligned), element (r,c) at a[r*pitch + c] for r,c < N-1,
+ * zero elsewhere; shared by the batch.  Weights are `generate_kernel`'s fp32 expressions of the source nodes, so on a
+ * two-phase map the result equals the pattern operator bit for bit on every interior node.  Default Dirichlet ring. */
+int mgfea_elem_stiffness_apply(const float *a, const float *u, float *out, int N, int pitch, int64_t plane, int B,
+                               void *stream);                       /* KNet.forward, FEANet/model.py:22-30 */
+int mgfea_elem_residual(const float *a, const float *u, const float *f, float *r, int N, int pitch, int64_t plane, int B,
+                        void *stream);                              /* f - Knet(u) */
+/* one sweep of JacobiBlock.jacobi_convolution (FEANet/jacobi.py:39-47), omega/d = fl(fl(1/d) * omega) per node with d
+ * the centre entry of the node's own kernel (jacobi.py:31-37); u_in may not alias u_out */
+int mgfea_elem_smooth(const float *a, const float *u_in, float *u_out, const float *f, float omega, int N, int pitch,
+                      int64_t plane, int B, void *stream);
+/* conductivity of the next coarser level: mean of the four child elements (fp32, row-major order).  Our convention: the
+ * reference rediscretises its inclusion on every level instead (FEANet/multigrid.py:19-29) */
+int mgfea_elem_coarsen(const float *a, float *ac, int N, int pitch, int pitch_c, void *stream);
+/* sumsq[b] = sum over interior nodes of r^2 in fp64, deterministic (Solve's residual norm for the element operator) */
+int mgfea_sumsq_interior(const float *r, double *sumsq, int N, int pitch, int64_t plane, int B, void *stream);
+
 /* ---- whole V-cycle ----------------------------------------------------------------------------------- */
 typedef struct mgfea_cycle_cfg {
     int32_t nu1, nu2;      /* pre / post sweeps (coarsest level gets nu1 + nu2) */

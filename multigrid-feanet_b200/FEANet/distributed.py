@@ -405,8 +405,12 @@ class SlabMultigrid:
             self.u = [self.ops.alloc(l) for l in range(ld)]
             self.u_alt = [self.ops.alloc(l) for l in range(ld)]
             self.f = [self.ops.alloc(l) for l in range(ld)]
-        # halo push fused into the finest up leg (MGFEA_FUSED_PUSH=0: separate exchange kernel after it)
-        self.fused_push = self.peer is not None and os.environ.get("MGFEA_FUSED_PUSH", "1") != "0"
+        # halo push fused into the finest up leg (the kernel's boundary strips store straight into the neighbours' ghost
+        # rows).  Measured at 8 GPUs / 16385^2 (profiles/r02_slab_trace_n8_fused.log vs _nofuse.log): the exchange step
+        # after the leg shrinks from 30 to 11-17 us, but the leg itself grows from 92-95 to 116-118 us -- the strips that
+        # issue the peer stores wait for NVLink, and a one-wave streaming kernel is as slow as its slowest strip -- so the
+        # separate exchange kernel stays the default; MGFEA_FUSED_PUSH=1 selects the fused path (parity-tested both ways)
+        self.fused_push = self.peer is not None and os.environ.get("MGFEA_FUSED_PUSH", "0") == "1"
         self._push0 = self.peer.push_desc("u", 0) if self.fused_push else None
         if self.peer is not None:  # mgfea_ctl + residual history of the device-side stopping rule (free-running by default)
             self.max_cycles = 256

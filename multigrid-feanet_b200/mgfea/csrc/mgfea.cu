@@ -16,6 +16,7 @@
 #include "mgfea_stream.cuh"
 #include "mgfea_p2p.cuh"
 #include "mgfea_mid.cuh"
+#include "mgfea_elem.cuh"
 #include "mgfea_f64.cuh"
 
 #ifndef MGFEA_MINBLOCKS
@@ -1996,6 +1997,73 @@ int mgfea_slab_defect_f64_ext(const mgfea_grid *g, const mgfea_slab *s, int ext,
 int mgfea_slab_correct_f64(const mgfea_grid *g, const mgfea_slab *s, double *u, const float *e, int B, void *stream) {
     if (!s) return MGFEA_EINVAL;
     return correct_f64(g, s, u, e, nullptr, B, stream);
+}
+
+/* ---- general per-element conductivity (mgfea_elem.cuh) ---------------------------------------------------- */
+static int elem_launch(int mode, const float *a, const float *u, const float *f, float *out, float omega, int N, int pitch,
+                       int64_t plane, int B, void *stream) {
+    if (!a || !u || !out || (mode != 0 && !f) || N < 3 || pitch < N || B < 1 || B > 65535) return MGFEA_EINVAL;
+    if ((pitch & 3) || (plane & 3) ||
+        ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(out)) & 15u))
+        return MGFEA_EALIGN;
+    if (u == out) return MGFEA_EINVAL;
+    ElemParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = N;
+    p.B = B;
+    p.pitch = pitch;
+    p.plane = plane;
+    p.a = a;
+    p.u = u;
+    p.f = f;
+    p.out = out;
+    p.omega = omega;
+    // FEANet/mesh.py:28-31: Ke = -1/6 * [[-4,1,2,1],[1,-4,1,2],[2,1,-4,1],[1,2,1,-4]] evaluated in fp32
+    static const float base[16] = {-4.f, 1.f, 2.f, 1.f, 1.f, -4.f, 1.f, 2.f, 2.f, 1.f, -4.f, 1.f, 1.f, 2.f, 1.f, -4.f};
+    const float sixth = -1.0f / 6.0f;
+    for (int i = 0; i < 16; ++i) p.ke[i] = sixth * base[i];
+    const dim3 grid((unsigned)((pitch / 4 + 31) / 32), (unsigned)((N + 7) / 8), (unsigned)B), block(32, 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    trace_stamp(st);
+    if (mode == 0) mg_elem_kernel<0><<<grid, block, 0, st>>>(p);
+    else if (mode == 1) mg_elem_kernel<1><<<grid, block, 0, st>>>(p);
+    else mg_elem_kernel<2><<<grid, block, 0, st>>>(p);
+    trace_stamp(st);
+    g_launches.fetch_add(1);
+    return (int)cudaGetLastError();
+}
+int mgfea_elem_stiffness_apply(const float *a, const float *u, float *out, int N, int pitch, int64_t plane, int B,
+                               void *stream) {
+    return elem_launch(0, a, u, nullptr, out, 0.0f, N, pitch, plane, B, stream);
+}
+int mgfea_elem_residual(const float *a, const float *u, const float *f, float *r, int N, int pitch, int64_t plane, int B,
+                        void *stream) {
+    return elem_launch(1, a, u, f, r, 0.0f, N, pitch, plane, B, stream);
+}
+int mgfea_elem_smooth(const float *a, const float *u_in, float *u_out, const float *f, float omega, int N, int pitch,
+                      int64_t plane, int B, void *stream) {
+    return elem_launch(2, a, u_in, f, u_out, omega, N, pitch, plane, B, stream);
+}
+int mgfea_elem_coarsen(const float *a, float *ac, int N, int pitch, int pitch_c, void *stream) {
+    if (!a || !ac || N < 5 || ((N - 1) & 1) || pitch < N || pitch_c < (N - 1) / 2 + 1) return MGFEA_EINVAL;
+    const int rows_c = (N - 1) / 2 + 1;
+    const dim3 grid((unsigned)((pitch_c + 255) / 256), (unsigned)rows_c);
+    elem_coarsen_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, ac, N - 1, pitch, pitch_c, rows_c);
+    g_launches.fetch_add(1);
+    return (int)cudaGetLastError();
+}
+int mgfea_sumsq_interior(const float *r, double *sumsq, int N, int pitch, int64_t plane, int B, void *stream) {
+    if (!r || !sumsq || N < 3 || pitch < N || B < 1 || B > 65535) return MGFEA_EINVAL;
+    int nb = N - 2 < 256 ? N - 2 : 256;
+    if (nb < 1) nb = 1;
+    DeviceScratch *scr = nullptr;
+    int rc = get_scratch((size_t)nb * B, &scr);
+    if (rc) return rc;
+    interior_sumsq_kernel<<<dim3((unsigned)nb, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(r, N, pitch, plane,
+                                                                                             scr->tile_partials,
+                                                                                             scr->counter + 4, sumsq);
+    g_launches.fetch_add(1);
+    return (int)cudaGetLastError();
 }
 
 int mgfea_vcycle(const mgfea_grid *grids, const mgfea_level_bufs *bufs, int nlevels, const mgfea_cycle_cfg *cfg,

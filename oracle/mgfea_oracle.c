@@ -327,3 +327,101 @@ void orc_pattern_keys(uint8_t *keys, int N, int shape) {
             keys[IDX(i, j)] = (uint8_t)k;
         }
 }
+
+/* ---------------------------------------------------------------------------------------------------------
+ * General per-ELEMENT conductivity (data model: `material`, one value per element, Data/dataset.py:71-104).
+ * The reference only ships the 16-pattern two-phase operator; this is that operator with the pattern lookup replaced by
+ * the element values themselves: the 3x3 kernel of a node is FEANet/mesh.py:103-117 `generate_kernel` evaluated (same
+ * fp32 expression order) with a[pattern[i]] replaced by the conductivity of the node's element e_{i+1}, and K u keeps the
+ * reference's form (FEANet/model.py:22-30): the weight of tap d is taken from the kernel of the SOURCE node i+d.  Each
+ * tap's weight only involves the elements shared by the source node and the output node, i.e. the output node's own four
+ * elements NW = E(i-1,j-1), NE = E(i-1,j), SW = E(i,j-1), SE = E(i,j) (E(r,c) = element with nodes (r,c) .. (r+1,c+1)):
+ * on a two-phase map this is BIT-IDENTICAL to the pattern operator on every interior node (tests pin that).  Elements
+ * outside the plate count as conductivity 0 (only the never-used boundary-ring outputs see them).
+ * a: [n][n] fp32, n = N - 1, shared by the batch.  ke: the 4x4 element matrix of FEANet/mesh.py:28-31 in fp32.
+ */
+static inline float elem_at(const float *a, int n, int r, int c) {
+    return (r < 0 || c < 0 || r >= n || c >= n) ? 0.0f : a[(size_t)r * n + c];
+}
+static inline void elem_weights(const float *a, const float *ke, int N, int i, int j, float *w) {
+    const int n = N - 1;
+    const float nw = elem_at(a, n, i - 1, j - 1), ne = elem_at(a, n, i - 1, j), sw = elem_at(a, n, i, j - 1),
+                se = elem_at(a, n, i, j);
+#define KE(r, c) ke[4 * (r) + (c)]
+    w[0] = nw * KE(1, 3);
+    w[1] = ne * KE(1, 2) + nw * KE(0, 3);
+    w[2] = ne * KE(0, 2);
+    w[3] = nw * KE(2, 3) + sw * KE(1, 0);
+    w[4] = ((sw * KE(0, 0) + se * KE(1, 1)) + ne * KE(2, 2)) + nw * KE(3, 3);
+    w[5] = ne * KE(3, 2) + se * KE(0, 1);
+    w[6] = sw * KE(2, 0);
+    w[7] = se * KE(2, 1) + sw * KE(3, 0);
+    w[8] = se * KE(3, 1);
+#undef KE
+}
+static inline float stencil_elem(const float *u, const float *a, const float *ke, int N, int i, int j) {
+    float w[9], acc = 0.0f;
+    elem_weights(a, ke, N, i, j, w);
+    for (int di = -1; di <= 1; ++di)
+        for (int dj = -1; dj <= 1; ++dj) {
+            int ii = i + di, jj = j + dj;
+            if (ii < 0 || ii >= N || jj < 0 || jj >= N) continue;
+            acc = fmaf(w[3 * (di + 1) + (dj + 1)], u[IDX(ii, jj)], acc);
+        }
+    return acc;
+}
+void orc_elem_stiffness_apply(const float *u, float *out, const float *a, const float *ke, int N, int B) {
+    for (int b = 0; b < B; ++b)
+#pragma omp parallel for schedule(static)
+        for (int i = 0; i < N; ++i)
+            for (int j = 0; j < N; ++j) out[(size_t)b * N * N + IDX(i, j)] = stencil_elem(u + (size_t)b * N * N, a, ke, N, i, j);
+}
+void orc_elem_residual(const float *u, const float *f, float *r, const float *a, const float *ke, int N, int B) {
+    for (int b = 0; b < B; ++b)
+#pragma omp parallel for schedule(static)
+        for (int i = 0; i < N; ++i)
+            for (int j = 0; j < N; ++j)
+                r[(size_t)b * N * N + IDX(i, j)] =
+                    f[(size_t)b * N * N + IDX(i, j)] - stencil_elem(u + (size_t)b * N * N, a, ke, N, i, j);
+}
+/* the node's Jacobi diagonal = centre entry of its own kernel (FEANet/jacobi.py:31-37) */
+void orc_elem_diag(float *d, const float *a, const float *ke, int N) {
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) {
+            float w[9];
+            elem_weights(a, ke, N, i, j, w);
+            d[IDX(i, j)] = w[4];
+        }
+}
+/* nsweeps of weighted Jacobi, FEANet/jacobi.py:39-47 with omega/d = fl(fl(1/d) * omega) per node (Tensor.__rtruediv__) */
+void orc_elem_jacobi(const float *u_in, float *u_out, const float *f, const float *a, const float *ke, float omega,
+                     const float *idx, const float *bval, size_t bc_bstride, int N, int B, int nsweeps) {
+    size_t M = (size_t)N * N;
+    float *tmp = (float *)malloc(M * sizeof(float));
+    float *cur = (float *)malloc(M * sizeof(float));
+    for (int b = 0; b < B; ++b) {
+        const float *ib = idx ? idx + b * bc_bstride : NULL;
+        const float *vb = bval ? bval + b * bc_bstride : NULL;
+        const float *fb = f + b * M;
+        memcpy(cur, u_in + b * M, M * sizeof(float));
+        for (int s = 0; s < nsweeps; ++s) {
+            for (int i = 0; i < N; ++i)
+                for (int j = 0; j < N; ++j) tmp[IDX(i, j)] = bc_apply(cur[IDX(i, j)], ib, vb, N, i, j);
+#pragma omp parallel for schedule(static)
+            for (int i = 0; i < N; ++i)
+                for (int j = 0; j < N; ++j) {
+                    float w[9];
+                    elem_weights(a, ke, N, i, j, w);
+                    float ku = stencil_elem(tmp, a, ke, N, i, j);
+                    float res = fb[IDX(i, j)] - ku;
+                    float inv = (1.0f / w[4]) * omega;
+                    float t = inv * res;
+                    float un = t + tmp[IDX(i, j)];
+                    cur[IDX(i, j)] = bc_apply(un, ib, vb, N, i, j);
+                }
+        }
+        memcpy(u_out + b * M, cur, M * sizeof(float));
+    }
+    free(tmp);
+    free(cur);
+}

@@ -190,6 +190,97 @@ def prolong_table(vc, u, keys_c, ptab, scale=None):
     return u
 
 
+# ----------------------------------------------------------------------------------------------
+# general per-element conductivity: see the block comment in mgfea_oracle.c
+# ----------------------------------------------------------------------------------------------
+KE = (-1.0 / 6.0 * np.array([[-4., 1., 2., 1.], [1., -4., 1., 2.], [2., 1., -4., 1.], [1., 2., 1., -4.]],
+                            dtype=np.float32)).astype(np.float32)  # FEANet/mesh.py:28-31, same expression
+
+
+def _elem(a, N):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    assert a.shape == (N - 1, N - 1), (a.shape, N)
+    return a
+
+
+def elem_stiffness_apply(u, a):
+    u = _as3(u)
+    B, N, _ = u.shape
+    out = np.empty_like(u)
+    lib().orc_elem_stiffness_apply(_p(u, _f32p), _p(out, _f32p), _p(_elem(a, N), _f32p), _p(KE, _f32p), N, B)
+    return out
+
+
+def elem_residual(u, f, a):
+    u, f = _as3(u), _as3(f)
+    B, N, _ = u.shape
+    out = np.empty_like(u)
+    lib().orc_elem_residual(_p(u, _f32p), _p(f, _f32p), _p(out, _f32p), _p(_elem(a, N), _f32p), _p(KE, _f32p), N, B)
+    return out
+
+
+def elem_diag(a):
+    N = a.shape[0] + 1
+    d = np.empty((N, N), np.float32)
+    lib().orc_elem_diag(_p(d, _f32p), _p(_elem(a, N), _f32p), _p(KE, _f32p), N)
+    return d
+
+
+def elem_jacobi(u, f, a, omega=2.0 / 3.0, idx=None, bval=None, nsweeps=1):
+    u, f = _as3(u), _as3(f)
+    B, N, _ = u.shape
+    idx, bval, bs = _bc(idx, bval, B, N)
+    out = np.empty_like(u)
+    lib().orc_elem_jacobi(_p(u, _f32p), _p(out, _f32p), _p(f, _f32p), _p(_elem(a, N), _f32p), _p(KE, _f32p),
+                          ctypes.c_float(float(np.float32(omega))), _p(idx, _f32p), _p(bval, _f32p), ctypes.c_size_t(bs),
+                          N, B, nsweeps)
+    return out
+
+
+def coarsen_elements(a):
+    """conductivity of a coarse element = mean of its four children, summed in fp32 in row-major order (our convention:
+    the reference rediscretises its two-phase inclusion on every level instead, FEANet/multigrid.py:19-29)"""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    s = (a[0::2, 0::2] + a[0::2, 1::2]).astype(np.float32)
+    s = (s + a[1::2, 0::2]).astype(np.float32)
+    s = (s + a[1::2, 1::2]).astype(np.float32)
+    return (s * np.float32(0.25)).astype(np.float32)
+
+
+def phase_map(N, shape=0):
+    """element phases (n x n, 0/1) of the reference's centred inclusion, from the bit-pinned pattern keys: the SE
+    element of node (i, j) is e4 of its pattern"""
+    keys = pattern_keys(N, shape)
+    e4 = np.array([REF_PATTERNS[k][3] for k in range(16)], dtype=np.int64)
+    ph = e4[keys[:-1, :-1].astype(np.int64)]
+    ph[0, :] = 0  # nodes on the ring carry key 0 whatever their elements are; the inclusion never touches the edge
+    ph[:, 0] = 0
+    return ph
+
+
+def elem_vcycle(a_levels, u, f, nu1=1, nu2=1, omega=2.0 / 3.0):
+    """V(nu1,nu2) with the per-element operator on every level (a_levels[l]: (n_l x n_l)), full weighting x4 and bilinear
+    prolongation (MM_Model_convergence.ipynb cell 3 skeleton)"""
+    L = len(a_levels)
+    us, fs = [None] * L, [None] * L
+    us[0], fs[0] = _as3(u), _as3(f)
+    B = us[0].shape[0]
+    for l in range(L):
+        N = a_levels[l].shape[0] + 1
+        if l > 0:
+            us[l] = np.zeros((B, N, N), np.float32)
+        if nu1 > 0:
+            us[l] = elem_jacobi(us[l], fs[l], a_levels[l], omega, nsweeps=nu1)
+        if l < L - 1:
+            fs[l + 1] = restrict(elem_residual(us[l], fs[l], a_levels[l]), None, FW16, 4.0)
+    for l in range(L - 1, -1, -1):
+        if l < L - 1:
+            us[l] = prolong_bilinear(us[l + 1], us[l])
+        if nu2 > 0:
+            us[l] = elem_jacobi(us[l], fs[l], a_levels[l], omega, nsweeps=nu2)
+    return us[0]
+
+
 def sumsq_interior(r):
     r = _as3(r)
     B, N, _ = r.shape

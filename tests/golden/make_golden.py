@@ -521,8 +521,32 @@ def gen_bands():
     print("bands.json written")
 
 
+def gen_testpoisson():
+    """Data/TestPoisson/poisson2d_33x33.h5 (Data/dataset.py:71-104 TestPoissonDataSet): per-ELEMENT `material` (32 x 32),
+    Dirichlet masks, source, FEM solution -- first 3 samples, as the fixture of the per-element operator"""
+    p = os.path.join(H.REF, "Data/TestPoisson/poisson2d_33x33.h5")
+    b33 = H.read_h5_contiguous(p, (10, 33, 33))  # file order: dirich_idx, dirich_value, neumann_idx, neumann_value, source, solution
+    b32 = H.read_h5_contiguous(p, (10, 32, 32))
+    assert len(b33) == 6 and len(b32) == 1
+    out = {"material": b32[0][:3].copy(), "dirich_idx": b33[0][:3].copy(), "dirich_value": b33[1][:3].copy(),
+           "neumann_idx": b33[2][:3].copy(), "neumann_value": b33[3][:3].copy(), "source": b33[4][:3].copy(),
+           "solution": b33[5][:3].copy()}
+    # known answer with the reference's own modules in fp64 (MM_poisson.ipynb cell 2: KNet(MeshSquare).double())
+    H.load_reference()
+    from FEANet.mesh import MeshSquare
+    from FEANet.model import FNet, KNet
+
+    knet, fnet = KNet(MeshSquare(2, 33)).double(), FNet(2.0 / 32).double()
+    knet.global_pattern = knet.global_pattern.double()
+    with torch.no_grad():
+        r = fnet(torch.from_numpy(out["source"])[:, None]) - knet(torch.from_numpy(out["solution"])[:, None])
+    out["ref_residual_interior_max"] = np.array([float(r[:, :, 1:-1, 1:-1].abs().max())])
+    print("testpoisson: max interior |fnet(source) - K solution| (fp64, reference modules) =", out["ref_residual_interior_max"])
+    np.savez_compressed(os.path.join(OUT, "testpoisson.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["mesh", "ops", "solve", "bands"]
+    which = sys.argv[1:] or ["mesh", "ops", "solve", "bands", "testpoisson"]
     if "mesh" in which:
         gen_mesh()
     if "ops" in which:
@@ -531,3 +555,5 @@ if __name__ == "__main__":
         gen_solve()
     if "bands" in which:
         gen_bands()
+    if "testpoisson" in which:
+        gen_testpoisson()

@@ -868,3 +868,129 @@ def test_device_pattern_keys(O, shape):
         mesh = MeshCenterInterface(2, [1, 20], n + 1, shape=shape)
         assert np.array_equal(k[:, :n + 1], mesh.pattern_keys)
         assert np.array_equal(host(mesh.device_pattern_keys()), k)
+
+
+# ------------------------------------------------------------------------------------------ per-element conductivity (8f.2)
+TP = np.load(os.path.join(G, "testpoisson.npz"))
+
+
+def _hetero(n, seed, lo=0.05, hi=50.0):
+    rs = np.random.RandomState(seed)
+    return np.exp(rs.uniform(np.log(lo), np.log(hi), (n, n))).astype(np.float32)
+
+
+@pytest.mark.parametrize("N,B", [(9, 2), (33, 1), (65, 3), (257, 1), (1025, 1)])
+def test_element_operator_bit_exact(O, N, B):
+    """ElementKNet.forward / residual / ElementJacobiBlock.jacobi_convolution (mgfea_elem_*) against the oracle on a random
+    heterogeneous conductivity field (1000x contrast), bit-exact on ALL nodes"""
+    from FEANet.element import ElementJacobiBlock, ElementKNet
+
+    a = _hetero(N - 1, 40 + N)
+    u, f = rand_fields(N, B, 900 + N)
+    knet = ElementKNet(torch.from_numpy(a))
+    exact(host(knet(cuda(u)))[:, 0], O.elem_stiffness_apply(u, a), "ElementKNet.forward")
+    exact(host(knet.residual(cuda(u), cuda(f)))[:, 0], O.elem_residual(u, f, a), "residual")
+    jac = ElementJacobiBlock(knet)
+    for k in (1, 3):
+        exact(host(jac.jacobi_convolution(cuda(u), cuda(f), n_iter=k))[:, 0], O.elem_jacobi(u, f, a, nsweeps=k),
+              f"element jacobi x{k}")
+    exact(host(jac.reset_boundary(cuda(u)))[:, 0], O.reset_boundary(u), "reset_boundary")
+    exact(jac.d_mat.numpy()[0, 0], O.elem_diag(a), "d_mat")
+    out_cpu = knet(torch.from_numpy(u))  # host in -> host out
+    assert not out_cpu.is_cuda
+    exact(out_cpu.numpy()[:, 0], O.elem_stiffness_apply(u, a), "forward(host)")
+
+
+@pytest.mark.parametrize("tag", ["c20", "s100"])
+@pytest.mark.parametrize("N", [17, 65, 513])
+def test_element_equals_pattern_kernels_on_two_phase_map(O, tag, N):
+    """fed with the two-phase conductivity map, the per-element kernels equal the 16-pattern kernels bit for bit: K u on the
+    interior (the ring of K u is never used by any caller), Jacobi sweeps on all nodes"""
+    from FEANet.element import ElementJacobiBlock, ElementKNet
+    from FEANet.jacobi import JacobiBlock
+    from FEANet.model import KNet
+
+    shape, prop = (0, [1, 20]) if tag == "c20" else (1, [1, 100])
+    mesh = make_mesh(tag, N)
+    a = np.array(prop, np.float32)[O.phase_map(N, shape)]
+    u, f = rand_fields(N, 2, 950 + N)
+    kp, ke = KNet(mesh), ElementKNet(torch.from_numpy(a))
+    exact(host(ke(cuda(u)))[:, 0, 1:-1, 1:-1], host(kp(cuda(u)))[:, 0, 1:-1, 1:-1], "K u interior")
+    jp, je = JacobiBlock(kp, mesh, 2 / 3., None, None), ElementJacobiBlock(ke)
+    exact(host(je.jacobi_convolution(cuda(u), cuda(f), n_iter=2))[:, 0],
+          host(jp.jacobi_convolution(cuda(u), cuda(f), n_iter=2))[:, 0], "jacobi x2")
+
+
+@pytest.mark.parametrize("n,B", [(16, 2), (64, 1), (256, 1)])
+def test_element_vcycle_bit_exact(O, n, B):
+    """ElementMultigrid (per-element operator on every level, 4-child mean coarsening on the device, full weighting x 4,
+    bilinear prolongation) against the oracle: coarse maps, u after every cycle and the residual norms"""
+    from FEANet.element import ElementMultigrid
+
+    a = _hetero(n, 7 + n, 0.2, 5.0)
+    mg = ElementMultigrid(n, torch.from_numpy(a))
+    levels = [a]
+    for l in range(1, mg.L):
+        levels.append(O.coarsen_elements(levels[-1]))
+        nl = n // 2 ** l
+        exact(host(mg.grids[l].Knet.material), levels[l], f"coarsened conductivity level {l}")
+        assert (host(mg.grids[l].Knet.a.store)[0, nl:, :] == 0).all() and (host(mg.grids[l].Knet.a.store)[0, :, nl:] == 0).all()
+    u0, f = rand_fields(n + 1, B, 970 + n)
+    f *= 0.01
+    mg.initial_v = torch.from_numpy(u0)
+    mg.grids[0].f = torch.from_numpy(f)
+    res = mg.Solve([1, 1], n_iter=3)
+    uo = u0[:, 0]
+    ref = []
+    for _ in range(3):
+        uo = O.elem_vcycle(levels, uo, f)
+        ref.append(float(np.sqrt(O.sumsq_interior(O.elem_residual(uo, f, a)).sum())))
+    exact(mg.grids[0].v.numpy()[:, 0], uo, "element V-cycle x3")
+    assert np.allclose(res, ref, rtol=1e-12)
+    res2 = mg.Solve([2, 1], n_iter=2)  # other sweep counts through the same kernels
+    uo = u0[:, 0]
+    for _ in range(2):
+        uo = O.elem_vcycle(levels, uo, f, nu1=2, nu2=1)
+    exact(mg.grids[0].v.numpy()[:, 0], uo, "element V(2,1) x2")
+    assert len(res2) == 2
+
+
+def test_element_two_phase_cycle_equals_pattern_cycle(O):
+    """config 5 in its general form: the same V-cycle through the per-element kernels (per-level two-phase maps) and through
+    the keyed pattern kernels (VCycleEngine, Jacobi, full weighting + bilinear) -- bit-identical iterates"""
+    from FEANet.drivers import _InterfaceSingleGrid
+    from FEANet.element import ElementMultigrid
+    from FEANet.solver import VCycleEngine
+
+    n, prop = 128, (1.0, 20.0)
+    L = int(np.log2(n))
+    maps = [torch.from_numpy(np.array(prop, np.float32)[O.phase_map(n // 2 ** l + 1, 0)]) for l in range(L)]
+    mg = ElementMultigrid(n, maps)
+    grids = [_InterfaceSingleGrid(2, n // 2 ** l, prop=prop, shape=0) for l in range(L)]
+    eng = VCycleEngine([g.jac for g in grids], B=1, smoother="jac")
+    u0, f = rand_fields(n + 1, 1, 990)
+    f *= 0.01
+    eng.set_u(torch.from_numpy(u0))
+    eng.set_f(torch.from_numpy(f))
+    mg.initial_v, mg.grids[0].f = torch.from_numpy(u0), torch.from_numpy(f)
+    res = mg.Solve([1, 1], n_iter=3)
+    ref = eng.run(n_iter=3)
+    exact(mg.grids[0].v.numpy()[:, 0], host(eng.solution)[:, 0], "element cycle vs pattern cycle")
+    assert np.allclose(res, ref, rtol=2e-7)
+
+
+def test_element_testpoisson_fixture(O):
+    """`material` (one value per element) of Data/TestPoisson/poisson2d_33x33.h5 through ElementKNet: K solution = fnet(source)
+    on the interior, and a solve from the dataset's source converges to the dataset's solution (zero Dirichlet samples)"""
+    from FEANet.element import ElementKNet
+    from FEANet.model import FNet
+
+    N = 33
+    for k in range(3):
+        a = TP["material"][k].astype(np.float32)
+        u, src = TP["solution"][k].astype(np.float32), TP["source"][k].astype(np.float32)
+        knet = ElementKNet(torch.from_numpy(a))
+        f = FNet(2.0 / (N - 1))(cuda(src[None, None]))
+        exact(host(knet.residual(cuda(u[None, None]), f))[:, 0], O.elem_residual(u, host(f)[:, 0], a), "residual of the FEM solution")
+        r = host(knet.residual(cuda(u[None, None]), f))[0, 0, 1:-1, 1:-1]
+        assert np.abs(r).max() <= 2e-5 * np.abs(host(knet(cuda(u[None, None])))).max()

@@ -290,3 +290,67 @@ def test_feanet_torch_matches_reference_histories():
     lvl = FT.Level(N, ktab, keys)
     u = torch.from_numpy(OPS[f"u_{N}"])
     assert np.array_equal(lvl.K(u).numpy()[:, 0], O.stiffness_apply(OPS[f"u_{N}"], keys, ktab))
+
+
+# ---------------------------------------------------------------- per-element conductivity
+TP = np.load(os.path.join(G, "testpoisson.npz"))
+
+
+@pytest.mark.parametrize("shape,prop", [(0, [1, 20]), (1, [1, 100]), (0, [3, 0.5])])
+@pytest.mark.parametrize("N", [9, 17, 33, 65])
+def test_element_operator_equals_pattern_operator(shape, prop, N):
+    """the per-element operator fed with the two-phase conductivity map reproduces the reference's 16-pattern operator
+    (pinned above against the reference) bit for bit: K u on the interior, Jacobi sweeps everywhere"""
+    keys, tab = O.pattern_keys(N, shape), O.kernel_table(prop, 16).reshape(16, 9)
+    a = np.array(prop, np.float32)[O.phase_map(N, shape)]
+    # the phase map is consistent with all four pattern positions of the reference's keys, not only e4
+    pat = np.array([O.REF_PATTERNS[k] for k in range(16)])[keys.astype(np.int64)]  # (N, N, 4): e1..e4
+    ph = np.zeros((N + 1, N + 1), np.int64)
+    ph[1:N, 1:N] = O.phase_map(N, shape)
+    i, j = np.meshgrid(np.arange(1, N - 1), np.arange(1, N - 1), indexing="ij")
+    assert np.array_equal(pat[i, j, 0], ph[i, j + 1]) and np.array_equal(pat[i, j, 1], ph[i, j])
+    assert np.array_equal(pat[i, j, 2], ph[i + 1, j]) and np.array_equal(pat[i, j, 3], ph[i + 1, j + 1])
+    rs = np.random.RandomState(N)
+    u = rs.standard_normal((2, N, N)).astype(np.float32)
+    f = rs.standard_normal((2, N, N)).astype(np.float32)
+    k1, k2 = O.stiffness_apply(u, keys, tab), O.elem_stiffness_apply(u, a)
+    assert np.array_equal(k1[:, 1:-1, 1:-1], k2[:, 1:-1, 1:-1])
+    j1 = O.jacobi(u, f, keys, tab, O.inv_diag(2 / 3., tab[:, 4]), nsweeps=3)
+    assert np.array_equal(j1, O.elem_jacobi(u, f, a, nsweeps=3))
+    d = O.elem_diag(a)
+    assert np.array_equal(d[1:-1, 1:-1], tab[:, 4][keys][1:-1, 1:-1])
+
+
+def test_element_operator_testpoisson_fixture():
+    """Data/TestPoisson/poisson2d_33x33.h5: `material` is one value per element (32 x 32); with it the per-element
+    operator satisfies K solution = fnet(source) on the interior like the reference's own modules do in fp64
+    (8.8e-10, recorded in the fixture), here in fp32"""
+    N = 33
+    for k in range(3):
+        a = TP["material"][k].astype(np.float32)
+        assert a.shape == (N - 1, N - 1)
+        u, src = TP["solution"][k].astype(np.float32), TP["source"][k].astype(np.float32)
+        f = O.conv3x3(src, O.load_vector_weights(2.0 / (N - 1)))
+        r = O.elem_residual(u, f, a)[0, 1:-1, 1:-1]
+        assert np.abs(r).max() <= 2e-5 * np.abs(O.elem_stiffness_apply(u, a)).max()
+        iso = O.stiffness_apply(u, None, O.kernel_table([1.0], 1).reshape(1, 9))
+        if (a == 1).all():  # this file's material is homogeneous: the element operator IS the MeshSquare operator
+            assert np.array_equal(O.elem_stiffness_apply(u, a)[:, 1:-1, 1:-1], iso[:, 1:-1, 1:-1])
+    assert float(TP["ref_residual_interior_max"][0]) < 1e-8
+
+
+def test_element_vcycle_converges_and_coarsening():
+    n = 64
+    rs = np.random.RandomState(4)
+    a = np.exp(rs.uniform(np.log(0.2), np.log(5.0), (n, n))).astype(np.float32)
+    levels = [a]
+    for _ in range(int(np.log2(n)) - 1):
+        levels.append(O.coarsen_elements(levels[-1]))
+    assert levels[-1].shape == (2, 2) and np.allclose(levels[1][0, 0], a[:2, :2].mean(), rtol=1e-6)
+    f = 0.01 * rs.standard_normal((1, n + 1, n + 1)).astype(np.float32)
+    u = np.zeros((1, n + 1, n + 1), np.float32)
+    res = [float(np.sqrt(O.sumsq_interior(O.elem_residual(u, f, a))[0]))]
+    for _ in range(8):
+        u = O.elem_vcycle(levels, u, f)
+        res.append(float(np.sqrt(O.sumsq_interior(O.elem_residual(u, f, a))[0])))
+    assert res[-1] < 1e-2 * res[0] and all(res[i + 1] < res[i] for i in range(8))  # q ~ 0.46 at 25x random contrast
