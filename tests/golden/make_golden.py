@@ -545,8 +545,33 @@ def gen_testpoisson():
     np.savez_compressed(os.path.join(OUT, "testpoisson.npz"), **out)
 
 
+def gen_h5manifest():
+    """names / shapes / dtypes / data hashes of the reference's HDF5 files as read by the product's own reader
+    (FEANet/h5lite.py), cross-checked against the byte-scanning reader this harness has used since round 1"""
+    import hashlib
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(HERE)), "multigrid-feanet_b200"))
+    for k in [k for k in sys.modules if k == "FEANet" or k.startswith("FEANet.")]:
+        del sys.modules[k]
+    if H.REF in sys.path:
+        sys.path.remove(H.REF)
+    from FEANet.h5lite import H5File
+
+    man = {}
+    for rel, shp in (("Data/IsoPoisson/poisson2d_33x33.h5", (100, 33, 33)), ("Data/TestPoisson/poisson2d_33x33.h5", None),
+                     ("Data/RHS/poisson2d_rhs_17x17.h5", None)):
+        f = H5File(os.path.join(H.REF, rel))
+        man[rel] = {k: dict(shape=list(f.shape(k)), dtype=str(f[k].dtype),
+                            sha256=hashlib.sha256(f[k].tobytes()).hexdigest()) for k in f.keys()}
+        if shp:
+            blocks = H.read_h5_contiguous(os.path.join(H.REF, rel), shp)
+            assert all(np.array_equal(f[k], b) for k, b in zip(f.order, blocks))
+    json.dump(man, open(os.path.join(OUT, "h5_manifest.json"), "w"), indent=1)
+    print("h5_manifest.json", {k: list(v) for k, v in man.items()})
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["mesh", "ops", "solve", "bands", "testpoisson"]
+    which = sys.argv[1:] or ["mesh", "ops", "solve", "bands", "testpoisson", "h5"]
     if "mesh" in which:
         gen_mesh()
     if "ops" in which:
@@ -557,3 +582,5 @@ if __name__ == "__main__":
         gen_bands()
     if "testpoisson" in which:
         gen_testpoisson()
+    if "h5" in which:
+        gen_h5manifest()

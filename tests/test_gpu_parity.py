@@ -994,3 +994,41 @@ def test_element_testpoisson_fixture(O):
         exact(host(knet.residual(cuda(u[None, None]), f))[:, 0], O.elem_residual(u, host(f)[:, 0], a), "residual of the FEM solution")
         r = host(knet.residual(cuda(u[None, None]), f))[0, 0, 1:-1, 1:-1]
         assert np.abs(r).max() <= 2e-5 * np.abs(host(knet(cuda(u[None, None])))).max()
+
+
+# ------------------------------------------------------------------------------------------ dataset ingestion (8f.3)
+@pytest.mark.parametrize("mode", ["jac", "hjac"])
+def test_dataset_batch_through_mgtest_multigrid(tmp_path, mode):
+    """IsoPoissonDataSet -> DeviceBatchLoader -> MGTestMultiGrid.forward / solve with PER-SAMPLE Dirichlet masks (the
+    mg_test notebook's data path, cells 7 and 21-22, batched): every sample of the batch reproduces the reference's
+    single-sample run (residual history within its recorded fp64 band, same cycle count, same solution)"""
+    from FEANet.dataset import DeviceBatchLoader, IsoPoissonDataSet
+    from FEANet.drivers import MGTestMultiGrid
+    from FEANet.h5lite import write_h5
+
+    path = write_h5(str(tmp_path / "iso.h5"), {"boundary_index": ARR["iso33_bidx"].astype(np.float64),
+                                               "boundary_value": ARR["iso33_bval"].astype(np.float64),
+                                               "rhs": ARR["iso33_rhs64"], "u": ARR["iso33_u64"]})
+    loader = DeviceBatchLoader(IsoPoissonDataSet(path), batch_size=3)
+    assert len(loader) == 1
+    u_fem, f, bval, bidx = next(iter(loader))
+    assert all(t.is_cuda and tuple(t.shape) == (3, 1, 33, 33) and t.dtype == torch.float32 for t in (u_fem, f, bval, bidx))
+    n = 32
+    P = torch.tensor([[1, 2, 1], [2, 4, 2], [1, 2, 1]], dtype=torch.float32) / 4.0
+    mg = MGTestMultiGrid(n=n, hnet=_hnet(), P=P, mode=mode)
+    u = torch.zeros(3, 1, n + 1, n + 1, device="cuda")
+    mg(u, f, bidx, bval, 1)
+    ncyc = max(len(HIST[f"mgtest_{mode}_s{k}"]["res"]) for k in range(3))
+    res = [mg.residual_norms(mg.u0)[:, 0].cpu().numpy()]
+    for _ in range(ncyc - 1):
+        u = mg.Step(u, mg.f)
+        res.append(mg.residual_norms(u)[:, 0].cpu().numpy())
+    res = np.array(res)  # (cycle, sample)
+    for k in range(3):
+        h = HIST[f"mgtest_{mode}_s{k}"]
+        m = len(h["res"])
+        check_band(res[:m, k], h["res"], BANDS[f"mgtest_{mode}_s{k}"]["res64"], f"batched mgtest {mode} sample {k}")
+        assert res[m - 1, k] <= 5e-5 < res[m - 2, k]  # the notebook's stopping rule fires at the same cycle
+    # the FEM solution of the dataset is what the solver converges to
+    sol, hist = mg.solve(torch.zeros(3, 1, n + 1, n + 1, device="cuda"), EPS=5e-5)
+    assert (sol - u_fem).abs().max().item() <= 2e-5 * u_fem.abs().max().item()
