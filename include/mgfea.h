@@ -257,6 +257,13 @@ int mgfea_slab_correct_f64(const mgfea_grid *g, const mgfea_slab *s, double *u, 
 int mgfea_slab_defect_f64_ext(const mgfea_grid *g, const mgfea_slab *s, int ext, const double *u, const double *f,
                               float *r, double *sumsq, int B, void *stream);
 
+/* JacobiBlockPBC.jacobi_convolution (FEANet/jacobi.py:50-97): one weighted-Jacobi sweep with PERIODIC boundary conditions,
+ * single pattern.  u (N x N nodes, node N-1 == node 0); f_pad = the (N+2) x (N+2) load vector the reference makes its
+ * caller pad (its Knet runs on the circularly padded (N+2)^2 array), padded-pitch layout of its own; w9 = the 3x3 kernel,
+ * invd = omega/d (both in device memory).  out = invd * (f_pad[1:-1,1:-1] - K_periodic u) + reset_boundary(u). */
+int mgfea_smooth_pbc(const float *w9, const float *invd, const float *u_in, float *u_out, const float *f_pad, int N,
+                     int pitch, int64_t plane, int pitch_f, int64_t plane_f, int B, void *stream);
+
 /* ---- general per-element conductivity ---------------------------------------------------- */
 /* The reference's data model carries one conductivity per ELEMENT (`material`, Data/dataset.py:71-104) but its operator
  * only knows the 16 two-phase patterns (FEANet/mesh.py:103-117).  These entries are that operator with the pattern lookup

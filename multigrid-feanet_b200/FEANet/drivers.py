@@ -160,7 +160,8 @@ class Multigrid():
 
     # ---- cycles
     def _run_cycle(self, l, v, f):
-        eng = self._engine(self.v1, self.v2, first_level=l, B=as_field(v).B if torch.is_tensor(v) else None)
+        B = (v.shape[0] if v.dim() == 4 else 1) if torch.is_tensor(v) else None  # no H2D copy just to learn the batch size
+        eng = self._engine(self.v1, self.v2, first_level=l, B=B)
         eng.refresh()
         eng.set_u(v)
         eng.set_f(f)
@@ -318,7 +319,9 @@ class HJacIterator(nn.Module):
         return torch.randn_like(x)
 
     def TrainSingleEpoch(self, *_a, **_k):
-        raise NotImplementedError("training the learned iterator (backward pass) is outside the solve() path")
+        raise mgfea.MgfeaError("HJacIterator.Train / TrainSingleEpoch: not supported -- the CUDA smoother has no backward "
+                               "pass (SURVEY 8f.4).  Train the HNet with the reference and load its state_dict here "
+                               "(HNet.load_state_dict); HRelax / MGTestMultiGrid then use the weights as they are.")
 
     Train = TrainSingleEpoch
 

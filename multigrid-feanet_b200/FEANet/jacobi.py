@@ -141,6 +141,75 @@ class JacobiBlock():
         `n_iter` accepts the older API that FEANet/multigrid.py:46 still calls."""
         uf, ff = as_field(initial_u), as_field(forcing_term)
         if ff.B != uf.B:
-            raise mgfea.MgfeaError("u and f batch sizes differ")
+            if ff.B == 1:  # the reference broadcasts a single right-hand side over the batch (elementwise ops)
+                ff = as_field(torch.as_tensor(forcing_term).reshape(1, 1, ff.N, ff.N).expand(uf.B, -1, -1, -1).contiguous())
+            else:
+                raise mgfea.MgfeaError("u and f batch sizes differ")
         out = self.smooth_fields(uf, ff, n_iter)
         return _like_input(initial_u, out)
+
+
+class JacobiBlockPBC():
+    """ Define all the methods necessary for a CNN-based Jacobi iteration (periodic boundary condition); currently only
+        for homogeneous problems (reference: FEANet/jacobi.py:50-97)
+
+        Knet: neural network model for stiffness terms
+    """
+
+    def __init__(self, mesh, Knet=None, omega=2. / 3.):
+        self.nnode_edge = mesh.nnode_edge
+        self.omega = omega
+        self.mesh = mesh
+        self.Knet = Knet
+        if len(mesh.kernel_dict) != 1:
+            raise mgfea.MgfeaError("JacobiBlockPBC is for homogeneous (single-pattern) meshes, like the reference's")
+        self._w9 = np.asarray(mesh.kernel_dict[0], dtype=np.float32).reshape(9)
+        self._invd = ((np.float32(1.0) / self._w9[4:5]).astype(np.float32) * np.float32(omega)).astype(np.float32)
+        self._dev = None
+        self._wtab = mgfea.DeviceTable()
+        self.d_mat = torch.zeros((1, 1, self.nnode_edge, self.nnode_edge))
+        self.compute_diagonal_matrix()
+
+    def compute_diagonal_matrix(self):
+        """ Compute diagonal matrix for Jacobi iteration """
+        for pkey in self.mesh.kernel_dict:
+            K_weights = torch.from_numpy(np.asarray(self.mesh.kernel_dict[pkey], dtype=np.float32))
+            global_pattern = torch.from_numpy(np.asarray(self.mesh.global_pattern_center[pkey])).reshape(
+                self.nnode_edge, self.nnode_edge)
+            self.d_mat[0, 0, :, :] += global_pattern * K_weights[1, 1]
+
+    def pbc_boundary(self, u):
+        """ Expand the domain boundary to be periodic.  Input size [n+1, n+1]; output size [n+3, n+3] """
+        u_central = u[:, :, :-1, :-1]
+        return torch.nn.functional.pad(u_central, (1, 2, 1, 2), 'circular')
+
+    def reset_boundary(self, u):
+        """ Copy the boundary values to be the same.  Input size [n+1, n+1]; output size [n+1, n+1] """
+        u_central = u[:, :, :-1, :-1]
+        return torch.nn.functional.pad(u_central, (0, 1, 0, 1), 'circular')
+
+    def _weights(self):
+        """live kernel: the Knet's net2 weight when a Knet was given (user edits / load_state_dict), else the mesh table"""
+        if self.Knet is not None and hasattr(self.Knet, "net2"):
+            return self._wtab.get(self.Knet.net2.weight.reshape(-1, 9)[:1])
+        return self._wtab.get(torch.from_numpy(self._w9.reshape(1, 9)))
+
+    def jacobi_convolution(self, u, forcing_term, n_iter=1):
+        """ Jacobi method iteration step defined as a convolution:
+        u_new = omega/d_mat*residual + u, where residual = f - K*u on the periodically padded field.
+        As in the reference the forcing_term must come padded to [n+3, n+3] (its Knet runs on the padded array). """
+        uf = as_field(u)
+        N = uf.N
+        ff = as_field(forcing_term)
+        if ff.N != N + 2 or ff.B != uf.B:
+            raise mgfea.MgfeaError(f"forcing_term must be (B,1,{N + 2},{N + 2}): the reference's caller pads it")
+        if self._dev is None:
+            self._dev = torch.from_numpy(self._invd).to(uf.store.device)
+        w = self._weights()
+        cur = uf
+        for _ in range(n_iter):
+            out = Field(uf.B, N, uf.store.device)
+            check(lib().mgfea_smooth_pbc(w.data_ptr(), self._dev.data_ptr(), cur.ptr, out.ptr, ff.ptr, N, uf.pitch,
+                                         uf.plane, ff.pitch, ff.plane, uf.B, stream_ptr()))
+            cur = out
+        return _like_input(u, cur)

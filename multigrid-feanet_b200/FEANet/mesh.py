@@ -127,6 +127,11 @@ class MeshCenterInterface(_StructuredQuad):
     (reference: FEANet/mesh.py:4-120).  ``pattern_keys`` is the uint8 (N,N) key map the kernels consume."""
 
     def __init__(self, size=2, prop=[1, 20], nnode_edge=65, shape=0, outfile=None):
+        if size != 2:
+            # the closed-form inclusion test (and mgfea_pattern_keys) is the reference's centroid test for the plate
+            # [-1, 1]^2 with radius / half-width 0.5; the reference derives centroids from `size`, so any other size
+            # would silently give a DIFFERENT inclusion than the reference does
+            raise ValueError("MeshCenterInterface: only size=2 (every driver of the reference) is supported")
         self.size, self.nnode_edge, self.shape = size, nnode_edge, shape
         self.a = np.array(prop, dtype=np.float32)
         self.ref_pattern_dict = {k: list(v) for k, v in _REF_PATTERNS.items()}

@@ -149,8 +149,19 @@ class MultiGrid(nn.Module):
                                         xf.B, stream_ptr()))
         return torch.sqrt(ss)
 
+    def _inference_only(self, what):
+        """The reference trains R / P / w by back-propagating through this cycle (multigrid.py:98-100,145-157); the fused
+        sm_100a cycle has no backward pass (not built).  Returning a silently detached tensor would make a
+        training loop fail far away ("does not require grad") or, worse, train nothing -- fail HERE instead."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise mgfea.MgfeaError(
+                f"MultiGrid.{what}: inference only -- the CUDA V-cycle is not differentiable, but conv / deconv / w "
+                "require grad and autograd is recording.  Wrap the call in torch.no_grad() (or "
+                "requires_grad_(False)) to solve; training the inter-grid operators is not supported by this package.")
+
     def qm(self, x):
         "Compute the convergence factor after m iterations"
+        self._inference_only("qm")
         r1, r0 = self._res_norms(x, self.f), self._res_norms(self.v_m0, self.f)
         return torch.mean(torch.pow(r1 / r0, 1.0 / (self.m - self.m0 + 1))).to(torch.float32).cpu()
 
@@ -163,6 +174,7 @@ class MultiGrid(nn.Module):
 
     def forward(self, F):
         '''Input is RHS field F'''
+        self._inference_only("forward")
         self.f = self.grids[0].fnet(F)
         self.v = torch.zeros(tuple(F.shape), requires_grad=False, dtype=torch.float32)
         self.random_sampling(self.v)
@@ -174,7 +186,8 @@ class MultiGrid(nn.Module):
         return self.iterate(U, self.f)
 
     def iterate(self, x, f):
-        '''one V(1,1) cycle; x is the current solution on the finest grid'''
+        '''one V(1,1) cycle; x is the current solution on the finest grid.  The result is DETACHED from autograd (see
+        _inference_only): iterate is the solve() building block, forward / qm are the training entry points and refuse'''
         eng = self._engine(x.shape[0])
         eng.refresh()
         eng.set_u(x)

@@ -194,6 +194,11 @@ class VCycleEngine:
         if n_iter > cap:
             raise mgfea.MgfeaError(f"n_iter={n_iter} exceeds the history capacity {cap}")
         eps2 = float(EPS) * float(EPS) if math.isfinite(EPS) else 1.7e308
+        if n_iter == 0 and EPS >= 1.0:
+            # the reference's loop starts from `res = 1` (MM_Model_convergence.ipynb cell 3 Solve): with EPS >= 1 and no
+            # n_iter it runs no cycle at all
+            self.last_hist = np.zeros((0, self.B))
+            return []
         self.refresh()
         self._ctl_reset(n_iter, eps2, cap)
         if use_graph:
@@ -211,9 +216,21 @@ class VCycleEngine:
         ncyc = int(self._ctl_host[0].item())
         h = self.hist[:ncyc].cpu().numpy()
         self.last_hist = h
+        self._warn_if_capped(h, ncyc, cap, n_iter, eps2)
         if self.conv_rule == mgfea.CONV_SUM:
             return [float(math.sqrt(v)) for v in h.sum(axis=1)]
         return [np.sqrt(row) for row in h]
+
+    def _warn_if_capped(self, h, ncyc, cap, n_iter, eps2):
+        """the reference loops until converged; this engine stops at the history capacity -- say so instead of returning a
+        history that silently did not reach EPS"""
+        if ncyc >= cap and ncyc > n_iter and eps2 < 1.7e308 and ncyc > 0:
+            last = h[-1].sum() if self.conv_rule == mgfea.CONV_SUM else h[-1].max()
+            if not last <= eps2:
+                import warnings
+
+                warnings.warn(f"mgfea: stopped after {ncyc} cycles (max_cycles) with residual {math.sqrt(last):.3e} > EPS "
+                              f"{math.sqrt(eps2):.3e}; raise max_cycles (reference: loops until converged)", RuntimeWarning)
 
     # -- fp64 defect correction around the fp32 cycle (SURVEY 8f.1; the reference's remedy is `.double()`) ----------
     def _mixed_setup(self):

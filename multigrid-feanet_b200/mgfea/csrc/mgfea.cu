@@ -2052,6 +2052,17 @@ int mgfea_elem_coarsen(const float *a, float *ac, int N, int pitch, int pitch_c,
     g_launches.fetch_add(1);
     return (int)cudaGetLastError();
 }
+int mgfea_smooth_pbc(const float *w9, const float *invd, const float *u_in, float *u_out, const float *f_pad, int N,
+                     int pitch, int64_t plane, int pitch_f, int64_t plane_f, int B, void *stream) {
+    if (!w9 || !invd || !u_in || !u_out || !f_pad || u_in == u_out || N < 4 || pitch < N || pitch_f < N + 2 || B < 1 ||
+        B > 65535)
+        return MGFEA_EINVAL;
+    const dim3 grid((unsigned)((pitch + 31) / 32), (unsigned)((N + 7) / 8), (unsigned)B), block(32, 8);
+    mg_jacobi_pbc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(u_in, u_out, f_pad, w9, invd, N, pitch, plane, pitch_f,
+                                                                  plane_f);
+    g_launches.fetch_add(1);
+    return (int)cudaGetLastError();
+}
 int mgfea_sumsq_interior(const float *r, double *sumsq, int N, int pitch, int64_t plane, int B, void *stream) {
     if (!r || !sumsq || N < 3 || pitch < N || B < 1 || B > 65535) return MGFEA_EINVAL;
     int nb = N - 2 < 256 ? N - 2 : 256;

@@ -106,6 +106,39 @@ __global__ void __launch_bounds__(256) mg_elem_kernel(const ElemParams p) {
         make_float4(o[0], o[1], o[2], o[3]);
 }
 
+// JacobiBlockPBC.jacobi_convolution (FEANet/jacobi.py:50-97): periodic 3x3 stencil on the n x n torus evaluated at all
+// (n+1)^2 nodes (node n == node 0), single pattern; f_pad is the caller-padded (N+2)^2 load vector the reference asks for
+__global__ void __launch_bounds__(256) mg_jacobi_pbc_kernel(const float *u, float *out, const float *fpad, const float *w9,
+                                                           const float *invd, int N, int pitch, long long plane, int pitch_f,
+                                                           long long plane_f) {
+    const int n = N - 1;
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, b = blockIdx.z;
+    if (x >= pitch || y >= N) return;
+    float o = 0.0f;
+    if (x < N) {
+        const float *ub = u + (long long)b * plane;
+        float s = 0.0f;
+#pragma unroll
+        for (int di = -1; di <= 1; ++di) {
+            int yy = y + di;
+            yy = yy < 0 ? yy + n : (yy >= n ? yy - n : yy);  // y + di in [-1, n + 1]
+            yy = yy >= n ? yy - n : yy;
+#pragma unroll
+            for (int dj = -1; dj <= 1; ++dj) {
+                int xx = x + dj;
+                xx = xx < 0 ? xx + n : (xx >= n ? xx - n : xx);
+                xx = xx >= n ? xx - n : xx;
+                const float v = __ldg(ub + (long long)yy * pitch + xx), w = __ldg(w9 + 3 * (di + 1) + (dj + 1));
+                s = (di == -1 && dj == -1) ? __fmul_rn(w, v) : __fmaf_rn(w, v, s);
+            }
+        }
+        const float r = __fsub_rn(__ldg(fpad + (long long)b * plane_f + (long long)(y + 1) * pitch_f + x + 1), s);
+        const float uc = __ldg(ub + (long long)(y == n ? 0 : y) * pitch + (x == n ? 0 : x));  // reset_boundary(u)
+        o = __fadd_rn(__fmul_rn(__ldg(invd), r), uc);
+    }
+    out[(long long)b * plane + (long long)y * pitch + x] = o;
+}
+
 // coarse element = mean of its four children, summed in fp32 in row-major order, times 0.25
 __global__ void __launch_bounds__(256) elem_coarsen_kernel(const float *a, float *ac, int n, int pitch, int pitch_c, int rows_c) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;

@@ -425,3 +425,42 @@ void orc_elem_jacobi(const float *u_in, float *u_out, const float *f, const floa
     free(tmp);
     free(cur);
 }
+
+/* ---------------------------------------------------------------------------------------------------------
+ * JacobiBlockPBC.jacobi_convolution (FEANet/jacobi.py:50-97), periodic boundary conditions, single pattern:
+ *   u_pbc = circular pad of u[:-1,:-1] by (1,2) -> (n+3)^2;  residual = f_pad - Knet(u_pbc) on the padded array (Knet pads
+ *   its mask with ones, FEANet/model.py:27-28), cropped [1:-1,1:-1];  u_new = omega/d * residual + reset_boundary(u)
+ * i.e. a periodic 3x3 stencil on the n x n torus evaluated at all (n+1)^2 nodes (node n == node 0).
+ * f_pad: [B][N+2][N+2] (the caller pads the load vector, as the reference requires); w9: the single 3x3 kernel.
+ */
+void orc_jacobi_pbc(const float *u_in, float *u_out, const float *f_pad, const float *w9, float invd, int N, int B,
+                    int nsweeps) {
+    const int n = N - 1, P = N + 2;
+    size_t M = (size_t)N * N;
+    float *cur = (float *)malloc(M * sizeof(float));
+    float *nxt = (float *)malloc(M * sizeof(float));
+    for (int b = 0; b < B; ++b) {
+        memcpy(cur, u_in + b * M, M * sizeof(float));
+        const float *fb = f_pad + (size_t)b * P * P;
+        for (int s = 0; s < nsweeps; ++s) {
+            for (int i = 0; i < N; ++i)
+                for (int j = 0; j < N; ++j) {
+                    float acc = 0.0f;
+                    for (int di = -1; di <= 1; ++di)
+                        for (int dj = -1; dj <= 1; ++dj) {
+                            int ii = ((i + di) % n + n) % n, jj = ((j + dj) % n + n) % n;
+                            acc = fmaf(w9[3 * (di + 1) + (dj + 1)], cur[IDX(ii, jj)], acc);
+                        }
+                    float res = fb[(size_t)(i + 1) * P + (j + 1)] - acc;
+                    float t = invd * res;
+                    nxt[IDX(i, j)] = t + cur[IDX(i % n, j % n)];
+                }
+            float *tmp = cur;
+            cur = nxt;
+            nxt = tmp;
+        }
+        memcpy(u_out + b * M, cur, M * sizeof(float));
+    }
+    free(cur);
+    free(nxt);
+}

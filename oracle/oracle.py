@@ -147,6 +147,17 @@ def hjacobi(u, f, keys, ktab, invd, hw, idx=None, bval=None, nsweeps=1):
     return out
 
 
+def jacobi_pbc(u, f_pad, w9, invd, nsweeps=1):
+    """JacobiBlockPBC.jacobi_convolution (FEANet/jacobi.py:89-97); f_pad (B, N+2, N+2) is the caller-padded load vector"""
+    u, f_pad = _as3(u), _as3(f_pad)
+    B, N, _ = u.shape
+    assert f_pad.shape == (B, N + 2, N + 2)
+    out = np.empty_like(u)
+    lib().orc_jacobi_pbc(_p(u, _f32p), _p(out, _f32p), _p(f_pad, _f32p), _p(_f(w9).reshape(9), _f32p),
+                         ctypes.c_float(float(np.float32(invd))), N, B, nsweeps)
+    return out
+
+
 def residual(u, f, keys, ktab):
     u, f = _as3(u), _as3(f)
     B, N, _ = u.shape

@@ -545,6 +545,35 @@ def gen_testpoisson():
     np.savez_compressed(os.path.join(OUT, "testpoisson.npz"), **out)
 
 
+def gen_pbc():
+    """JacobiBlockPBC (FEANet/jacobi.py:50-97) of the unmodified reference on random fields: 1 and 3 sweeps, the
+    reset_boundary / pbc_boundary helpers, d_mat"""
+    H.load_reference()
+    from FEANet.jacobi import JacobiBlockPBC
+    from FEANet.mesh import MeshSquare
+    from FEANet.model import KNet
+
+    g = torch.Generator().manual_seed(77)
+    out = {}
+    for n in (8, 16, 32):
+        N = n + 1
+        mesh = MeshSquare(2, N)
+        jac = JacobiBlockPBC(mesh, KNet(mesh))
+        u = torch.randn(2, 1, N, N, generator=g)
+        fp = torch.randn(2, 1, N + 2, N + 2, generator=g)
+        with torch.no_grad():
+            out[f"u_{n}"], out[f"fpad_{n}"] = t2n(u), t2n(fp)
+            out[f"pbc_{n}"], out[f"reset_{n}"] = t2n(jac.pbc_boundary(u)), t2n(jac.reset_boundary(u))
+            v = jac.jacobi_convolution(u, fp)
+            out[f"jac1_{n}"] = t2n(v)
+            for _ in range(2):
+                v = jac.jacobi_convolution(v, fp)
+            out[f"jac3_{n}"] = t2n(v)
+            out[f"dmat_{n}"] = t2n(jac.d_mat)
+    np.savez_compressed(os.path.join(OUT, "pbc.npz"), **out)
+    print("pbc.npz", len(out))
+
+
 def gen_h5manifest():
     """names / shapes / dtypes / data hashes of the reference's HDF5 files as read by the product's own reader
     (FEANet/h5lite.py), cross-checked against the byte-scanning reader this harness has used since round 1"""
@@ -571,7 +600,7 @@ def gen_h5manifest():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["mesh", "ops", "solve", "bands", "testpoisson", "h5"]
+    which = sys.argv[1:] or ["mesh", "ops", "solve", "bands", "testpoisson", "pbc", "h5"]
     if "mesh" in which:
         gen_mesh()
     if "ops" in which:
@@ -582,5 +611,7 @@ if __name__ == "__main__":
         gen_bands()
     if "testpoisson" in which:
         gen_testpoisson()
+    if "pbc" in which:
+        gen_pbc()
     if "h5" in which:
         gen_h5manifest()

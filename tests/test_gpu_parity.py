@@ -1032,3 +1032,38 @@ def test_dataset_batch_through_mgtest_multigrid(tmp_path, mode):
     # the FEM solution of the dataset is what the solver converges to
     sol, hist = mg.solve(torch.zeros(3, 1, n + 1, n + 1, device="cuda"), EPS=5e-5)
     assert (sol - u_fem).abs().max().item() <= 2e-5 * u_fem.abs().max().item()
+
+
+# ------------------------------------------------------------------------------------------ periodic-BC smoother (8f.4)
+PBC = np.load(os.path.join(G, "pbc.npz"))
+
+
+@pytest.mark.parametrize("n", [8, 16, 32])
+def test_jacobi_pbc_matches_reference(O, n):
+    """JacobiBlockPBC (FEANet/jacobi.py:50-97) against the UNMODIFIED reference's outputs (tests/golden/pbc.npz), bit-exact:
+    1 and 3 sweeps, the two padding helpers, d_mat; and against the oracle on a larger grid"""
+    from FEANet.jacobi import JacobiBlockPBC
+    from FEANet.mesh import MeshSquare
+    from FEANet.model import KNet
+
+    N = n + 1
+    mesh = MeshSquare(2, N)
+    jac = JacobiBlockPBC(mesh, KNet(mesh))
+    u, fp = cuda(PBC[f"u_{n}"]), cuda(PBC[f"fpad_{n}"])
+    exact(host(jac.pbc_boundary(u)), PBC[f"pbc_{n}"], "pbc_boundary")
+    exact(host(jac.reset_boundary(u)), PBC[f"reset_{n}"], "reset_boundary")
+    exact(jac.d_mat.numpy(), PBC[f"dmat_{n}"], "d_mat")
+    v = jac.jacobi_convolution(u, fp)
+    exact(host(v), PBC[f"jac1_{n}"], "jacobi_convolution x1")
+    exact(host(jac.jacobi_convolution(v, fp, n_iter=2)), PBC[f"jac3_{n}"], "x3")
+    exact(jac.jacobi_convolution(torch.from_numpy(PBC[f"u_{n}"]), torch.from_numpy(PBC[f"fpad_{n}"])).numpy(),
+          PBC[f"jac1_{n}"], "host in -> host out")
+    if n == 32:
+        Nb = 513
+        rs = np.random.RandomState(3)
+        ub, fb = rs.standard_normal((2, 1, Nb, Nb)).astype(np.float32), rs.standard_normal((2, 1, Nb + 2, Nb + 2)).astype(np.float32)
+        mb = MeshSquare(2, Nb)
+        w = O.kernel_table([1.0], 1).reshape(9)
+        invd = float(O.inv_diag(2 / 3., np.array([w[4]], np.float32))[0])
+        exact(host(JacobiBlockPBC(mb, KNet(mb)).jacobi_convolution(cuda(ub), cuda(fb), n_iter=2))[:, 0],
+              O.jacobi_pbc(ub, fb, w, invd, 2), "513^2 x2 vs oracle")

@@ -354,3 +354,16 @@ def test_element_vcycle_converges_and_coarsening():
         u = O.elem_vcycle(levels, u, f)
         res.append(float(np.sqrt(O.sumsq_interior(O.elem_residual(u, f, a))[0])))
     assert res[-1] < 1e-2 * res[0] and all(res[i + 1] < res[i] for i in range(8))  # q ~ 0.46 at 25x random contrast
+
+
+# ---------------------------------------------------------------- periodic-BC smoother (FEANet/jacobi.py:50-97)
+PBC = np.load(os.path.join(G, "pbc.npz"))
+
+
+@pytest.mark.parametrize("n", [8, 16, 32])
+def test_jacobi_pbc_bit_exact(n):
+    w = O.kernel_table([1.0], 1).reshape(9)
+    invd = float(O.inv_diag(2 / 3., np.array([w[4]], np.float32))[0])
+    for k, tag in ((1, "jac1"), (3, "jac3")):
+        got = O.jacobi_pbc(PBC[f"u_{n}"], PBC[f"fpad_{n}"], w, invd, k)
+        assert np.array_equal(got, PBC[f"{tag}_{n}"][:, 0]), (n, k)
