@@ -338,6 +338,44 @@ def secondary_configs(which):
                                                   1, 1, hist, steps=10, reset=lambda: eng.u[0].zero_())
         del eng, grids
         torch.cuda.empty_cache()
+    if "cfg5_element_1gpu" in which:  # config 5 in its general form: one conductivity per ELEMENT
+        from FEANet.element import ElementMultigrid
+
+        n, L = 16384, 14
+        g = torch.Generator(device="cuda").manual_seed(5)
+        a = torch.exp(torch.rand((n, n), generator=g, device="cuda") * np.log(25.0) + np.log(0.2))  # 0.2 .. 5, log-uniform
+        mg = ElementMultigrid(n, a)
+        del a
+        N = n + 1
+        mg.u[0].zero_()
+        mg.f[0].view.copy_(mg.grids[0].fnet(torch.ones(1, 1, N, N, device="cuda")))
+        r0 = float(torch.sqrt(mg.residual_sumsq().sum()).item())
+        hist = []
+        for _ in range(6):
+            hist.append(float(torch.sqrt(mg.cycle().sum()).item()) / r0)
+        runs = []
+        for _ in range(REPEATS):
+            mg.u[0].zero_()
+            torch.cuda.synchronize()
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record()
+            for _ in range(5):
+                mg.cycle(want_norm=True)
+            eb.record()
+            torch.cuda.synchronize()
+            runs.append(ea.elapsed_time(eb) / 5)
+        ms = float(np.median(runs))
+        balg = algorithmic_bytes_per_cycle(n, L, key_bytes=4)  # + 4 B per node per K-apply for the element field
+        peak, _ = hbm_peak()
+        out["cfg5_element_1gpu"] = {
+            "config": "config 5, general heterogeneous conductivity: 16385^2, one log-uniform conductivity in [0.2, 5] per "
+                      "ELEMENT, 14 levels (4-child mean coarsening), V(1,1) Jacobi, F=ones; per-element kernels "
+                      "(mgfea_elem_*, one pass per operator, not fused yet), eager launches incl. the residual norm",
+            "ms_per_cycle": ms, "ms_runs": runs, "v_cycles_per_s": 1e3 / ms, "gdof_per_s": N * N / ms / 1e6,
+            "algorithmic_GB": balg / 1e9, "cycle_roofline_frac": balg / (ms * 1e-3) / 1e9 / peak,
+            "residual_history_rel": hist}
+        del mg
+        torch.cuda.empty_cache()
     return out
 
 
@@ -594,7 +632,7 @@ def run_ours(args):
         del eng
         prob._engines.clear()
         torch.cuda.empty_cache()
-        configs = secondary_configs(["cfg2", "cfg3", "cfg3_jacobi", "cfg4_1gpu", "cfg5_1gpu", "cfg5_two_phase_1gpu"]
+        configs = secondary_configs(["cfg2", "cfg3", "cfg3_jacobi", "cfg4_1gpu", "cfg5_1gpu", "cfg5_two_phase_1gpu", "cfg5_element_1gpu"]
                                     if not args.configs else args.configs.split(","))
     cpu = cpu_baseline_sample(n, L) if (world == 1 and not args.no_cpu_baseline) else None
     line = {"metric": METRIC, "value": cycles_per_s * dof / 1e9, "unit": "GDOF/s", "n_gpus": world, "steps": steps,
@@ -926,7 +964,7 @@ def main():
     ap.add_argument("--n-multi", type=int, default=0, help="grid intervals for the row-slab run at N > 1 (default by N)")
     ap.add_argument("--no-configs", action="store_true", help="skip the secondary BASELINE configs block")
     ap.add_argument("--configs", default="", help="comma list out of cfg2,cfg3,cfg3_jacobi,cfg4_1gpu,cfg5_1gpu,"
-                                                  "cfg5_two_phase_1gpu (default: all at N=1)")
+                                                  "cfg5_two_phase_1gpu,cfg5_element_1gpu (default: all at N=1)")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the slab-vs-single-GPU bit-identity self-check")
     args = ap.parse_args()
     if args.impl == "reference":
