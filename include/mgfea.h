@@ -264,6 +264,12 @@ int mgfea_slab_defect_f64_ext(const mgfea_grid *g, const mgfea_slab *s, int ext,
 int mgfea_smooth_pbc(const float *w9, const float *invd, const float *u_in, float *u_out, const float *f_pad, int N,
                      int pitch, int64_t plane, int pitch_f, int64_t plane_f, int B, void *stream);
 
+/* Backward pass of one HNet layer (the reference back-propagates through HJacIterator.HRelax with autograd,
+ * M-FEANet-learn_iterator.ipynb cell 7): weight gradient of the zero-padded correlation out = w (*) a,
+ * acc9[3 dy + dx] += sum_{b,i,j} a[b][i+dy-1][j+dx-1] * g[b][i][j] in fp64 (the caller zeroes acc9; atomics across blocks).
+ * The input gradient is the same correlation with the flipped kernel (mgfea_load_vector), the adjoint of K is K. */
+int mgfea_corr9(const float *a, const float *g, double *acc9, int N, int pitch, int64_t plane, int B, void *stream);
+
 /* ---- general per-element conductivity ---------------------------------------------------- */
 /* The reference's data model carries one conductivity per ELEMENT (`material`, Data/dataset.py:71-104) but its operator
  * only knows the 16 two-phase patterns (FEANet/mesh.py:103-117).  These entries are that operator with the pattern lookup

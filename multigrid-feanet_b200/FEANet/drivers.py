@@ -286,8 +286,8 @@ class HNet(nn.Module):
 
 
 class HJacIterator(nn.Module):
-    '''Jacobi + learned correction: u <- J(u) + H(J(u) - u) (mg_test cell 5).  Inference only: training the HNet
-    (TrainSingleEpoch / Train) is outside the solve() path.'''
+    '''Jacobi + learned correction: u <- J(u) + H(J(u) - u) (mg_test cell 5).  HRelax is the fused inference kernel;
+    HRelaxGrad / TrainSingleEpoch / Train back-propagate through the sweeps to the HNet kernels.'''
 
     def __init__(self, n, size=2, hnet=None, grid=None, batch_size=5, max_epochs=1000, nb_layers=3,
                  model_name='iso_poisson_33x33', model_dir='Model/learn_iterator/iso_poisson'):
@@ -318,12 +318,125 @@ class HJacIterator(nn.Module):
     def RandomSampling(self, x):
         return torch.randn_like(x)
 
-    def TrainSingleEpoch(self, *_a, **_k):
-        raise mgfea.MgfeaError("HJacIterator.Train / TrainSingleEpoch: not supported -- the CUDA smoother has no backward "
-                               "pass (SURVEY 8f.4).  Train the HNet with the reference and load its state_dict here "
-                               "(HNet.load_state_dict); HRelax / MGTestMultiGrid then use the weights as they are.")
+    # ---- training (M-FEANet-learn_iterator.ipynb cell 8; mg_test cell 5): back-propagation through HRelax
+    def HRelaxGrad(self, v, f, num_sweeps_down):
+        """HRelax with a backward pass w.r.t. the HNet kernels (and v): the forward runs the sweeps operator by operator
+        (Jacobi kernel, x = J(u) - u, three masked 3x3 correlations) keeping what the adjoint needs; the backward uses the
+        same sm_100a kernels -- the adjoint of a zero-padded correlation is the correlation with the flipped kernel, the
+        adjoint of K is K (symmetric), the weight gradients are `mgfea_corr9` reductions.  CUDA tensors in and out."""
+        ws = [l.weight for l in self.net.convLayers]
+        return _HRelaxFn.apply(v, f, self, int(num_sweeps_down), *ws)
 
-    Train = TrainSingleEpoch
+    def TrainSingleEpoch(self, train_dataloader, k_range=(1, 20)):
+        """one pass over `train_dataloader` (batches (u, f, bc_value, bc_index), host or CUDA tensors: the reference's
+        DataLoader or FEANet.dataset.DeviceBatchLoader): Adadelta on MSELoss(reduction='sum') of HRelax(random u0, fnet(f), k)
+        against the FEM solution, k drawn from k_range like the notebook's random.randint(1, 20)"""
+        import random
+
+        if not hasattr(self, "optimizer"):
+            self.loss = nn.MSELoss(reduction='sum')
+            self.optimizer = torch.optim.Adadelta(self.net.parameters())
+        dev = mgfea.require_cuda()
+        running_loss, i = 0., -1
+        for i, data in enumerate(train_dataloader):
+            u_train, f_train, bc_value_train, bc_index_train = [t.to(dev, dtype=torch.float32) for t in data]
+            self.optimizer.zero_grad()
+            k = random.randint(*k_range)
+            self.grid.ResetBoundary(bc_index_train, bc_value_train)
+            ff = self.grid.fnet(f_train)
+            uu = self.RandomSampling(f_train)
+            u_out = self.HRelaxGrad(uu, ff, k)
+            loss_i = self.loss(u_out, u_train)
+            loss_i.backward()
+            self.optimizer.step()
+            running_loss += loss_i.item()
+        return running_loss / (i + 1)
+
+    def Train(self, training_set, save=True):
+        from .dataset import DeviceBatchLoader
+
+        train_dataloader = DeviceBatchLoader(training_set, batch_size=self.batch_size, shuffle=True)
+        loss_train = torch.zeros((self.max_epochs, 1))
+        avg_loss = self.TrainSingleEpoch(train_dataloader)
+        print('Step-0 loss:', avg_loss)
+        loss_train[0] = avg_loss
+        for epoch in range(1, self.max_epochs):
+            avg_loss = self.TrainSingleEpoch(train_dataloader)
+            if epoch % 50 == 0:
+                print('Step-' + str(epoch) + ' loss:', avg_loss)
+            if save:  # save the model's state (mg_test cell 5)
+                os.makedirs(self.model_dir, exist_ok=True)
+                torch.save(self.net.state_dict(), os.path.join(self.model_dir, self.model_name + '.pth'))
+            loss_train[epoch] = avg_loss
+        return loss_train
+
+
+def _flip9(w):
+    return torch.flip(w.detach().reshape(3, 3), (0, 1)).contiguous().reshape(1, 9)
+
+
+class _HRelaxFn(torch.autograd.Function):
+    """u_{s+1} = J(u_s) + H(J(u_s) - u_s), H = (c3 . m) o (c2 . m) o (c1 . m)  (mg_test cells 4-5), `k` sweeps"""
+
+    @staticmethod
+    def _conv(fld, w9_dev):
+        out = Field(fld.B, fld.N, fld.store.device)
+        check(lib().mgfea_load_vector(w9_dev.data_ptr(), fld.ptr, out.ptr, fld.N, fld.pitch, fld.plane, fld.B, stream_ptr()))
+        return out
+
+    @staticmethod
+    def forward(ctx, v, f, it, k, *ws):
+        dev = mgfea.require_cuda()
+        jac = it.grid.jac
+        uf, ff = as_field(v.detach()), as_field(f.detach())
+        m = as_field(jac.geometry_idx.to(dev)).store  # (B or 1, N, pitch): 1 inside, 0 on the Dirichlet nodes
+        wd = [w.detach().to(dev, torch.float32).reshape(1, 9).contiguous() for w in ws]
+        saved = []
+        u = uf
+        for _ in range(k):
+            vj = jac.smooth_fields(u, ff, 1)                        # J(u): one Jacobi sweep (mgfea_smooth)
+            x = Field(u.B, u.N, dev, store=vj.store - u.store)      # fields are zero in the padding columns
+            h, acts = x, [x]
+            for w9 in wd:
+                z = _HRelaxFn._conv(h, w9)
+                h = Field(u.B, u.N, dev, store=z.store * m)
+                acts.append(h)
+            saved.append(acts[:3])                                  # x, h1, h2: inputs of the three layers
+            u = Field(u.B, u.N, dev, store=vj.store + acts[3].store)
+        ctx.it, ctx.k, ctx.saved, ctx.m, ctx.wd, ctx.wdev = it, k, saved, m, wd, [w.device for w in ws]
+        ctx.host_out = not v.is_cuda
+        return _like_input(v, u).clone() if v.is_cuda else _like_input(v, u)
+
+    @staticmethod
+    def backward(ctx, g_out):
+        it, k, m, wd = ctx.it, ctx.k, ctx.m, ctx.wd
+        jac = it.grid.jac
+        dev = m.device
+        g = as_field(g_out.detach().to(dev).contiguous())
+        acc = torch.zeros((len(wd), 9), dtype=torch.float64, device=dev)
+        flipped = [_flip9(w) for w in wd]
+        s = float(jac._invd_np[0])  # omega / d (single pattern: the HNet iterators are iso, like the reference's)
+        if jac.Knet.n_channel != 1:
+            raise mgfea.MgfeaError("HRelaxGrad: single-pattern meshes only (the reference trains on MeshSquare)")
+        gs = g.store
+        for sweep in range(k - 1, -1, -1):
+            acts = ctx.saved[sweep]
+            gh = gs                                                  # dL/dh3
+            for l in range(len(wd) - 1, -1, -1):
+                gz = Field(g.B, g.N, dev, store=gh * m)              # through the mask
+                check(lib().mgfea_corr9(acts[l].ptr, gz.ptr, acc[l].data_ptr(), g.N, gz.pitch, gz.plane, g.B, stream_ptr()))
+                gh = _HRelaxFn._conv(gz, flipped[l]).store           # adjoint of the correlation: flipped kernel
+            gx = gh
+            gv = gs + gx                                             # u' = v + H(x), x = v - u
+            gw = Field(g.B, g.N, dev, store=gv * m)                  # v = reset(w): mask (the boundary values are constants)
+            kg = Field(g.B, g.N, dev)
+            check(lib().mgfea_stiffness_apply(jac.grid_struct(gw), gw.ptr, kg.ptr, g.B, stream_ptr()))  # K^T = K
+            gs = (gw.store - s * kg.store) * m - gx                  # w = u~ + s (f - K u~), u~ = reset(u)
+            gs[:, :, g.N:] = 0                                       # K leaves nothing there, keep the padding clean
+        gu = Field(g.B, g.N, dev, store=gs)
+        grad_v = _like_input(g_out, gu)
+        gws = [acc[l].to(torch.float32).reshape(1, 1, 3, 3).to(ctx.wdev[l]) for l in range(len(wd))]
+        return (grad_v, None, None, None) + tuple(gws)
 
 
 class RestrictionNet1(nn.Module):

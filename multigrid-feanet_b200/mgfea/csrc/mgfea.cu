@@ -2063,6 +2063,13 @@ int mgfea_smooth_pbc(const float *w9, const float *invd, const float *u_in, floa
     g_launches.fetch_add(1);
     return (int)cudaGetLastError();
 }
+int mgfea_corr9(const float *a, const float *g, double *acc9, int N, int pitch, int64_t plane, int B, void *stream) {
+    if (!a || !g || !acc9 || N < 3 || pitch < N || B < 1 || B > 65535) return MGFEA_EINVAL;
+    const int nb = N < 64 ? N : 64;
+    corr9_kernel<<<dim3((unsigned)nb, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(a, g, acc9, N, pitch, plane);
+    g_launches.fetch_add(1);
+    return (int)cudaGetLastError();
+}
 int mgfea_sumsq_interior(const float *r, double *sumsq, int N, int pitch, int64_t plane, int B, void *stream) {
     if (!r || !sumsq || N < 3 || pitch < N || B < 1 || B > 65535) return MGFEA_EINVAL;
     int nb = N - 2 < 256 ? N - 2 : 256;

@@ -139,6 +139,45 @@ __global__ void __launch_bounds__(256) mg_jacobi_pbc_kernel(const float *u, floa
     out[(long long)b * plane + (long long)y * pitch + x] = o;
 }
 
+// weight gradient of a zero-padded 3x3 correlation out = w (*) a (the backward pass of an HNet layer):
+// acc[t] += sum over batch and nodes of a[i+dy-1][j+dx-1] * g[i][j], t = 3 dy + dx, accumulated in fp64
+__global__ void __launch_bounds__(256) corr9_kernel(const float *a, const float *g, double *acc, int N, int pitch, long long plane) {
+    __shared__ double red[8][9];
+    const int b = blockIdx.y;
+    const float *ab = a + (long long)b * plane, *gb = g + (long long)b * plane;
+    double s[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) s[t] = 0.0;
+    for (int y = blockIdx.x; y < N; y += gridDim.x)
+        for (int x = threadIdx.x; x < N; x += 256) {
+            const double gv = (double)gb[(long long)y * pitch + x];
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+                const int yy = y + dy - 1;
+                if (yy < 0 || yy >= N) continue;
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const int xx = x + dx - 1;
+                    if (xx < 0 || xx >= N) continue;
+                    s[3 * dy + dx] += (double)ab[(long long)yy * pitch + xx] * gv;
+                }
+            }
+        }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        double v = s[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][t] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 9) {
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+        atomicAdd(acc + threadIdx.x, v);
+    }
+}
+
 // coarse element = mean of its four children, summed in fp32 in row-major order, times 0.25
 __global__ void __launch_bounds__(256) elem_coarsen_kernel(const float *a, float *ac, int n, int pitch, int pitch_c, int rows_c) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;

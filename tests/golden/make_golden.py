@@ -574,6 +574,37 @@ def gen_pbc():
     print("pbc.npz", len(out))
 
 
+def gen_hgrad():
+    """gradients of the reference's HNet training step (M-FEANet-learn_iterator.ipynb cell 8 / mg_test cell 5:
+    loss = MSELoss(sum)(HRelax(uu, fnet(f), k), u) with per-sample Dirichlet masks) by the reference's own autograd"""
+    nsT = H.notebook_namespace("M-FEANet-mg_test.ipynb", [1, 2, 3, 4, 5])
+    sd = torch.load(os.path.join(H.REF, "Model/learn_iterator/iso_poisson/iso_poisson_33x33.pth"), weights_only=True)
+    bi, bv, rhs, uex = H.read_h5_contiguous(os.path.join(H.REF, "Data/IsoPoisson/poisson2d_33x33.h5"), (100, 33, 33))
+    out = {}
+    g = torch.Generator().manual_seed(99)
+    for k in (1, 3):
+        hnet = nsT["HNet"](3)
+        hnet.load_state_dict(sd)
+        it = nsT["HJacIterator"](n=32, hnet=hnet)
+        B = 2
+        u_train = torch.from_numpy(uex[:B].astype(np.float32))[:, None]
+        f_train = torch.from_numpy(rhs[:B].astype(np.float32))[:, None]
+        bval = torch.from_numpy(bv[:B].astype(np.float32))[:, None]
+        bidx = torch.from_numpy(bi[:B].astype(np.float32))[:, None]
+        it.grid.ResetBoundary(bidx, bval)
+        ff = it.grid.fnet(f_train)
+        uu = torch.randn(B, 1, 33, 33, generator=g).requires_grad_(True)
+        u_out = it.HRelax(uu, ff, k)
+        loss = torch.nn.MSELoss(reduction="sum")(u_out, u_train)
+        loss.backward()
+        out[f"uu_k{k}"], out[f"uout_k{k}"], out[f"loss_k{k}"] = t2n(uu), t2n(u_out), np.array([loss.item()])
+        out[f"guu_k{k}"] = t2n(uu.grad)
+        for l, layer in enumerate(hnet.convLayers):
+            out[f"gw{l}_k{k}"] = t2n(layer.weight.grad).reshape(9)
+        print("hgrad k", k, loss.item(), [float(np.abs(out[f"gw{l}_k{k}"]).max()) for l in range(3)])
+    np.savez_compressed(os.path.join(OUT, "hgrad.npz"), **out)
+
+
 def gen_h5manifest():
     """names / shapes / dtypes / data hashes of the reference's HDF5 files as read by the product's own reader
     (FEANet/h5lite.py), cross-checked against the byte-scanning reader this harness has used since round 1"""
@@ -600,7 +631,7 @@ def gen_h5manifest():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["mesh", "ops", "solve", "bands", "testpoisson", "pbc", "h5"]
+    which = sys.argv[1:] or ["mesh", "ops", "solve", "bands", "testpoisson", "pbc", "hgrad", "h5"]
     if "mesh" in which:
         gen_mesh()
     if "ops" in which:
@@ -613,5 +644,7 @@ if __name__ == "__main__":
         gen_testpoisson()
     if "pbc" in which:
         gen_pbc()
+    if "hgrad" in which:
+        gen_hgrad()
     if "h5" in which:
         gen_h5manifest()

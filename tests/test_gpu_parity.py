@@ -1067,3 +1067,54 @@ def test_jacobi_pbc_matches_reference(O, n):
         invd = float(O.inv_diag(2 / 3., np.array([w[4]], np.float32))[0])
         exact(host(JacobiBlockPBC(mb, KNet(mb)).jacobi_convolution(cuda(ub), cuda(fb), n_iter=2))[:, 0],
               O.jacobi_pbc(ub, fb, w, invd, 2), "513^2 x2 vs oracle")
+
+
+# ------------------------------------------------------------------------------------------ HNet training step (8f.4)
+HG = np.load(os.path.join(G, "hgrad.npz"))
+
+
+@pytest.mark.parametrize("k", [1, 3])
+def test_hrelax_backward_matches_reference_autograd(k):
+    """HJacIterator.HRelaxGrad: loss = MSELoss(sum)(HRelax(uu, fnet(f), k), u) with per-sample Dirichlet masks -- forward
+    value, loss, gradients of the three HNet kernels and of the initial iterate against the reference's own autograd
+    (tests/golden/hgrad.npz, M-FEANet-learn_iterator.ipynb cell 8)"""
+    from FEANet.drivers import HJacIterator
+
+    hnet = _hnet()
+    it = HJacIterator(n=32, hnet=hnet)
+    B = 2
+    u_train, f_train = cuda(ARR["iso33_u"][:B, None]), cuda(ARR["iso33_rhs"][:B, None])
+    it.grid.ResetBoundary(torch.from_numpy(ARR["iso33_bidx"][:B, None]), torch.from_numpy(ARR["iso33_bval"][:B, None]))
+    ff = it.grid.fnet(f_train)
+    uu = cuda(HG[f"uu_k{k}"]).requires_grad_(True)
+    u_out = it.HRelaxGrad(uu, ff, k)
+    ref_out = HG[f"uout_k{k}"]
+    assert np.abs(host(u_out) - ref_out).max() <= 2e-6 * np.abs(ref_out).max()
+    exact(host(u_out), host(it.HRelax(uu.detach(), ff, k)), "HRelaxGrad forward == fused HRelax kernel")
+    loss = torch.nn.MSELoss(reduction="sum")(u_out, u_train)
+    assert abs(loss.item() - float(HG[f"loss_k{k}"][0])) <= 1e-5 * float(HG[f"loss_k{k}"][0])
+    loss.backward()
+    for l, layer in enumerate(hnet.convLayers):
+        got, ref = layer.weight.grad.reshape(9).numpy(), HG[f"gw{l}_k{k}"]
+        assert np.abs(got - ref).max() <= 1e-4 * np.abs(ref).max(), (l, got, ref)
+    gu, ref = host(uu.grad), HG[f"guu_k{k}"]
+    assert np.abs(gu - ref).max() <= 1e-4 * np.abs(ref).max()
+
+
+def test_hnet_training_reduces_loss(tmp_path):
+    """HJacIterator.TrainSingleEpoch over FEANet.dataset batches (the learn_iterator notebook's loop): the loss goes down"""
+    from FEANet.dataset import DeviceBatchLoader, IsoPoissonDataSet
+    from FEANet.drivers import HJacIterator, HNet
+    from FEANet.h5lite import write_h5
+
+    path = write_h5(str(tmp_path / "iso.h5"), {"boundary_index": ARR["iso33_bidx"].astype(np.float64),
+                                               "boundary_value": ARR["iso33_bval"].astype(np.float64),
+                                               "rhs": ARR["iso33_rhs64"], "u": ARR["iso33_u64"]})
+    torch.manual_seed(0)
+    import random
+
+    random.seed(0)
+    it = HJacIterator(n=32, hnet=HNet(3), batch_size=3)
+    loader = DeviceBatchLoader(IsoPoissonDataSet(path), batch_size=3)
+    losses = [it.TrainSingleEpoch(loader, k_range=(4, 4)) for _ in range(12)]
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
