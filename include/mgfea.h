@@ -270,6 +270,20 @@ int mgfea_smooth_pbc(const float *w9, const float *invd, const float *u_in, floa
  * The input gradient is the same correlation with the flipped kernel (mgfea_load_vector), the adjoint of K is K. */
 int mgfea_corr9(const float *a, const float *g, double *acc9, int N, int pitch, int64_t plane, int B, void *stream);
 
+/* Backward of the table restriction / prolongation of FEANet/multigrid.py:50-73,115-130 (the reference trains R / P by
+ * back-propagating through MultiGrid.iterate).  Tables [n][9], n = 1 or 16 (by the FINE source node's key for R, by the
+ * COARSE node's key for P: g->keys / gc->keys); `scale` = w[0] / w[1].
+ *   restrict_adjoint:  g_r  (fine)   = d(fc)/d(r)^T  g_fc      prolong_adjoint:  g_vc (coarse) = d(e)/d(vc)^T g_vf
+ *   *_wgrad:           acc[n][9] (fp64, caller-zeroed, atomics) += table gradient */
+int mgfea_restrict_adjoint(const mgfea_grid *g, const mgfea_grid *gc, const float *rtab, int rtab_n, float scale,
+                           const float *g_fc, float *g_r, int B, void *stream);
+int mgfea_prolong_adjoint(const mgfea_grid *g, const mgfea_grid *gc, const float *ptab, int ptab_n, float scale,
+                          const float *g_vf, float *g_vc, int B, void *stream);
+int mgfea_restrict_wgrad(const mgfea_grid *g, const mgfea_grid *gc, int rtab_n, float scale, const float *r,
+                         const float *g_fc, double *acc, int B, void *stream);
+int mgfea_prolong_wgrad(const mgfea_grid *g, const mgfea_grid *gc, int ptab_n, float scale, const float *vc,
+                        const float *g_vf, double *acc, int B, void *stream);
+
 /* ---- general per-element conductivity ---------------------------------------------------- */
 /* The reference's data model carries one conductivity per ELEMENT (`material`, Data/dataset.py:71-104) but its operator
  * only knows the 16 two-phase patterns (FEANet/mesh.py:103-117).  These entries are that operator with the pattern lookup

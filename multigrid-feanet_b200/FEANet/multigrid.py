@@ -149,19 +149,18 @@ class MultiGrid(nn.Module):
                                         xf.B, stream_ptr()))
         return torch.sqrt(ss)
 
-    def _inference_only(self, what):
-        """The reference trains R / P / w by back-propagating through this cycle (multigrid.py:98-100,145-157); the fused
-        sm_100a cycle has no backward pass (not built).  Returning a silently detached tensor would make a
-        training loop fail far away ("does not require grad") or, worse, train nothing -- fail HERE instead."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise mgfea.MgfeaError(
-                f"MultiGrid.{what}: inference only -- the CUDA V-cycle is not differentiable, but conv / deconv / w "
-                "require grad and autograd is recording.  Wrap the call in torch.no_grad() (or "
-                "requires_grad_(False)) to solve; training the inter-grid operators is not supported by this package.")
+    def _training(self):
+        """autograd is recording and R / P / w are trainable: the reference's training mode (multigrid.py:98-100)"""
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
 
     def qm(self, x):
         "Compute the convergence factor after m iterations"
-        self._inference_only("qm")
+        if self._training() or (torch.is_tensor(x) and x.requires_grad):
+            # differentiable w.r.t. x (the last iterate): d||r||/dx = -K r / ||r|| on the interior, K symmetric
+            r1 = _ResNormFn.apply(x, self.f, self)
+            with torch.no_grad():
+                r0 = self._res_norms(self.v_m0, self.f).to(r1.device)
+            return torch.mean(torch.pow(r1 / r0, 1.0 / (self.m - self.m0 + 1))).to(torch.float32)
         r1, r0 = self._res_norms(x, self.f), self._res_norms(self.v_m0, self.f)
         return torch.mean(torch.pow(r1 / r0, 1.0 / (self.m - self.m0 + 1))).to(torch.float32).cpu()
 
@@ -173,21 +172,25 @@ class MultiGrid(nn.Module):
                 v[i, j, :, :] = torch.from_numpy(coef[0] * np.random.random((d3, d4)) + coef[1])
 
     def forward(self, F):
-        '''Input is RHS field F'''
-        self._inference_only("forward")
+        '''Input is RHS field F.  Under autograd with trainable R / P / w the LAST cycle is differentiable (the earlier
+        ones are detached, as in the reference: multigrid.py:152-157), so `qm(forward(F)).backward()` trains the
+        inter-grid kernels like the learn_intergrid notebooks do.'''
         self.f = self.grids[0].fnet(F)
         self.v = torch.zeros(tuple(F.shape), requires_grad=False, dtype=torch.float32)
         self.random_sampling(self.v)
         U = torch.clone(self.v).to(F.device)
-        for i in range(self.m - 1):
-            U = self.iterate(U, self.f)
-            if i == self.m0 - 1:
-                self.v_m0 = U.clone()
+        with torch.no_grad():
+            for i in range(self.m - 1):
+                U = self.iterate(U, self.f)
+                if i == self.m0 - 1:
+                    self.v_m0 = U.clone()
+        if self._training():
+            return self.iterate_grad(U, self.f)
         return self.iterate(U, self.f)
 
     def iterate(self, x, f):
-        '''one V(1,1) cycle; x is the current solution on the finest grid.  The result is DETACHED from autograd (see
-        _inference_only): iterate is the solve() building block, forward / qm are the training entry points and refuse'''
+        '''one V(1,1) cycle (fused kernels); x is the current solution on the finest grid.  The result is detached from
+        autograd: use iterate_grad (or forward) to train R / P / w'''
         eng = self._engine(x.shape[0])
         eng.refresh()
         eng.set_u(x)
@@ -196,3 +199,172 @@ class MultiGrid(nn.Module):
         out = eng.solution.clone() if x.is_cuda else eng.solution.cpu().contiguous()
         self.grids[0].v, self.grids[0].f = out, f
         return out
+
+    def iterate_grad(self, x, f):
+        '''the same cycle with a backward pass to conv.net.weight (R), deconv.net.weight (P) and w: run
+        operator by operator so that the adjoint sweep finds every level's intermediate fields; bit-identical forward'''
+        return _IterateFn.apply(x, f, self, self.conv.net.weight, self.deconv.net.weight, self.w)
+
+
+def _zero_ring(t, N):
+    t[:, 0, :] = 0
+    t[:, N - 1, :] = 0
+    t[:, :, 0] = 0
+    t[:, :, N - 1:] = 0
+    return t
+
+
+class _ResNormFn(torch.autograd.Function):
+    '''per-sample interior 2-norm of f - K x (multigrid.py:132-136), differentiable w.r.t. x'''
+
+    @staticmethod
+    def forward(ctx, x, f, mg):
+        xf, ff = as_field(x.detach()), as_field(f.detach())
+        jac = mg.grids[0].jac
+        r = Field(xf.B, xf.N, xf.store.device)
+        check(lib().mgfea_residual(jac.grid_struct(xf), xf.ptr, ff.ptr, r.ptr, xf.B, stream_ptr()))
+        _zero_ring(r.store, xf.N)
+        ss = torch.zeros(xf.B, dtype=torch.float64, device=r.store.device)
+        check(lib().mgfea_sumsq_interior(r.ptr, ss.data_ptr(), xf.N, xf.pitch, xf.plane, xf.B, stream_ptr()))
+        nrm = torch.sqrt(ss)
+        ctx.r, ctx.nrm, ctx.jac, ctx.host = r, nrm, jac, not x.is_cuda
+        return nrm.to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        r, jac = ctx.r, ctx.jac
+        kr = Field(r.B, r.N, r.store.device)
+        check(lib().mgfea_stiffness_apply(jac.grid_struct(r), r.ptr, kr.ptr, r.B, stream_ptr()))  # K^T r = K r
+        coef = (-g.to(r.store.device, torch.float64) / ctx.nrm).to(torch.float32)
+        gx = Field(r.B, r.N, r.store.device, store=kr.store * coef[:, None, None])
+        out = gx.view.contiguous()
+        return (out.cpu() if ctx.host else out), None, None
+
+
+class _IterateFn(torch.autograd.Function):
+    '''MultiGrid.iterate (multigrid.py:159-185) with reverse-mode differentiation through every level.
+    Level j:  s_j = Jac(a_j, f_j)   (a_0 = x, a_j = 0)      r_j = f_j - K s_j       f_{j+1} = w0 R(r_j)
+              coarsest: t = Jac(s, f)        up: c_j = s_j + w1 P(t_{j+1}),  t_j = Jac(c_j, f_j);   result t_0.
+    Adjoints: Jac: g_w = m g, g_f = D^-1 g_w, g_u = m (g_w - K D^-1 g_w)   (K symmetric, D^-1 = omega / d per node);
+    R / P: mgfea_restrict_adjoint / mgfea_prolong_adjoint; tables: mgfea_*_wgrad; w: <f_{j+1}, g> / w0, <c_j - s_j, g> / w1.'''
+
+    @staticmethod
+    def forward(ctx, x, f, mg, Rw, Pw, w):
+        dev = mgfea.require_cuda()
+        L, B = mg.L, x.shape[0]
+        jacs = [mg.grids[j].jac for j in range(L)]
+        rt = Rw.detach().to(dev, torch.float32).reshape(-1, 9).contiguous()
+        pt = Pw.detach().to(dev, torch.float32).reshape(-1, 9).contiguous()
+        w0, w1 = float(w[0]), float(w[1])
+        a0, f0 = as_field(x.detach()), as_field(f.detach())
+        fs, ss, rs, ts, cs = [f0], [], [], [None] * L, [None] * L
+
+        def zeros(j):
+            return Field(B, jacs[j].nnode_edge, dev)
+
+        for j in range(L):
+            s_j = jacs[j].smooth_fields(a0 if j == 0 else zeros(j), fs[j], 1)
+            ss.append(s_j)
+            if j < L - 1:
+                g = jacs[j].grid_struct(s_j)
+                r = zeros(j)
+                check(lib().mgfea_residual(g, s_j.ptr, fs[j].ptr, r.ptr, B, stream_ptr()))
+                fc = zeros(j + 1)
+                check(lib().mgfea_restrict(g, r.ptr, fc.ptr, fc.pitch, fc.plane, rt.data_ptr(), rt.shape[0], 1, w0, None, B,
+                                           stream_ptr()))
+                rs.append(r)
+                fs.append(fc)
+        ts[L - 1] = jacs[L - 1].smooth_fields(ss[L - 1], fs[L - 1], 1)
+        for j in range(L - 2, -1, -1):
+            c = zeros(j)
+            check(lib().mgfea_prolong_correct_smooth(jacs[j].grid_struct(c), jacs[j + 1].grid_struct(ts[j + 1]),
+                                                     ts[j + 1].ptr, ss[j].ptr, c.ptr, None, mgfea.PROLONG_TABLE,
+                                                     pt.data_ptr(), pt.shape[0], 1, w1, None, 0, 0, None, 0, B, stream_ptr()))
+            cs[j] = c
+            ts[j] = jacs[j].smooth_fields(c, fs[j], 1)
+        ctx.mg, ctx.jacs, ctx.tabs, ctx.w01 = mg, jacs, (rt, pt), (w0, w1)
+        ctx.fields = (fs, ss, rs, ts, cs)
+        ctx.meta = (Rw.shape, Pw.shape, Rw.device, Pw.device, w.device, not x.is_cuda)
+        out = ts[0].view.clone()
+        return out.cpu() if not x.is_cuda else out
+
+    @staticmethod
+    def _invd_field(jac, fld):
+        '''omega / d per node as a padded (1, N, pitch) device field'''
+        cache = getattr(jac, "_invd_field", None)
+        if cache is None:
+            inv = jac.invd_dev()
+            kd = jac.Knet.keys_dev()
+            N, pitch = fld.N, fld.pitch
+            out = torch.zeros((1, N, pitch), dtype=torch.float32, device=fld.store.device)
+            out[0, :, :N] = inv[kd[:, :N].long()] if kd is not None else inv[0]
+            cache = jac._invd_field = out
+        return cache
+
+    @staticmethod
+    def _jac_adjoint(jac, g_out):
+        '''g_out = dL/d Jac(u, f)  ->  (dL/du, dL/df), default Dirichlet ring with zero boundary values'''
+        dev = g_out.store.device
+        N = g_out.N
+        gw = _zero_ring(g_out.store.clone(), N)
+        gf = Field(g_out.B, N, dev, store=gw * _IterateFn._invd_field(jac, g_out))
+        kg = Field(g_out.B, N, dev)
+        check(lib().mgfea_stiffness_apply(jac.grid_struct(gf), gf.ptr, kg.ptr, g_out.B, stream_ptr()))
+        gu = _zero_ring(gw - kg.store, N)
+        return Field(g_out.B, N, dev, store=gu), gf
+
+    @staticmethod
+    def backward(ctx, g):
+        mg, jacs = ctx.mg, ctx.jacs
+        fs, ss, rs, ts, cs = ctx.fields
+        rt, pt = ctx.tabs
+        w0, w1 = ctx.w01
+        L = mg.L
+        dev = rt.device
+        B = g.shape[0]
+        if not jacs[0]._default_bc:
+            raise mgfea.MgfeaError("iterate_grad: default Dirichlet ring only (the reference's MultiGrid)")
+        accR = torch.zeros((rt.shape[0], 9), dtype=torch.float64, device=dev)
+        accP = torch.zeros((pt.shape[0], 9), dtype=torch.float64, device=dev)
+        gw0 = torch.zeros((), dtype=torch.float64, device=dev)
+        gw1 = torch.zeros((), dtype=torch.float64, device=dev)
+        g_t = as_field(g.detach().to(dev).contiguous())
+        g_s, g_f = [None] * L, [None] * L
+        # ---- up leg, fine -> coarse
+        for j in range(L - 1):
+            g_c, gf = _IterateFn._jac_adjoint(jacs[j], g_t)       # t_j = Jac(c_j, f_j)
+            g_f[j] = gf.store
+            g_s[j] = g_c.store                                     # c_j = s_j + w1 P(t_{j+1})
+            gj, gcj = jacs[j].grid_struct(g_c), jacs[j + 1].grid_struct(ts[j + 1])
+            check(lib().mgfea_prolong_wgrad(gj, gcj, pt.shape[0], w1, ts[j + 1].ptr, g_c.ptr, accP.data_ptr(), B, stream_ptr()))
+            if w1 != 0.0:
+                gw1 += ((cs[j].store - ss[j].store).double() * g_c.store.double()).sum() / w1
+            g_tn = Field(B, jacs[j + 1].nnode_edge, dev)
+            check(lib().mgfea_prolong_adjoint(gj, gcj, pt.data_ptr(), pt.shape[0], w1, g_c.ptr, g_tn.ptr, B, stream_ptr()))
+            g_t = g_tn
+        # ---- coarsest level: t = Jac(s, f), s = Jac(0, f)
+        g_sL, gf = _IterateFn._jac_adjoint(jacs[L - 1], g_t)
+        g_f[L - 1] = gf.store
+        g_a, gf2 = _IterateFn._jac_adjoint(jacs[L - 1], g_sL)
+        g_f[L - 1] = g_f[L - 1] + gf2.store
+        # ---- down leg, coarse -> fine
+        for j in range(L - 2, -1, -1):
+            gfn = Field(B, jacs[j + 1].nnode_edge, dev, store=g_f[j + 1].contiguous())   # dL/d f_{j+1}
+            gj, gcj = jacs[j].grid_struct(rs[j]), jacs[j + 1].grid_struct(gfn)
+            check(lib().mgfea_restrict_wgrad(gj, gcj, rt.shape[0], w0, rs[j].ptr, gfn.ptr, accR.data_ptr(), B, stream_ptr()))
+            if w0 != 0.0:
+                gw0 += (fs[j + 1].store.double() * gfn.store.double()).sum() / w0
+            g_r = Field(B, jacs[j].nnode_edge, dev)
+            check(lib().mgfea_restrict_adjoint(gj, gcj, rt.data_ptr(), rt.shape[0], w0, gfn.ptr, g_r.ptr, B, stream_ptr()))
+            kg = Field(B, jacs[j].nnode_edge, dev)                 # r_j = f_j - K s_j
+            check(lib().mgfea_stiffness_apply(gj, g_r.ptr, kg.ptr, B, stream_ptr()))
+            gs_tot = Field(B, jacs[j].nnode_edge, dev, store=g_s[j] - kg.store)
+            g_a, gf3 = _IterateFn._jac_adjoint(jacs[j], gs_tot)    # s_j = Jac(a_j, f_j)
+            g_f[j] = g_f[j] + g_r.store + gf3.store
+        Rs, Ps, Rd, Pd, wd, host = ctx.meta
+        gR = accR.to(torch.float32).reshape(Rs).to(Rd)
+        gP = accP.to(torch.float32).reshape(Ps).to(Pd)
+        gw = torch.stack([gw0, gw1]).to(torch.float32).to(wd)
+        gx = g_a.view.contiguous()
+        gf0 = Field(B, jacs[0].nnode_edge, dev, store=g_f[0].contiguous()).view.contiguous()
+        return (gx.cpu() if host else gx), (gf0.cpu() if host else gf0), None, gR, gP, gw

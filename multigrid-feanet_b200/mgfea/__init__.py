@@ -33,7 +33,8 @@ EXPORTS = [
     "mgfea_defect_f64", "mgfea_correct_f64", "mgfea_slab_defect_f64", "mgfea_slab_correct_f64", "mgfea_pattern_keys",
     "mgfea_widen_f64", "mgfea_slab_defect_f64_ext", "mgfea_slab_prolong_correct_smooth_push",
     "mgfea_elem_stiffness_apply", "mgfea_elem_residual", "mgfea_elem_smooth", "mgfea_elem_coarsen", "mgfea_sumsq_interior",
-    "mgfea_smooth_pbc", "mgfea_corr9",
+    "mgfea_smooth_pbc", "mgfea_corr9", "mgfea_restrict_adjoint", "mgfea_prolong_adjoint", "mgfea_restrict_wgrad",
+    "mgfea_prolong_wgrad",
 ]
 
 
@@ -155,6 +156,10 @@ def lib():
         L.mgfea_elem_smooth.argtypes = [vp, vp, vp, vp, f32, i32, i32, i64, i32, vp]
         L.mgfea_elem_coarsen.argtypes = [vp, vp, i32, i32, i32, vp]
         L.mgfea_sumsq_interior.argtypes = [vp, vp, i32, i32, i64, i32, vp]
+        L.mgfea_restrict_adjoint.argtypes = [G, G, vp, i32, f32, vp, vp, i32, vp]
+        L.mgfea_prolong_adjoint.argtypes = [G, G, vp, i32, f32, vp, vp, i32, vp]
+        L.mgfea_restrict_wgrad.argtypes = [G, G, i32, f32, vp, vp, vp, i32, vp]
+        L.mgfea_prolong_wgrad.argtypes = [G, G, i32, f32, vp, vp, vp, i32, vp]
         L.mgfea_corr9.argtypes = [vp, vp, vp, i32, i32, i64, i32, vp]
         L.mgfea_smooth_pbc.argtypes = [vp, vp, vp, vp, vp, i32, i32, i64, i32, i64, i32, vp]
         L.mgfea_widen_f64.argtypes = [vp, vp, i32, i32, i64, i32, i32, vp]

@@ -16,6 +16,7 @@
 #include "mgfea_stream.cuh"
 #include "mgfea_p2p.cuh"
 #include "mgfea_mid.cuh"
+#include "mgfea_adjoint.cuh"
 #include "mgfea_elem.cuh"
 #include "mgfea_f64.cuh"
 
@@ -2062,6 +2063,67 @@ int mgfea_smooth_pbc(const float *w9, const float *invd, const float *u_in, floa
                                                                   plane_f);
     g_launches.fetch_add(1);
     return (int)cudaGetLastError();
+}
+/* ---- backward of the table restriction / prolongation (mgfea_adjoint.cuh) ----------------------------------- */
+static int intergrid_adjoint(int mode, const mgfea_grid *g, const mgfea_grid *gc, const float *tab, int ntab, float scale,
+                             const float *fine, const float *coarse, float *out, double *acc, int B, void *stream) {
+    if (!g || !gc || !tab || (ntab != 1 && ntab != 16) || B < 1 || B > 65535) return MGFEA_EINVAL;
+    if (gc->N != (g->N - 1) / 2 + 1) return MGFEA_EINVAL;
+    AdjParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = g->N;
+    p.Nc = gc->N;
+    p.B = B;
+    p.pitch = g->pitch;
+    p.pitch_c = gc->pitch;
+    p.plane = g->plane;
+    p.plane_c = gc->plane;
+    p.keys = g->keys;
+    p.key_pitch = g->key_pitch;
+    p.keys_c = gc->keys;
+    p.key_pitch_c = gc->key_pitch;
+    p.ntab = ntab;
+    p.tab = tab;
+    p.scale = scale;
+    p.fine = fine;
+    p.coarse = coarse;
+    p.out = out;
+    p.acc = acc;
+    const dim3 block(32, 8);
+    const dim3 gf((unsigned)((g->pitch + 31) / 32), (unsigned)((g->N + 7) / 8), (unsigned)B);
+    const dim3 gcg((unsigned)((gc->pitch + 31) / 32), (unsigned)((gc->N + 7) / 8), (unsigned)B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == 0) {
+        if (!coarse || !out) return MGFEA_EINVAL;
+        intergrid_adjoint_kernel<0><<<gf, block, 0, st>>>(p);
+    } else if (mode == 1) {
+        if (!fine || !out) return MGFEA_EINVAL;
+        intergrid_adjoint_kernel<1><<<gcg, block, 0, st>>>(p);
+    } else {
+        if (!fine || !coarse || !acc) return MGFEA_EINVAL;
+        if (mode == 2) intergrid_wgrad_kernel<2><<<gcg, block, 0, st>>>(p);
+        else intergrid_wgrad_kernel<3><<<gcg, block, 0, st>>>(p);
+    }
+    g_launches.fetch_add(1);
+    return (int)cudaGetLastError();
+}
+int mgfea_restrict_adjoint(const mgfea_grid *g, const mgfea_grid *gc, const float *rtab, int rtab_n, float scale,
+                           const float *g_fc, float *g_r, int B, void *stream) {
+    return intergrid_adjoint(0, g, gc, rtab, rtab_n, scale, nullptr, g_fc, g_r, nullptr, B, stream);
+}
+int mgfea_prolong_adjoint(const mgfea_grid *g, const mgfea_grid *gc, const float *ptab, int ptab_n, float scale,
+                          const float *g_vf, float *g_vc, int B, void *stream) {
+    return intergrid_adjoint(1, g, gc, ptab, ptab_n, scale, g_vf, nullptr, g_vc, nullptr, B, stream);
+}
+int mgfea_restrict_wgrad(const mgfea_grid *g, const mgfea_grid *gc, int rtab_n, float scale, const float *r,
+                         const float *g_fc, double *acc, int B, void *stream) {
+    static const float dummy = 0.f;
+    return intergrid_adjoint(2, g, gc, &dummy, rtab_n, scale, r, g_fc, nullptr, acc, B, stream);
+}
+int mgfea_prolong_wgrad(const mgfea_grid *g, const mgfea_grid *gc, int ptab_n, float scale, const float *vc,
+                        const float *g_vf, double *acc, int B, void *stream) {
+    static const float dummy = 0.f;
+    return intergrid_adjoint(3, g, gc, &dummy, ptab_n, scale, g_vf, vc, nullptr, acc, B, stream);
 }
 int mgfea_corr9(const float *a, const float *g, double *acc9, int N, int pitch, int64_t plane, int B, void *stream) {
     if (!a || !g || !acc9 || N < 3 || pitch < N || B < 1 || B > 65535) return MGFEA_EINVAL;

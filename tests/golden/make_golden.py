@@ -605,6 +605,34 @@ def gen_hgrad():
     np.savez_compressed(os.path.join(OUT, "hgrad.npz"), **out)
 
 
+def gen_mggrad():
+    """one training step of the committed FEANet/multigrid.py MultiGrid (n_iter shim): q = qm(forward(F)); q.backward()
+    -> gradients of the 16-channel R / P kernels by the reference's own autograd (multigrid.py:98-100,132-157)"""
+    M = H.load_reference_multigrid_module()
+    out = {}
+    for n in (16, 32):
+        P4 = torch.tensor([[1, 2, 1], [2, 4, 2], [1, 2, 1]], dtype=torch.float32) / 4.0
+        R16 = torch.tensor([[1, 2, 1], [2, 4, 2], [1, 2, 1]], dtype=torch.float32) / 16.0
+        mg = M.MultiGrid(n, R16, P4, torch.tensor([4.0, 1.0]))
+        mg.w.requires_grad_(True)  # also record the gradient of the ratios (some shipped models have learned w)
+        gp = torch.Generator().manual_seed(3 + n)
+        with torch.no_grad():  # perturb so that the 16 channels differ
+            mg.conv.net.weight += 0.02 * torch.randn(mg.conv.net.weight.shape, generator=gp)
+            mg.deconv.net.weight += 0.02 * torch.randn(mg.deconv.net.weight.shape, generator=gp)
+        rs = np.random.RandomState(21 + n)
+        F = torch.from_numpy(rs.standard_normal((2, 1, n + 1, n + 1)).astype(np.float32))
+        np.random.seed(5)
+        u = mg(F)
+        q = mg.qm(u)
+        q.backward()
+        out[f"F_{n}"], out[f"R_{n}"], out[f"P_{n}"] = t2n(F), t2n(mg.conv.net.weight), t2n(mg.deconv.net.weight)
+        out[f"u_{n}"], out[f"q_{n}"] = t2n(u), np.array([q.item()])
+        out[f"gR_{n}"], out[f"gP_{n}"], out[f"gw_{n}"] = t2n(mg.conv.net.weight.grad), t2n(mg.deconv.net.weight.grad), t2n(mg.w.grad)
+        print("mggrad", n, q.item(), float(mg.conv.net.weight.grad.abs().max()), float(mg.deconv.net.weight.grad.abs().max()),
+              mg.w.grad.tolist())
+    np.savez_compressed(os.path.join(OUT, "mggrad.npz"), **out)
+
+
 def gen_h5manifest():
     """names / shapes / dtypes / data hashes of the reference's HDF5 files as read by the product's own reader
     (FEANet/h5lite.py), cross-checked against the byte-scanning reader this harness has used since round 1"""
@@ -631,7 +659,7 @@ def gen_h5manifest():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["mesh", "ops", "solve", "bands", "testpoisson", "pbc", "hgrad", "h5"]
+    which = sys.argv[1:] or ["mesh", "ops", "solve", "bands", "testpoisson", "pbc", "hgrad", "mggrad", "h5"]
     if "mesh" in which:
         gen_mesh()
     if "ops" in which:
@@ -646,5 +674,7 @@ if __name__ == "__main__":
         gen_pbc()
     if "hgrad" in which:
         gen_hgrad()
+    if "mggrad" in which:
+        gen_mggrad()
     if "h5" in which:
         gen_h5manifest()

@@ -1118,3 +1118,41 @@ def test_hnet_training_reduces_loss(tmp_path):
     loader = DeviceBatchLoader(IsoPoissonDataSet(path), batch_size=3)
     losses = [it.TrainSingleEpoch(loader, k_range=(4, 4)) for _ in range(12)]
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+
+
+MGG = np.load(os.path.join(G, "mggrad.npz"))
+
+
+@pytest.mark.parametrize("n", [16, 32])
+def test_multigrid_training_step_matches_reference_autograd(n):
+    """FEANet.multigrid.MultiGrid in training mode: q = qm(forward(F)); q.backward() -- the last cycle is differentiable
+    (MultiGrid.iterate_grad), gradients of the 16-channel restriction / prolongation kernels and of the ratios w against the
+    reference's own autograd (tests/golden/mggrad.npz; multigrid.py:98-100,132-157)"""
+    from FEANet.multigrid import MultiGrid
+
+    P4 = torch.tensor([[1, 2, 1], [2, 4, 2], [1, 2, 1]], dtype=torch.float32) / 4.0
+    mg = MultiGrid(n, P4 / 4, P4, torch.tensor([4.0, 1.0]))
+    mg.w.requires_grad_(True)
+    with torch.no_grad():
+        mg.conv.net.weight.copy_(torch.from_numpy(MGG[f"R_{n}"]))
+        mg.deconv.net.weight.copy_(torch.from_numpy(MGG[f"P_{n}"]))
+    np.random.seed(5)  # random_sampling draws the initial iterate from numpy's global stream, like the reference
+    u = mg(cuda(MGG[f"F_{n}"]))
+    ref_u = MGG[f"u_{n}"]
+    assert np.abs(host(u) - ref_u).max() <= 5e-5 * np.abs(ref_u).max()
+    # the differentiable cycle is the fused cycle, bit for bit
+    with torch.no_grad():
+        exact(host(mg.iterate_grad(mg.v_m0, mg.f)), host(mg.iterate(mg.v_m0, mg.f)), "iterate_grad forward == fused iterate")
+    q = mg.qm(u)
+    assert abs(q.item() - float(MGG[f"q_{n}"][0])) <= 2e-4 * float(MGG[f"q_{n}"][0])
+    q.backward()
+    for name, got, ref in (("R", mg.conv.net.weight.grad, MGG[f"gR_{n}"]), ("P", mg.deconv.net.weight.grad, MGG[f"gP_{n}"]),
+                           ("w", mg.w.grad, MGG[f"gw_{n}"])):
+        got = got.detach().cpu().numpy()
+        assert got.shape == ref.shape
+        assert np.abs(got - ref).max() <= 2e-3 * np.abs(ref).max(), (name, np.abs(got - ref).max(), np.abs(ref).max())
+    # inference is unchanged: no autograd, detached fused cycle
+    with torch.no_grad():
+        np.random.seed(5)
+        u2 = mg(cuda(MGG[f"F_{n}"]))
+    assert not u2.requires_grad and np.abs(host(u2) - ref_u).max() <= 5e-5 * np.abs(ref_u).max()
