@@ -94,7 +94,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-NCU_PROFILE = "r01_ncu_full_stream2_final.json"
+NCU_PROFILE = "r02_ncu_full_stream2.json"
 
 
 def ncu_traffic(kernel_prefix, grid=None):
@@ -103,9 +103,12 @@ def ncu_traffic(kernel_prefix, grid=None):
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", NCU_PROFILE)))
         for name, d in prof.items():
-            if name.startswith(kernel_prefix) and (grid is None or f"({grid}," in name):
-                mb = float(d["dram__bytes_read.sum"].split()[0]) + float(d["dram__bytes_write.sum"].split()[0])
-                return int(mb * 1e6)
+            if kernel_prefix in name and (grid is None or f"({grid}," in name):
+                def mb(v):
+                    x, unit = v.split()[0], (v.split() + [""])[1].lower()
+                    return float(x) * {"gbyte": 1e9, "mbyte": 1e6, "kbyte": 1e3, "byte": 1.0}.get(unit, 1e6)
+
+                return int(mb(d["dram__bytes_read.sum"]) + mb(d["dram__bytes_write.sum"]))
     except Exception:
         pass
     return None

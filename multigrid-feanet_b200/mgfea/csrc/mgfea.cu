@@ -731,6 +731,7 @@ struct Knobs {
     int th = 32, stages = 1, ctas = 0, threads = 256;
     int stream_min_n = 129;   // levels with N >= this use the register-chained streaming kernels (0 disables)
     int stream_r = 0;         // rows per strip (0 = auto)
+    int stream_rmin = 2;      // auto: never shorter than this (short strips pay 5 halo rows + pipeline fill each)
     int stream_packed = 1;    // 1: FFMA2 (fma.rn.f32x2) streaming kernels, 0: scalar FFMA
     int stream_keys = 0;      // 1: two-phase levels also stream (see stream_eligible)
     int tile_minb2 = 1;       // 1: tile programs limited to <= 2 CTAs per SM by shared memory use the 128-register build
@@ -748,6 +749,7 @@ struct Knobs {
         if (const char *e = getenv("MGFEA_CTAS")) ctas = atoi(e);
         if (const char *e = getenv("MGFEA_STREAM_MIN_N")) stream_min_n = atoi(e);
         if (const char *e = getenv("MGFEA_STREAM_R")) stream_r = atoi(e);
+        if (const char *e = getenv("MGFEA_STREAM_RMIN")) stream_rmin = atoi(e);
         if (const char *e = getenv("MGFEA_STREAM_PACKED")) stream_packed = atoi(e);
         if (const char *e = getenv("MGFEA_STREAM_KEYS")) stream_keys = atoi(e);
         if (const char *e = getenv("MGFEA_TILE_MINB2")) tile_minb2 = atoi(e);
@@ -835,6 +837,7 @@ static int run_stream(const Program &pr, cudaStream_t st) {
         for (int c = 2; c <= 256; c *= 2)  // powers of two divide N-1 = 2^k exactly
             if (abs(c - R) < abs(best - R)) best = c;
         R = best;
+        while (R < knobs().stream_rmin && R * 2 <= g->N - 1) R *= 2;
     }
     if (R < 2) R = 2;
     R &= ~1;

@@ -806,7 +806,9 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
                 float4 uv = ZERO_INIT ? make_float4(0.f, 0.f, 0.f, 0.f) : ring_u[slot];
                 const bool arow_in = !EDGE || (a >= 1 && a <= N - 2);
                 if (MODE == 1) {
-                    // u += reset(bilinear P v_c) on row a
+                    // u += reset(bilinear P v_c) on row a.  fl(a/2 + b/2) is written fma(0.5, a, 0.5 b): halving is exact, so
+                    // this is the same single rounding of the exact sum as the reference's mul, mul, add -- one FMA-pipe
+                    // instruction less per value (the up leg is FMA-pipe bound)
                     const float2 cv = ring_c[slot];
                     const float c2 = __shfl_down_sync(0xffffffffu, cv.x, 1);
                     if (!EDGE || (a >= 0 && a <= N - 1)) {
@@ -816,13 +818,13 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
                             vt[1] = cv.y;
                             vt[2] = c2;
                             e.x = vt[0];
-                            e.y = __fadd_rn(__fmul_rn(0.5f, vt[0]), __fmul_rn(0.5f, vt[1]));
+                            e.y = __fmaf_rn(0.5f, vt[0], __fmul_rn(0.5f, vt[1]));
                             e.z = vt[1];
-                            e.w = __fadd_rn(__fmul_rn(0.5f, vt[1]), __fmul_rn(0.5f, vt[2]));
+                            e.w = __fmaf_rn(0.5f, vt[1], __fmul_rn(0.5f, vt[2]));
                         } else {  // a odd: between coarse rows (a-1)/2 (vt, kept from the previous step) and (a+1)/2
                             const float vb0 = cv.x, vb1 = cv.y, vb2 = c2;
-                            e.x = __fadd_rn(__fmul_rn(0.5f, vt[0]), __fmul_rn(0.5f, vb0));
-                            e.z = __fadd_rn(__fmul_rn(0.5f, vt[1]), __fmul_rn(0.5f, vb1));
+                            e.x = __fmaf_rn(0.5f, vt[0], __fmul_rn(0.5f, vb0));
+                            e.z = __fmaf_rn(0.5f, vt[1], __fmul_rn(0.5f, vb1));
                             if (p.prolong_seq) {
                                 float v = __fadd_rn(__fmul_rn(0.25f, vt[0]), __fmul_rn(0.25f, vt[1]));
                                 v = __fadd_rn(v, __fmul_rn(0.25f, vb0));
@@ -831,12 +833,12 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
                                 v = __fadd_rn(v, __fmul_rn(0.25f, vb1));
                                 e.w = __fadd_rn(v, __fmul_rn(0.25f, vb2));
                             } else {
-                                const float ta = __fadd_rn(__fmul_rn(0.5f, vt[0]), __fmul_rn(0.5f, vt[1]));
-                                const float ba = __fadd_rn(__fmul_rn(0.5f, vb0), __fmul_rn(0.5f, vb1));
-                                e.y = __fadd_rn(__fmul_rn(0.5f, ta), __fmul_rn(0.5f, ba));
-                                const float tb = __fadd_rn(__fmul_rn(0.5f, vt[1]), __fmul_rn(0.5f, vt[2]));
-                                const float bb = __fadd_rn(__fmul_rn(0.5f, vb1), __fmul_rn(0.5f, vb2));
-                                e.w = __fadd_rn(__fmul_rn(0.5f, tb), __fmul_rn(0.5f, bb));
+                                const float ta = __fmaf_rn(0.5f, vt[0], __fmul_rn(0.5f, vt[1]));
+                                const float ba = __fmaf_rn(0.5f, vb0, __fmul_rn(0.5f, vb1));
+                                e.y = __fmaf_rn(0.5f, ta, __fmul_rn(0.5f, ba));
+                                const float tb = __fmaf_rn(0.5f, vt[1], __fmul_rn(0.5f, vt[2]));
+                                const float bb = __fmaf_rn(0.5f, vb1, __fmul_rn(0.5f, vb2));
+                                e.w = __fmaf_rn(0.5f, tb, __fmul_rn(0.5f, bb));
                             }
                         }
                         if (EDGE) e = mask4(e, arow_in ? cin : 0u);  // fine level's reset_boundary of the correction
