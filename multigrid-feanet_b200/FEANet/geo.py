@@ -21,13 +21,15 @@ class Geometry():
         g[0, 0, :, -1] = 0.0
         self.geometry_idx = g
         self.boundary_value = torch.zeros_like(g)
-        self.geometry_idx._mgfea_default_ring = True
-        self.boundary_value._mgfea_zero = True
+        # fast-path tags for JacobiBlock (index arithmetic instead of mask fields); they carry the tensors' version counters
+        # so that an in-place edit made behind set_square_bc's back invalidates them
+        self.geometry_idx._mgfea_default_ring = self.geometry_idx._version
+        self.boundary_value._mgfea_zero = self.boundary_value._version
 
     def set_square_bc(self, bc_values):
         '''Input bc is a 2D array, only the locations at boundaries have values'''
         self.boundary_value[:, :, :, :] = bc_values
-        self.boundary_value._mgfea_zero = False
+        self.boundary_value._mgfea_zero = None
 
     def l_shaped_geometry(self, nnode_edge, l_cutout_size=None):
         # The reference's L-shaped constructor is broken (geo.py:41 unpacks the None returned by square_geometry and

@@ -11,8 +11,9 @@ from .model import _like_input
 def _is_default_ring(geometry_idx, boundary_value):
     """True when the masks are the square ring with zero boundary values (geo.py:13-30): the kernels then use index
     arithmetic instead of reading mask fields.  Tagged tensors from FEANet.geo skip the O(N^2) comparison."""
-    if getattr(geometry_idx, "_mgfea_default_ring", False) and getattr(boundary_value, "_mgfea_zero", False):
-        return True
+    tg, tb = getattr(geometry_idx, "_mgfea_default_ring", None), getattr(boundary_value, "_mgfea_zero", None)
+    if tg is not None and tb is not None and tg == geometry_idx._version and tb == boundary_value._version:
+        return True  # untouched since FEANet.geo built them (an in-place edit bumps the version -> full comparison below)
     if geometry_idx.shape[0] != 1 or geometry_idx.shape != boundary_value.shape:
         return False
     g = geometry_idx.detach().cpu()
