@@ -14,6 +14,7 @@
 #include "mgfea_tile.cuh"
 #include "mgfea_tail.cuh"
 #include "mgfea_stream.cuh"
+#include "mgfea_hstream.cuh"
 #include "mgfea_p2p.cuh"
 #include "mgfea_mid.cuh"
 #include "mgfea_adjoint.cuh"
@@ -734,6 +735,8 @@ struct Knobs {
     int stream_rmin = 2;      // auto: never shorter than this (short strips pay 5 halo rows + pipeline fill each)
     int stream_packed = 1;    // 1: FFMA2 (fma.rn.f32x2) streaming kernels, 0: scalar FFMA
     int stream_keys = 0;      // 1: two-phase levels also stream (see stream_eligible)
+    int hstream_min_n = 0;    // learned-smoother levels with N >= this use mg_hstream_kernel (0 = off: see DESIGN)
+    int hstream_r = 0;        // rows per strip of mg_hstream_kernel (0 = auto)
     int tile_minb2 = 1;       // 1: tile programs limited to <= 2 CTAs per SM by shared memory use the 128-register build
     int mid_min_n = 66;       // coarse levels with mid_min_n <= N <= mid_max_n use the latency-oriented mid kernels
     int mid_max_n = 513;      // (mid_max_n = 0 disables them; at 1025 the streaming DOWN kernel wins: profiles/)
@@ -752,6 +755,8 @@ struct Knobs {
         if (const char *e = getenv("MGFEA_STREAM_RMIN")) stream_rmin = atoi(e);
         if (const char *e = getenv("MGFEA_STREAM_PACKED")) stream_packed = atoi(e);
         if (const char *e = getenv("MGFEA_STREAM_KEYS")) stream_keys = atoi(e);
+        if (const char *e = getenv("MGFEA_HSTREAM_MIN_N")) hstream_min_n = atoi(e);
+        if (const char *e = getenv("MGFEA_HSTREAM_R")) hstream_r = atoi(e);
         if (const char *e = getenv("MGFEA_TILE_MINB2")) tile_minb2 = atoi(e);
         if (const char *e = getenv("MGFEA_THREADS")) threads = atoi(e);
         threads = 256;
@@ -984,6 +989,137 @@ static int run_stream(const Program &pr, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// learned-smoother streaming kernels (mgfea_hstream.cuh): eligibility + launch
+static bool hstream_eligible(const Program &pr, bool keys, bool gbc) {
+    const int minn = knobs().hstream_min_n;
+    if (minn <= 0 || pr.g->N < minn || !(pr.g->N & 1)) return false;
+    if (gbc || pr.reset_only || pr.ktab_override || pr.slab || pr.push) return false;
+    if (pr.smoother != MGFEA_SMOOTH_HJACOBI || pr.nsweeps != 1 || pr.nlayers != HS_NL || !pr.hw) return false;
+    if (!pr.u_out || !pr.f) return false;
+    if (pr.out_mode == OUT_RESTRICT && pr.prolong_mode == 0)
+        return pr.fc && pr.rtab && (pr.rtab_n == 1 || (keys && pr.rtab_n == pr.g->npat));
+    if (pr.out_mode != OUT_NONE && pr.out_mode != OUT_NORM) return false;
+    if (!pr.u_in || !pr.vc || !pr.gc) return false;
+    if (pr.prolong_mode == MGFEA_PROLONG_BILINEAR) return true;
+    if (pr.prolong_mode == MGFEA_PROLONG_TABLE)
+        return pr.ptab && (pr.ptab_n == 1 || (pr.ptab_n == pr.gc->npat && (keys || !pr.gc->keys)));
+    return false;
+}
+
+static int run_hstream(const Program &pr, cudaStream_t st) {
+    const mgfea_grid *g = pr.g;
+    StreamParams p;
+    memset(&p, 0, sizeof(p));
+    const int mode = (pr.out_mode == OUT_RESTRICT) ? 0 : 1;
+    const bool keys = (g->keys != nullptr) && !pr.ignore_keys;
+    p.N = g->N;
+    p.B = pr.B;
+    p.pitch = g->pitch;
+    p.plane = g->plane;
+    p.ntx = (g->N + HS_TWI - 1) / HS_TWI;
+    p.Nc = (g->N - 1) / 2 + 1;
+    DeviceScratch *scr = nullptr;
+    int rc;
+    if ((rc = get_scratch(1, &scr))) return rc;
+    // rows per strip: about one resident wave of warps (1 CTA x 8 warps per SM); a strip recomputes 10 halo rows, so
+    // never shorter than 32 rows
+    int R = knobs().hstream_r;
+    if (R <= 0) {
+        const double slots = (double)scr->num_sms * HS_WARPS;
+        const double rt = (double)(g->N - 1) * p.ntx * pr.B / slots;
+        R = 32;
+        for (int c = 32; c <= 512; c *= 2)
+            if (fabs((double)c - rt) < fabs((double)R - rt)) R = c;
+    }
+    R &= ~1;
+    if (R < 2) R = 2;
+    while (R > g->N - 1) R /= 2;
+    p.R = R;
+    p.nry = (g->N - 1) / R;
+    if (p.nry < 1) p.nry = 1;
+    p.nstrips = p.ntx * p.nry;
+    const long long total = (long long)p.nstrips * pr.B;
+    if (total >= (1 << 24)) return MGFEA_EUNSUPPORTED;
+    p.row0 = 0;
+    p.nrloc = g->N;
+    p.own0 = 0;
+    p.own1 = g->N;
+    p.crow0 = 0;
+    p.nrc = p.Nc;
+    p.one = 1.0f;
+    p.inv_nstrips = 1.0f / (float)p.nstrips;
+    p.inv_ntx = 1.0f / (float)p.ntx;
+    p.u_in = pr.u_in;
+    p.u_out = pr.u_out;
+    p.f = pr.f;
+    p.ktab = g->ktab;
+    p.invd = g->invd;
+    p.hw = pr.hw;
+    p.npat = g->npat;
+    if (keys) {
+        if ((g->key_pitch & 15) || g->npat < 1 || g->npat > MAXPAT) return MGFEA_EALIGN;
+        p.keys = g->keys;
+        p.key_pitch = g->key_pitch;
+    }
+    if (mode == 0) {
+        if ((pr.pitch_c & 1) || (reinterpret_cast<uintptr_t>(pr.fc) & 7u)) return MGFEA_EALIGN;
+        p.fc = pr.fc;
+        p.pitch_c = pr.pitch_c;
+        p.plane_c = pr.plane_c;
+        p.rtab = pr.rtab;
+        p.rtab_n = pr.rtab_n;
+        p.r_has_scale = pr.r_has_scale;
+        p.r_scale = pr.r_scale;
+        p.r_scale_dev = pr.r_scale_dev;
+    } else {
+        if (pr.gc->N != p.Nc) return MGFEA_EINVAL;
+        if ((rc = check_field(pr.vc, pr.gc->pitch, pr.gc->plane))) return rc;
+        p.vc = pr.vc;
+        p.pitch_c = pr.gc->pitch;
+        p.plane_c = pr.gc->plane;
+        p.prolong_mode = pr.prolong_mode;
+        p.want_norm = (pr.out_mode == OUT_NORM);
+        if (pr.prolong_mode == MGFEA_PROLONG_TABLE) {
+            p.ptab = pr.ptab;
+            p.ptab_n = pr.ptab_n;
+            p.p_has_scale = pr.p_has_scale;
+            p.p_scale = pr.p_scale;
+            p.p_scale_dev = pr.p_scale_dev;
+            if (pr.ptab_n > 1 && pr.gc->keys) {
+                if (pr.gc->key_pitch & 15) return MGFEA_EALIGN;
+                p.keys_c = pr.gc->keys;
+                p.key_pitch_c = pr.gc->key_pitch;
+            }
+        }
+    }
+    if ((rc = get_scratch((size_t)total, &scr))) return rc;
+    p.partials = scr->tile_partials;
+    p.counter = scr->counter;
+    p.sumsq = pr.sumsq;
+    p.hist = pr.hist;
+    p.ctl = pr.ctl;
+    const size_t smem = hs_smem_bytes(mode, keys);
+    const long long ctas = (total + HS_WARPS - 1) / HS_WARPS;
+    const int grid = (int)(ctas < scr->num_sms ? ctas : scr->num_sms);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(mg_hstream_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs_smem_bytes(0, false));
+        cudaFuncSetAttribute(mg_hstream_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs_smem_bytes(0, true));
+        cudaFuncSetAttribute(mg_hstream_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs_smem_bytes(1, false));
+        cudaFuncSetAttribute(mg_hstream_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs_smem_bytes(1, true));
+        configured = true;
+    }
+    cudaError_t le;
+    if (mode == 0) le = keys ? launch_pdl(mg_hstream_kernel<0, true>, grid, HS_WARPS * 32, smem, st, p)
+                             : launch_pdl(mg_hstream_kernel<0, false>, grid, HS_WARPS * 32, smem, st, p);
+    else le = keys ? launch_pdl(mg_hstream_kernel<1, true>, grid, HS_WARPS * 32, smem, st, p)
+                   : launch_pdl(mg_hstream_kernel<1, false>, grid, HS_WARPS * 32, smem, st, p);
+    if (le != cudaSuccess) return (int)le;
+    g_launches.fetch_add(1);
+    return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // mid-level kernels (mgfea_mid.cuh): eligibility + launch
 static int mid_mode(const Program &pr, bool keys, bool gbc) {
     const Knobs &k = knobs();
@@ -1074,6 +1210,12 @@ static int run_program_(const Program &pr, cudaStream_t st) {
         if ((rc = check_field(pr.u_out, g->pitch, g->plane))) return rc;
         if ((rc = check_field(pr.f, g->pitch, g->plane))) return rc;
         return run_stream(pr, st);
+    }
+    if (hstream_eligible(pr, keys, gbc)) {
+        if (pr.u_in && (rc = check_field(pr.u_in, g->pitch, g->plane))) return rc;
+        if ((rc = check_field(pr.u_out, g->pitch, g->plane))) return rc;
+        if ((rc = check_field(pr.f, g->pitch, g->plane))) return rc;
+        return run_hstream(pr, st);
     }
     if (pr.u_in && (rc = check_field(pr.u_in, g->pitch, g->plane))) return rc;
     if (pr.u_out && (rc = check_field(pr.u_out, g->pitch, g->plane))) return rc;

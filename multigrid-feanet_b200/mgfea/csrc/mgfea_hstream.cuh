@@ -1,0 +1,672 @@
+// Streaming (register-chained) legs of the V-cycle for the LEARNED smoother (HJacIterator.HRelax + HNet.forward,
+// M-FEANet-mg_test.ipynb cells 4, 5) on two-phase or single-pattern meshes with table restriction / prolongation
+// (FEANet/multigrid.py:62-73, 124-130, 177-179) -- the config the tile programs run at 0.28 of the HBM roofline because
+// every HNet layer is one more barrier-separated pass over a shared-memory box.
+//
+// Same skeleton as mg_stream2_kernel (mgfea_stream.cuh): one WARP owns a strip of 128 box columns (lane l: columns
+// 4l..4l+3), marches down its rows, and every stage of the leg consumes the row the previous stage produced in the same
+// step from a rotating 3-row register window.  The chain is longer:
+//
+//   u row a -> J row a-1 (Jacobi), x = J - u -> L1 row a-3 -> L2 row a-5 -> L3 row a-7, u' = J + L3 (stored)
+//           -> r row a-9 (= f - K u') -> down leg: coarse f row (a-10)/2 (restriction) | up leg: sum r^2
+//
+// Every stage works on the rows its producer finished in EARLIER steps (a software pipeline: two rows of lag per stage), so
+// the five stencils of a step are independent instruction streams -- with one dependent chain through all stages a warp
+// needed ~1200 cycles per row (profiles/r02_cfg3iso_hstream_launches_v1.csv).  The data dependences are those of the
+// operators: column halo 8 (112 interior columns per strip), 6 rows above / 4 below a strip recomputed.
+// u, f (and the key map) are read from HBM once, u' is written once; the three HNet layers never leave the registers.
+// Weights of the current material pattern sit in registers; blocks of 6 rows that a material interface crosses take a
+// per-node lookup variant (as in mg_stream2_kernel<.., KEYS>).
+//
+// Arithmetic: operation order of oracle/mgfea_oracle.c (orc_hjacobi, orc_residual, orc_restrict, orc_prolong_table):
+// row-major FMA chains, explicit roundings.
+#pragma once
+#include "mgfea_stream.cuh"
+
+namespace mgfea {
+
+constexpr int HS_WARPS = 8;
+constexpr int HS_TWI = BW - 16;  // interior columns per strip (column halo 8 = chain depth 6, rounded to the lane width)
+constexpr int HS_RD = 12;        // u (and coarse) prefetch ring rows: two halves of 6, the unroll factor
+constexpr int HS_FD = 18;        // f ring rows (three thirds of 6): the residual stage re-reads f nine rows behind
+constexpr int HS_JD = 6;         // J delay line (rows): J row a-1 meets the last layer's row six steps later
+constexpr int HS_PD = 6;         // prefetch distance (rows)
+constexpr int HS_KD = 24;        // key ring rows (look-back 10 + the block being fetched)
+constexpr int HS_NL = 3;         // HNet layers
+// float4 units per lane: u ring, f ring, J delay line, coarse float2 ring (up leg)
+__host__ __device__ constexpr int hs_ring_f4(int mode) { return HS_RD + HS_FD + HS_JD + (mode == 1 ? HS_RD / 2 : 0); }
+__host__ __device__ constexpr size_t hs_smem_bytes(int mode, bool keys) {
+    return (size_t)HS_WARPS * ((size_t)hs_ring_f4(mode) * 32 * 16 + (keys ? (size_t)HS_KD * 32 * 4 : 0));
+}
+
+// keyed restriction: feed residual row values (columns 4l-1 .. 4l+3) into the lane's two coarse chains; taps 3*row..3*row+2
+// with the weight of every SOURCE node's pattern.  first: the chain starts with a product (row 0).
+__device__ __noinline__ void hs_restrict_feed_keys(const float *rtab, unsigned int w, int row, float rl, float4 r,
+                                                   float &acc0, float &acc1) {
+    const unsigned int l = __shfl_up_sync(0xffffffffu, w, 1);
+    const int k0 = (int)(l >> 24), k1 = (int)(w & 0xffu), k2 = (int)((w >> 8) & 0xffu), k3 = (int)((w >> 16) & 0xffu),
+              k4 = (int)(w >> 24);
+    const int t = 3 * row;
+    if (row == 0) {
+        acc0 = __fmul_rn(rtab[9 * k0 + t], rl);
+        acc1 = __fmul_rn(rtab[9 * k2 + t], r.y);
+    } else {
+        acc0 = __fmaf_rn(rtab[9 * k0 + t], rl, acc0);
+        acc1 = __fmaf_rn(rtab[9 * k2 + t], r.y, acc1);
+    }
+    acc0 = __fmaf_rn(rtab[9 * k1 + t + 1], r.x, acc0);
+    acc1 = __fmaf_rn(rtab[9 * k3 + t + 1], r.z, acc1);
+    acc0 = __fmaf_rn(rtab[9 * k2 + t + 2], r.y, acc0);
+    acc1 = __fmaf_rn(rtab[9 * k4 + t + 2], r.w, acc1);
+}
+
+// table prolongation of one fine row (ConvTranspose2d(C->1, 3, stride 2, pad 1), taps in (a asc, c asc) order):
+// top = coarse row floor(y/2), bot = coarse row (y+1)/2 (odd rows), each at coarse columns cxl, cxl+1, cxl+2;
+// kt / kb = pattern keys of those coarse nodes (all zero for a single table)
+__device__ __forceinline__ float4 hs_prolong_table(const float *P, bool odd, const float (&top)[3], const float (&bot)[3],
+                                                   const int (&kt)[3], const int (&kb)[3]) {
+    float e[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int jl = q >> 1;
+        float s;
+        if (!odd) {
+            if (!(q & 1)) {
+                s = __fmul_rn(P[9 * kt[jl] + 4], top[jl]);
+            } else {
+                s = __fmul_rn(P[9 * kt[jl + 1] + 3], top[jl + 1]);
+                s = __fmaf_rn(P[9 * kt[jl] + 5], top[jl], s);
+            }
+        } else {
+            if (!(q & 1)) {
+                s = __fmul_rn(P[9 * kb[jl] + 1], bot[jl]);
+                s = __fmaf_rn(P[9 * kt[jl] + 7], top[jl], s);
+            } else {
+                s = __fmul_rn(P[9 * kb[jl + 1] + 0], bot[jl + 1]);
+                s = __fmaf_rn(P[9 * kb[jl] + 2], bot[jl], s);
+                s = __fmaf_rn(P[9 * kt[jl + 1] + 6], top[jl + 1], s);
+                s = __fmaf_rn(P[9 * kt[jl] + 8], top[jl], s);
+            }
+        }
+        e[q] = s;
+    }
+    return make_float4(e[0], e[1], e[2], e[3]);
+}
+__device__ __noinline__ float4 hs_prolong_table_keys(const float *P, int odd, float t0, float t1, float t2, float b0,
+                                                     float b1, float b2, unsigned int wt, unsigned int wb) {
+    // wt / wb: this lane's two coarse keys (bytes 0, 1); the third comes from the next lane
+    const unsigned int nt = __shfl_down_sync(0xffffffffu, wt, 1), nb = __shfl_down_sync(0xffffffffu, wb, 1);
+    const float top[3] = {t0, t1, t2}, bot[3] = {b0, b1, b2};
+    const int kt[3] = {(int)(wt & 0xffu), (int)((wt >> 8) & 0xffu), (int)(nt & 0xffu)};
+    const int kb[3] = {(int)(wb & 0xffu), (int)((wb >> 8) & 0xffu), (int)(nb & 0xffu)};
+    return hs_prolong_table(P, odd != 0, top, bot, kt, kb);
+}
+
+// source-key indexed stencil of one row (blocks a material interface crosses): the row-major FMA chain of stencil_rows
+// with tab[key(source node)][tap]; inv4 = omega/d of the four centre nodes.  Out of line: the single-pattern path keeps
+// its registers.
+__device__ __noinline__ void hs_stencil_keys(const float *tab, const float *invt, unsigned int w0, unsigned int w1,
+                                             unsigned int w2, R6 t, R6 m, R6 b, float4 *ku, float4 *inv4) {
+    const K6 kt = key6(w0), km = key6(w1), kb = key6(w2);
+    float acc[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        float s = __fmul_rn(tab[9 * kt.k[e] + 0], t.a[e]);
+        s = __fmaf_rn(tab[9 * kt.k[e + 1] + 1], t.a[e + 1], s);
+        s = __fmaf_rn(tab[9 * kt.k[e + 2] + 2], t.a[e + 2], s);
+        s = __fmaf_rn(tab[9 * km.k[e] + 3], m.a[e], s);
+        s = __fmaf_rn(tab[9 * km.k[e + 1] + 4], m.a[e + 1], s);
+        s = __fmaf_rn(tab[9 * km.k[e + 2] + 5], m.a[e + 2], s);
+        s = __fmaf_rn(tab[9 * kb.k[e] + 6], b.a[e], s);
+        s = __fmaf_rn(tab[9 * kb.k[e + 1] + 7], b.a[e + 1], s);
+        s = __fmaf_rn(tab[9 * kb.k[e + 2] + 8], b.a[e + 2], s);
+        acc[e] = s;
+    }
+    *ku = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *inv4 = make_float4(invt[km.k[1]], invt[km.k[2]], invt[km.k[3]], invt[km.k[4]]);
+}
+
+// MODE 0: down leg (HNet sweep, store u, residual, table restriction -> fc); p.u_in == NULL: zero initial guess
+// MODE 1: up leg   (bilinear / table prolongation + correction, HNet sweep, store u, optional interior residual norm)
+template <int MODE, bool KEYS>
+__global__ void __launch_bounds__(HS_WARPS * 32, 1) mg_hstream_kernel(const StreamParams p) {
+    extern __shared__ __align__(16) unsigned char st_smem[];
+    __shared__ double red[HS_WARPS];
+    __shared__ int lastflag;
+    __shared__ float s_tab[KEYS ? MAXPAT * 9 : 1];                 // stiffness tables of all patterns
+    __shared__ float s_inv[KEYS ? MAXPAT : 1];                     // omega / d per pattern
+    __shared__ float s_rp[MAXPAT * 9];                             // restriction (MODE 0) / prolongation (MODE 1) tables
+    pdl_launch_dependents();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int N = p.N;
+    const int ntab = (MODE == 0) ? p.rtab_n : p.ptab_n;  // 1, or one table per pattern
+    const float *gtab = (MODE == 0) ? p.rtab : p.ptab;
+    const bool ptable = (MODE == 1) && (p.prolong_mode == 3);
+    const bool pkeys = ptable && ntab > 1 && p.keys_c != nullptr;  // coarse-node keys select the prolongation table
+    const bool rkeys = KEYS && (MODE == 0) && ntab > 1;
+
+    // ---- weights in registers for the whole kernel (pattern 0; two-phase strips reload on a pattern change)
+    // (scalar FFMA, not the packed FFMA2 of mg_stream2_kernel: on B200 an FFMA2 occupies the FMA pipe exactly as long as
+    // two FFMAs (tools/ubench/fma_pipe.cu: 1.70 vs 0.85 cycles per warp instruction), and keeping rows as overlapping
+    // register PAIRS cost ~85 MOVs per row step here -- this chain is FMA-pipe bound, not issue bound)
+    float kw[9], hw[HS_NL][9];
+    float tw[9];  // restriction (down leg) / prolongation (up leg, table mode) taps of the current pattern
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+        kw[q] = p.ktab[q];
+        tw[q] = (gtab != nullptr) ? gtab[q] : 0.0f;
+#pragma unroll
+        for (int l = 0; l < HS_NL; ++l) hw[l][q] = p.hw[9 * l + q];
+    }
+    float inv = p.invd[0];
+    const float tscale = (MODE == 0) ? (p.r_has_scale ? (p.r_scale_dev ? *p.r_scale_dev : p.r_scale) : 1.0f)
+                                     : (p.p_has_scale ? (p.p_scale_dev ? *p.p_scale_dev : p.p_scale) : 1.0f);
+    const bool has_scale = (MODE == 0) ? (p.r_has_scale != 0) : (p.p_has_scale != 0);
+    if (KEYS) {
+        for (int i = threadIdx.x; i < MAXPAT * 9; i += HS_WARPS * 32) s_tab[i] = (i < p.npat * 9) ? p.ktab[i] : 0.0f;
+        if (threadIdx.x < MAXPAT) s_inv[threadIdx.x] = (threadIdx.x < p.npat) ? p.invd[threadIdx.x] : 0.0f;
+    }
+    for (int i = threadIdx.x; i < MAXPAT * 9; i += HS_WARPS * 32) s_rp[i] = (gtab != nullptr && i < ntab * 9) ? gtab[i] : 0.0f;
+    __syncthreads();
+    int kcur = 0, ccur = 0;  // fine / coarse pattern whose weights sit in kw, inv (and tw)
+    pdl_wait();
+    const int solve_done = (p.ctl != nullptr) ? ld_volatile_s32(&reinterpret_cast<const Ctl *>(p.ctl)->done) : 0;
+    const bool zero = (p.u_in == nullptr);
+
+    constexpr int PD = HS_PD;
+    constexpr int RF4 = hs_ring_f4(MODE);
+    float4 *ring_u = reinterpret_cast<float4 *>(st_smem) + warp * (RF4 * 32);
+    float4 *ring_f = ring_u + HS_RD * 32;
+    float4 *ring_j = ring_f + HS_FD * 32;  // per-lane delay line: every lane reads back what it wrote itself
+    float2 *ring_c = reinterpret_cast<float2 *>(ring_j + HS_JD * 32);
+    unsigned int *ring_k = reinterpret_cast<unsigned int *>(st_smem + HS_WARPS * RF4 * 32 * 16) + warp * (HS_KD * 32);
+
+    const int total = p.nstrips * p.B;
+    for (int s = blockIdx.x * HS_WARPS + warp; s < total; s += gridDim.x * HS_WARPS) {
+        int b = 0, rem = s;
+        if (p.B > 1) {
+            b = __float2int_rz(__int2float_rn(s) * p.inv_nstrips);
+            int r0 = s - b * p.nstrips;
+            if (r0 < 0) {
+                --b;
+                r0 += p.nstrips;
+            } else if (r0 >= p.nstrips) {
+                ++b;
+                r0 -= p.nstrips;
+            }
+            rem = r0;
+        }
+        int ry = __float2int_rz(__int2float_rn(rem) * p.inv_ntx);
+        int tx = rem - ry * p.ntx;
+        if (tx < 0) {
+            --ry;
+            tx += p.ntx;
+        } else if (tx >= p.ntx) {
+            ++ry;
+            tx -= p.ntx;
+        }
+        const int y0 = ry * p.R;                              // R is even
+        const int y1 = (ry == p.nry - 1) ? N : y0 + p.R;      // exclusive
+        const int gx = tx * HS_TWI - 8 + 4 * lane;            // first global column of this lane
+        const bool lane_int = (lane >= 2 && lane <= 29);
+        unsigned int cin = 0, cdom = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (gx + e >= 1 && gx + e <= N - 2) cin |= 1u << e;
+            if (gx + e >= 0 && gx + e <= N - 1) cdom |= 1u << e;
+        }
+        const bool col_ok = (gx >= 0) && (gx + 3 < p.pitch);
+        const float *ub = zero ? nullptr : p.u_in + (long long)b * p.plane + gx;
+        const float *fb = p.f + (long long)b * p.plane + gx;
+        float *uo = p.u_out + (long long)b * p.plane + gx;
+        const int cxl = gx >> 1;  // coarse column of this lane's first fine column (gx is a multiple of 4)
+        const bool ccol_ok = (MODE == 1) && (cxl >= 0) && (cxl + 1 < p.pitch_c);
+        const float *cbp = (MODE == 1) ? p.vc + (long long)b * p.plane_c + cxl : nullptr;
+        float *fco = (MODE == 0) ? p.fc + (long long)b * p.plane_c + cxl : nullptr;
+        const bool fc_ok = lane_int && cxl >= 0 && cxl <= p.Nc - 1;
+
+        // first streamed row (data dependences only): the down leg's first coarse row y0/2 needs r row y0-1 <- u' y0-2 <-
+        // u y0-6 (even start); the up leg's first residual row y0 needs u' y0-1 <- u y0-5 (odd start: the row parity
+        // drives the prolongation)
+        const int a0 = (MODE == 0) ? y0 - 6 : y0 - 5;
+        // last step: the stage that finishes last.  Down leg: the restriction centred on fine row y1-2 closes with r row
+        // y1-1 = a-9 (the last strip also writes the coarse ring row (N-1)/2, closed by r row N); up leg: norm row y1-1 =
+        // a-9, else the store of u' row y1-1 = a-7
+        const int alast = (MODE == 0) ? (y1 == N ? N + 9 : y1 + 8) : (p.want_norm ? y1 + 8 : y1 + 6);
+        const int K = alast - a0 + 1;
+        const bool edge = (a0 <= 0) || (alast >= N - 1) || (tx == 0) || ((tx + 1) * HS_TWI + 8 >= N - 1);
+        const int klo = 0 - a0;               // first k whose row is inside the domain
+        const int khi = min(N - a0, K);       // one past the last such k
+        const float *pf_u = zero ? nullptr : ub + (long long)a0 * p.pitch;
+        const float *pf_f = fb + (long long)a0 * p.pitch;
+        int kpf = 0;
+        auto fetch_keys = [&](int keyrow0) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const int kr = keyrow0 + j, gy = a0 + kr;
+                const bool okk = (gx >= 0 && gx + 3 < p.key_pitch && gy >= 0 && gy < N);
+                const void *src = okk ? (const void *)(p.keys + (long long)gy * p.key_pitch + gx) : (const void *)p.f;
+                const uint32_t sz = okk ? 4u : 0u;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(&ring_k[(kr % HS_KD) * 32 + lane])),
+                             "l"(src), "r"(sz)
+                             : "memory");
+            }
+        };
+        // prefetch of streamed row kpf into u-ring row `su`, f-ring row `sf`
+        auto prefetch = [&](auto check_tag, int su, int sf) {
+            constexpr bool CHECK = decltype(check_tag)::value;
+            const bool ok = !CHECK || (col_ok && kpf >= klo && kpf < khi);
+            if (!zero) st_cp16(&ring_u[su * 32 + lane], ok ? (const void *)pf_u : (const void *)p.f, ok);
+            st_cp16(&ring_f[sf * 32 + lane], ok ? (const void *)pf_f : (const void *)p.f, ok);
+            if (MODE == 1) {  // coarse row ceil(a/2)
+                const int I = (a0 + kpf + 1) >> 1;
+                const bool okc = !CHECK || (ccol_ok && (I >= 0) && (I < p.Nc) && kpf < K);
+                const void *src = okc ? (const void *)(cbp + (long long)I * p.pitch_c) : (const void *)p.f;
+                const uint32_t sz = okc ? 8u : 0u;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(&ring_c[su * 32 + lane])), "l"(src),
+                             "r"(sz)
+                             : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (!zero) pf_u += p.pitch;
+            pf_f += p.pitch;
+            ++kpf;
+        };
+        // coarse keys of the lane's coarse columns cxl, cxl+1 on coarse row I (two bytes), 0 outside
+        auto coarse_keys = [&](int I) -> unsigned int {
+            if (!pkeys || I < 0 || I >= p.Nc || cxl < 0 || cxl + 1 >= p.key_pitch_c) return 0u;
+            return (unsigned int)__ldg(reinterpret_cast<const unsigned short *>(p.keys_c + (long long)I * p.key_pitch_c + cxl));
+        };
+        if (KEYS) fetch_keys(0);
+#pragma unroll
+        for (int k = 0; k < PD; ++k) prefetch(std::true_type{}, k, k);  // at k0 = 0 streamed row k sits in ring row k
+        if (solve_done) break;
+
+        // rotating 3-row windows; slot (ph+2)%3 is the one the producer overwrites in this step
+        R6 A[3], X0[3], X1[3], X2[3], Bw[3];
+        float4 rawv = make_float4(0.f, 0.f, 0.f, 0.f);  // un-reset input row a-1 (edge strips)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) A[i].a[j] = X0[i].a[j] = X1[i].a[j] = X2[i].a[j] = Bw[i].a[j] = 0.0f;
+        }
+        float racc0 = 0.f, racc1 = 0.f;
+        float *st_u = uo + (long long)(a0 - 7) * p.pitch;  // u' row a-7 at step 0
+        float *st_c = (MODE == 0) ? fco + (long long)((a0 - 10) / 2) * p.pitch_c : nullptr;  // coarse row (a-10)/2
+        float vt[3] = {0.f, 0.f, 0.f};  // coarse row floor(a/2) at coarse columns cxl .. cxl+2 (up leg)
+        unsigned int kvt = 0;            // its keys (lane's two bytes)
+        unsigned int ckw[3] = {0u, 0u, 0u}, ckn[3] = {0u, 0u, 0u};  // coarse keys of this / the next block's 3 coarse rows
+        double part = 0.0;
+        if (MODE == 1 && a0 >= 1) {  // odd first row: its upper coarse row
+            const int I = a0 >> 1;
+            const float *row = p.vc + (long long)b * p.plane_c + (long long)I * p.pitch_c;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int c = cxl + q;
+                vt[q] = (c >= 0 && c < p.Nc && I >= 0 && I < p.Nc) ? __ldg(row + c) : 0.0f;
+            }
+            kvt = coarse_keys(I);
+        }
+        if (MODE == 1 && pkeys) {
+            const int I0 = (a0 + 1) >> 1;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) ckw[j] = coarse_keys(I0 + j);
+        }
+
+        auto block6 = [&](auto guard_tag, auto edge_tag, auto pf_tag, auto keyed_tag, int k0) {
+            constexpr bool GUARD = decltype(guard_tag)::value;
+            constexpr bool EDGE = decltype(edge_tag)::value;
+            constexpr bool KEYED = decltype(keyed_tag)::value;
+            const int blk = k0 / 6;
+            // u / coarse ring: two halves; streamed row k0 + d, d in [0, 11]
+            const int uc = (blk & 1) * 6, un = 6 - uc;
+            auto urow = [&](int d) { return d < 6 ? uc + d : un + d - 6; };
+            // f ring: three thirds; streamed row k0 + d, d in [-12, 11]
+            const int t3 = blk % 3;
+            const int fc_ = t3 * 6, fn = ((t3 + 1) % 3) * 6, fp = ((t3 + 2) % 3) * 6;
+            auto frow = [&](int d) { return d < -6 ? fn + d + 12 : (d < 0 ? fp + d + 6 : (d < 6 ? fc_ + d : fn + d - 6)); };
+            auto krow = [&](int k) { return ((k + HS_KD) % HS_KD) * 32 + lane; };
+            if (MODE == 1 && pkeys) {  // the next block's coarse keys: a whole block of latency to hide
+                const int I0n = (a0 + k0 + 6 + 1) >> 1;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) ckn[j] = coarse_keys(I0n + j);
+            }
+#pragma unroll
+            for (int ph = 0; ph < 6; ++ph) {
+                const int k = k0 + ph;
+                if (GUARD && k >= K) break;
+                const int a = a0 + k;
+                if (KEYS && ph == 0) fetch_keys(k0 + 6);
+                prefetch(pf_tag, urow(ph + PD), frow(ph + PD));
+                asm volatile("cp.async.wait_group %0;" ::"n"(PD) : "memory");
+                // window slots before this step's producers write: oldest (ph+2)%3, middle ph%3, newest (ph+1)%3
+                // ================= stage 5: residual row a-9 from the u' rows of earlier steps
+                if ((MODE == 0 || p.want_norm) && (!GUARD || k >= 10)) {
+                    const int yr = a - 9;
+                    const R6 &t = Bw[(ph + 2) % 3], &m = Bw[ph % 3], &bq = Bw[(ph + 1) % 3];  // rows a-10, a-9, a-8
+                    float4 ku;
+                    if (KEYED) {
+                        float4 iv;
+                        hs_stencil_keys(s_tab, s_inv, ring_k[krow(k - 10)], ring_k[krow(k - 9)], ring_k[krow(k - 8)], t, m, bq,
+                                        &ku, &iv);
+                    } else {
+                        ku = stencil_rows(kw, t, m, bq);
+                    }
+                    const float4 f2 = ring_f[frow(ph - 9) * 32 + lane];
+                    float4 r;
+                    r.x = __fsub_rn(f2.x, ku.x);
+                    r.y = __fsub_rn(f2.y, ku.y);
+                    r.z = __fsub_rn(f2.z, ku.z);
+                    r.w = __fsub_rn(f2.w, ku.w);
+                    if (MODE == 1) {
+                        if (lane_int && (!GUARD || (yr >= y0 && yr < y1)) && (!EDGE || (yr >= 1 && yr <= N - 2))) {
+                            const float4 q = EDGE ? mask4(r, cin) : r;
+                            float s4 = __fmul_rn(q.x, q.x);
+                            s4 = __fmaf_rn(q.y, q.y, s4);
+                            s4 = __fmaf_rn(q.z, q.z, s4);
+                            s4 = __fmaf_rn(q.w, q.w, s4);
+                            part += (double)s4;
+                        }
+                    } else {
+                        // restriction fed row by row (row-major taps).  a0 is even: k even <=> residual row a-9 odd = bottom
+                        // row of the coarse stencil centred on fine row a-10 and top row of the next one
+                        const float rl = __shfl_up_sync(0xffffffffu, r.w, 1);  // column 4l-1
+                        const unsigned int kwr = (KEYED && rkeys) ? ring_k[krow(k - 9)] : 0u;
+                        if ((ph & 1) == 0) {
+                            if (!GUARD || k >= 12) {
+                                const int yc = a - 10;
+                                float c0, c1;
+                                if (KEYED && rkeys) {
+                                    c0 = racc0;
+                                    c1 = racc1;
+                                    hs_restrict_feed_keys(s_rp, kwr, 2, rl, r, c0, c1);
+                                } else {
+                                    c0 = __fmaf_rn(tw[6], rl, racc0);
+                                    c1 = __fmaf_rn(tw[6], r.y, racc1);
+                                    c0 = __fmaf_rn(tw[7], r.x, c0);
+                                    c1 = __fmaf_rn(tw[7], r.z, c1);
+                                    c0 = __fmaf_rn(tw[8], r.y, c0);
+                                    c1 = __fmaf_rn(tw[8], r.w, c1);
+                                }
+                                if (has_scale) {
+                                    c0 = __fmul_rn(tscale, c0);
+                                    c1 = __fmul_rn(tscale, c1);
+                                }
+                                if (EDGE) {
+                                    const int I = yc >> 1;
+                                    const bool Iin = (I >= 1 && I <= p.Nc - 2);
+                                    c0 = (Iin && cxl >= 1 && cxl <= p.Nc - 2) ? c0 : 0.0f;
+                                    c1 = (Iin && cxl + 1 >= 1 && cxl + 1 <= p.Nc - 2) ? c1 : 0.0f;
+                                }
+                                st_global_v2_pred(st_c, c0, c1, fc_ok && (!GUARD || (yc >= y0 && yc < y1)));
+                            }
+                            if (KEYED && rkeys) {
+                                hs_restrict_feed_keys(s_rp, kwr, 0, rl, r, racc0, racc1);
+                            } else {
+                                racc0 = __fmul_rn(tw[0], rl);
+                                racc1 = __fmul_rn(tw[0], r.y);
+                                racc0 = __fmaf_rn(tw[1], r.x, racc0);
+                                racc1 = __fmaf_rn(tw[1], r.z, racc1);
+                                racc0 = __fmaf_rn(tw[2], r.y, racc0);
+                                racc1 = __fmaf_rn(tw[2], r.w, racc1);
+                            }
+                        } else {
+                            if (KEYED && rkeys) {
+                                hs_restrict_feed_keys(s_rp, kwr, 1, rl, r, racc0, racc1);
+                            } else {
+                                racc0 = __fmaf_rn(tw[3], rl, racc0);
+                                racc1 = __fmaf_rn(tw[3], r.y, racc1);
+                                racc0 = __fmaf_rn(tw[4], r.x, racc0);
+                                racc1 = __fmaf_rn(tw[4], r.z, racc1);
+                                racc0 = __fmaf_rn(tw[5], r.y, racc0);
+                                racc1 = __fmaf_rn(tw[5], r.w, racc1);
+                            }
+                        }
+                    }
+                }
+                // ================= stage 4: HNet layer 3 row a-7, u' = J + h, store; new u' row into Bw
+                if (!GUARD || k >= 8) {
+                    const int y = a - 7;
+                    float4 h = stencil_rows(hw[2], X2[(ph + 2) % 3], X2[ph % 3], X2[(ph + 1) % 3]);  // rows a-8, a-7, a-6
+                    if (EDGE) h = mask4(h, (y >= 1 && y <= N - 2) ? cin : 0u);
+                    const float4 jv = ring_j[ph * 32 + lane];  // J row a-7
+                    const float4 o = make_float4(__fadd_rn(jv.x, h.x), __fadd_rn(jv.y, h.y), __fadd_rn(jv.z, h.z),
+                                                 __fadd_rn(jv.w, h.w));
+                    const bool st_ok = lane_int && (!GUARD || (y >= y0 && y < y1)) && (!EDGE || (cdom & 1u));
+                    st_global_v4_pred(st_u, o.x, o.y, o.z, o.w, st_ok);
+                    Bw[(ph + 2) % 3] = widen(o);
+                }
+                // ================= stage 3: layer 2 row a-5
+                if (!GUARD || k >= 6) {
+                    float4 h = stencil_rows(hw[1], X1[(ph + 2) % 3], X1[ph % 3], X1[(ph + 1) % 3]);  // rows a-6, a-5, a-4
+                    if (EDGE) h = mask4(h, (a - 5 >= 1 && a - 5 <= N - 2) ? cin : 0u);
+                    X2[(ph + 2) % 3] = widen(h);
+                }
+                // ================= stage 2: layer 1 row a-3
+                if (!GUARD || k >= 4) {
+                    float4 h = stencil_rows(hw[0], X0[(ph + 2) % 3], X0[ph % 3], X0[(ph + 1) % 3]);  // rows a-4, a-3, a-2
+                    if (EDGE) h = mask4(h, (a - 3 >= 1 && a - 3 <= N - 2) ? cin : 0u);
+                    X1[(ph + 2) % 3] = widen(h);
+                }
+                // ================= stage 0: input row a (+ prolongation / correction on the up leg)
+                float4 uv = zero ? make_float4(0.f, 0.f, 0.f, 0.f) : ring_u[urow(ph) * 32 + lane];
+                const bool arow_in = !EDGE || (a >= 1 && a <= N - 2);
+                if (MODE == 1) {
+                    const float2 cv = ring_c[urow(ph) * 32 + lane];
+                    const float c2 = __shfl_down_sync(0xffffffffu, cv.x, 1);
+                    const bool odd = (ph & 1) == 0;  // a0 is odd
+                    const unsigned int kb = pkeys ? ckw[ph >> 1] : 0u;  // keys of coarse row ceil(a/2) (a odd at ph = 0)
+                    if (!EDGE || (a >= 0 && a <= N - 1)) {
+                        float4 e;
+                        if (ptable) {
+                            float top[3], bot[3];
+                            if (!odd) {
+                                vt[0] = cv.x;
+                                vt[1] = cv.y;
+                                vt[2] = c2;
+                                kvt = kb;
+                            }
+                            top[0] = vt[0];
+                            top[1] = vt[1];
+                            top[2] = vt[2];
+                            bot[0] = cv.x;
+                            bot[1] = cv.y;
+                            bot[2] = c2;
+                            if (KEYED) {
+                                e = hs_prolong_table_keys(s_rp, odd ? 1 : 0, top[0], top[1], top[2], bot[0], bot[1], bot[2],
+                                                          kvt, kb);
+                            } else {
+                                const int kz[3] = {0, 0, 0};
+                                e = hs_prolong_table(tw, odd, top, bot, kz, kz);
+                            }
+                            if (has_scale) {
+                                e.x = __fmul_rn(tscale, e.x);
+                                e.y = __fmul_rn(tscale, e.y);
+                                e.z = __fmul_rn(tscale, e.z);
+                                e.w = __fmul_rn(tscale, e.w);
+                            }
+                        } else {
+                            // bilinear: fl(a/2 + b/2) == fma(0.5, a, 0.5 b) (halving is exact)
+                            if (!odd) {
+                                vt[0] = cv.x;
+                                vt[1] = cv.y;
+                                vt[2] = c2;
+                                e.x = vt[0];
+                                e.y = __fmaf_rn(0.5f, vt[0], __fmul_rn(0.5f, vt[1]));
+                                e.z = vt[1];
+                                e.w = __fmaf_rn(0.5f, vt[1], __fmul_rn(0.5f, vt[2]));
+                            } else {
+                                const float vb0 = cv.x, vb1 = cv.y, vb2 = c2;
+                                e.x = __fmaf_rn(0.5f, vt[0], __fmul_rn(0.5f, vb0));
+                                e.z = __fmaf_rn(0.5f, vt[1], __fmul_rn(0.5f, vb1));
+                                const float ta = __fmaf_rn(0.5f, vt[0], __fmul_rn(0.5f, vt[1]));
+                                const float ba = __fmaf_rn(0.5f, vb0, __fmul_rn(0.5f, vb1));
+                                e.y = __fmaf_rn(0.5f, ta, __fmul_rn(0.5f, ba));
+                                const float tb = __fmaf_rn(0.5f, vt[1], __fmul_rn(0.5f, vt[2]));
+                                const float bb = __fmaf_rn(0.5f, vb1, __fmul_rn(0.5f, vb2));
+                                e.w = __fmaf_rn(0.5f, tb, __fmul_rn(0.5f, bb));
+                            }
+                            if (EDGE) e = mask4(e, arow_in ? cin : 0u);  // fine level's reset_boundary of the correction
+                        }
+                        uv.x = __fadd_rn(uv.x, e.x);
+                        uv.y = __fadd_rn(uv.y, e.y);
+                        uv.z = __fadd_rn(uv.z, e.z);
+                        uv.w = __fadd_rn(uv.w, e.w);
+                        if (EDGE) uv = mask4(uv, cdom);
+                    } else if (!odd) {  // row outside the domain: still advance the carried coarse row
+                        vt[0] = cv.x;
+                        vt[1] = cv.y;
+                        vt[2] = c2;
+                        kvt = kb;
+                    }
+                }
+                // x = J - (un-reset u): keep the raw row of edge strips; reset_boundary of the sweep's input
+                const float4 rawp = rawv;  // raw row a-1
+                if (EDGE) {
+                    rawv = uv;
+                    uv = mask4(uv, arow_in ? cin : 0u);
+                }
+                A[(ph + 2) % 3] = widen(uv);
+                // ================= stage 1: Jacobi row a-1, x = J - u; J into the delay line (read above by stage 4)
+                if (!GUARD || k >= 2) {
+                    const int y = a - 1;
+                    const R6 &t = A[(ph + 0) % 3], &m = A[(ph + 1) % 3], &bq = A[(ph + 2) % 3];
+                    float4 ku, iv = make_float4(inv, inv, inv, inv);
+                    if (KEYED) hs_stencil_keys(s_tab, s_inv, ring_k[krow(k - 2)], ring_k[krow(k - 1)], ring_k[krow(k)], t, m, bq, &ku, &iv);
+                    else ku = stencil_rows(kw, t, m, bq);
+                    const float4 ff = ring_f[frow(ph - 1) * 32 + lane];
+                    // u + inv * (f - K u): separate mul and add (two roundings, as the reference)
+                    float4 j;
+                    j.x = __fadd_rn(__fmul_rn(iv.x, __fsub_rn(ff.x, ku.x)), m.a[1]);
+                    j.y = __fadd_rn(__fmul_rn(iv.y, __fsub_rn(ff.y, ku.y)), m.a[2]);
+                    j.z = __fadd_rn(__fmul_rn(iv.z, __fsub_rn(ff.z, ku.z)), m.a[3]);
+                    j.w = __fadd_rn(__fmul_rn(iv.w, __fsub_rn(ff.w, ku.w)), m.a[4]);
+                    if (EDGE) j = mask4(j, (y >= 1 && y <= N - 2) ? cin : 0u);
+                    ring_j[ph * 32 + lane] = j;
+                    float4 x;
+                    x.x = __fsub_rn(j.x, EDGE ? rawp.x : m.a[1]);
+                    x.y = __fsub_rn(j.y, EDGE ? rawp.y : m.a[2]);
+                    x.z = __fsub_rn(j.z, EDGE ? rawp.z : m.a[3]);
+                    x.w = __fsub_rn(j.w, EDGE ? rawp.w : m.a[4]);
+                    X0[(ph + 2) % 3] = widen(x);
+                }
+                st_u += p.pitch;
+                if (MODE == 0 && (ph & 1) == 0) st_c += p.pitch_c;
+            }
+            if (MODE == 1 && pkeys) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) ckw[j] = ckn[j];
+            }
+            if (KEYS && !EDGE) {  // a per-node block (always an EDGE variant) may follow: hand it the raw row (== the reset one)
+                rawv = make_float4(A[1].a[1], A[1].a[2], A[1].a[3], A[1].a[4]);
+            }
+        };
+        using T_ = std::true_type;
+        using F_ = std::false_type;
+        // steady state: pipeline full (the coarse row (a-10)/2 of the block's first step is >= y0/2: k0 >= 18 covers both
+        // legs) and every store row inside [y0, y1) (u' row a-7 <= y1-1 at the block's last step)
+        const int ksteady = y1 + 6 - a0;
+        int prev_key = -2, prev2_key = -2, prev_ckey = -2;  // uniform key of the previous blocks (-1 mixed, -2 none)
+        for (int k0 = 0; k0 < K; k0 += 6) {
+            bool fast = true;
+            if (KEYS) {
+                // this block's keys travel in the oldest outstanding group (fetched one block ago with row k0's prefetch)
+                asm volatile("cp.async.wait_group %0;" ::"n"(PD - 1) : "memory");
+                const unsigned int w0 = ring_k[(k0 % HS_KD) * 32 + lane];
+                const unsigned int pat = (__shfl_sync(0xffffffffu, w0, 0) & 0xffu) * 0x01010101u;
+                unsigned int diff = w0 ^ pat;
+#pragma unroll
+                for (int j = 1; j < 6; ++j) diff |= ring_k[((k0 + j) % HS_KD) * 32 + lane] ^ pat;
+                // the residual stage looks 10 rows back: the two previous blocks must carry the same single pattern
+                const int bkey = __all_sync(0xffffffffu, diff == 0u) ? (int)(pat & 0xffu) : -1;
+                fast = (bkey >= 0) && (prev_key == -2 || prev_key == bkey) && (prev2_key == -2 || prev2_key == bkey);
+                prev2_key = prev_key;
+                prev_key = bkey;
+                if (fast && bkey != kcur) {
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) {
+                        kw[q] = s_tab[9 * bkey + q];
+                        if (MODE == 0 && ntab > 1) tw[q] = s_rp[9 * bkey + q];
+                    }
+                    inv = s_inv[bkey];
+                    kcur = bkey;
+                }
+            }
+            if (MODE == 1 && pkeys) {  // the prolongation table follows the COARSE nodes' keys
+                const unsigned int pat = (__shfl_sync(0xffffffffu, ckw[0], 0) & 0xffu) * 0x0101u;
+                const unsigned int diff = (ckw[0] ^ pat) | (ckw[1] ^ pat) | (ckw[2] ^ pat) | (k0 == 0 ? (kvt ^ pat) : 0u);
+                const int ckey = __all_sync(0xffffffffu, diff == 0u) ? (int)(pat & 0xffu) : -1;
+                const bool cfast = (ckey >= 0) && (prev_ckey == -2 || prev_ckey == ckey);
+                prev_ckey = ckey;
+                if (fast && cfast && ckey != ccur) {
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) tw[q] = s_rp[9 * ckey + q];
+                    ccur = ckey;
+                }
+                fast = fast && cfast;
+            }
+            if (!fast) block6(T_{}, T_{}, T_{}, T_{}, k0);
+            else if (edge) block6(T_{}, T_{}, T_{}, F_{}, k0);
+            else if (k0 >= 18 && k0 + 5 <= ksteady && k0 + 5 + PD < khi) block6(F_{}, F_{}, F_{}, F_{}, k0);
+            else block6(T_{}, F_{}, T_{}, F_{}, k0);
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (MODE == 1 && p.want_norm) {
+            part = warp_sum_d(part);
+            if (lane == 0) p.partials[s] = part;
+        }
+    }
+
+    if (solve_done) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        return;
+    }
+    // ---- deterministic final reduction of the per-strip partial sums by the last CTA to finish
+    if (MODE == 1 && p.want_norm) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int ticket = atomicAdd(p.counter, 1u);
+            lastflag = (ticket == gridDim.x - 1) ? 1 : 0;
+        }
+        __syncthreads();
+        if (lastflag) {
+            __threadfence();
+            Ctl *ctl = reinterpret_cast<Ctl *>(p.ctl);
+            double tot = 0.0, mx = 0.0;
+            for (int b = 0; b < p.B; ++b) {
+                double v = 0.0;
+                for (int i = threadIdx.x; i < p.nstrips; i += blockDim.x)
+                    v += __ldcg(p.partials + (long long)b * p.nstrips + i);
+                v = warp_sum_d(v);
+                __syncthreads();
+                if (lane == 0) red[warp] = v;
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    double sum = 0.0;
+                    for (int w = 0; w < HS_WARPS; ++w) sum += red[w];
+                    if (p.sumsq) p.sumsq[b] = sum;
+                    if (ctl && p.hist && ctl->cycle < ctl->max_cycles) p.hist[(long long)ctl->cycle * p.B + b] = sum;
+                    tot += sum;
+                    mx = sum > mx ? sum : mx;
+                }
+            }
+            if (threadIdx.x == 0) {
+                if (ctl) {
+                    const int cyc = ctl->cycle + 1;
+                    ctl->cycle = cyc;
+                    const double metric = (ctl->conv_rule == 1) ? mx : tot;
+                    bool done = false;
+                    if (ctl->eps2 >= 0.0 && cyc >= ctl->min_cycles && metric <= ctl->eps2) done = true;
+                    if (cyc >= ctl->max_cycles) done = true;
+                    if (!(metric == metric) || metric > 1.7e308) done = true;
+                    if (done) ctl->done = 1;
+                }
+                *p.counter = 0u;
+                __threadfence();
+            }
+        }
+    }
+}
+
+}  // namespace mgfea

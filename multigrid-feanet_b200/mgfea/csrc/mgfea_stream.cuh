@@ -89,6 +89,16 @@ struct StreamParams {
     unsigned int *push_ticket;  // 2 local words (up, dn), left at 0
     unsigned int *push_flag_up, *push_flag_dn;
     int ctl_ro;  // row slabs: `ctl` is only read (done flag); the stopping rule belongs to the all-reduce step
+    // learned smoother + table transfer operators (mg_hstream_kernel, mgfea_hstream.cuh)
+    const float *hw;              // [3][9] HNet layer kernels
+    int rtab_n;                   // restriction tables: 1, or one per pattern (indexed by the fine source node's key)
+    int prolong_mode;             // MGFEA_PROLONG_BILINEAR | MGFEA_PROLONG_TABLE
+    const float *ptab;            // [ptab_n][9]
+    int ptab_n, p_has_scale;
+    float p_scale;
+    const float *p_scale_dev;
+    const unsigned char *keys_c;  // coarse level's key map (ptab_n > 1)
+    int key_pitch_c;
 };
 
 __device__ __forceinline__ double warp_sum_d(double v) {
