@@ -23,7 +23,7 @@ PROLONG_BILINEAR, PROLONG_TABLE = 1, 3
 CONV_SUM, CONV_MAX = 0, 1
 
 EXPORTS = [
-    "mgfea_version", "mgfea_error_string", "mgfea_set_loader", "mgfea_launch_count", "mgfea_pack", "mgfea_unpack",
+    "mgfea_version", "mgfea_error_string", "mgfea_set_loader", "mgfea_set_option", "mgfea_launch_count", "mgfea_pack", "mgfea_unpack",
     "mgfea_stiffness_apply", "mgfea_load_vector", "mgfea_split_x", "mgfea_reset_boundary", "mgfea_smooth",
     "mgfea_residual", "mgfea_restrict", "mgfea_smooth_residual_restrict", "mgfea_prolong_correct_smooth",
     "mgfea_residual_norm", "mgfea_vcycle", "mgfea_restrict_channels", "mgfea_prolong_channels",
@@ -129,6 +129,7 @@ def lib():
         vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
         G = ctypes.POINTER(Grid)
         L.mgfea_set_loader.argtypes = [i32]
+        L.mgfea_set_option.argtypes = [ctypes.c_char_p, i32]
         L.mgfea_trace.argtypes = [vp, i32]
         L.mgfea_pack.argtypes = [vp, vp, i32, i32, i64, i32, vp]
         L.mgfea_unpack.argtypes = [vp, vp, i32, i32, i64, i32, vp]
@@ -238,6 +239,15 @@ def launch_count() -> int:
 
 def set_loader(use_tma: bool) -> int:
     return int(lib().mgfea_set_loader(1 if use_tma else 0))
+
+
+def set_option(name: str, value: int) -> int:
+    """kernel-selection threshold `name` (see include/mgfea.h mgfea_set_option); returns the previous value.  Engines
+    that captured a CUDA graph keep replaying the kernels chosen at capture time."""
+    rc = int(lib().mgfea_set_option(name.encode(), int(value)))
+    if rc < 0:
+        raise MgfeaError(f"mgfea_set_option({name!r}): {rc}")
+    return rc
 
 
 # ----------------------------------------------------------------------------------------------------------

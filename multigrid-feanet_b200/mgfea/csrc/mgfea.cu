@@ -764,10 +764,11 @@ struct Knobs {
         if (stages != 2) stages = 1;
     }
 };
-static const Knobs &knobs() {
+static Knobs &knobs_mut() {
     static Knobs k;
     return k;
 }
+static const Knobs &knobs() { return knobs_mut(); }
 
 template <bool KEYS, bool GBC, int MINB>
 static cudaError_t launch_tile_(const TileMaps &maps, const TileParams &p, int grid, size_t smem, cudaStream_t st) {
@@ -1105,15 +1106,20 @@ static int run_hstream(const Program &pr, cudaStream_t st) {
     if (!configured) {
         cudaFuncSetAttribute(mg_hstream_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs_smem_bytes(0, false));
         cudaFuncSetAttribute(mg_hstream_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs_smem_bytes(0, true));
-        cudaFuncSetAttribute(mg_hstream_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs_smem_bytes(1, false));
-        cudaFuncSetAttribute(mg_hstream_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs_smem_bytes(1, true));
+        cudaFuncSetAttribute(mg_hstream_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs_smem_bytes(1, false));
+        cudaFuncSetAttribute(mg_hstream_kernel<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs_smem_bytes(1, true));
+        cudaFuncSetAttribute(mg_hstream_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs_smem_bytes(1, false));
+        cudaFuncSetAttribute(mg_hstream_kernel<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs_smem_bytes(1, true));
         configured = true;
     }
+    const bool ptab = (mode == 1) && (pr.prolong_mode == MGFEA_PROLONG_TABLE);
     cudaError_t le;
     if (mode == 0) le = keys ? launch_pdl(mg_hstream_kernel<0, true>, grid, HS_WARPS * 32, smem, st, p)
                              : launch_pdl(mg_hstream_kernel<0, false>, grid, HS_WARPS * 32, smem, st, p);
-    else le = keys ? launch_pdl(mg_hstream_kernel<1, true>, grid, HS_WARPS * 32, smem, st, p)
-                   : launch_pdl(mg_hstream_kernel<1, false>, grid, HS_WARPS * 32, smem, st, p);
+    else if (ptab) le = keys ? launch_pdl(mg_hstream_kernel<1, true, true>, grid, HS_WARPS * 32, smem, st, p)
+                             : launch_pdl(mg_hstream_kernel<1, false, true>, grid, HS_WARPS * 32, smem, st, p);
+    else le = keys ? launch_pdl(mg_hstream_kernel<1, true, false>, grid, HS_WARPS * 32, smem, st, p)
+                   : launch_pdl(mg_hstream_kernel<1, false, false>, grid, HS_WARPS * 32, smem, st, p);
     if (le != cudaSuccess) return (int)le;
     g_launches.fetch_add(1);
     return (int)cudaGetLastError();
@@ -1624,6 +1630,21 @@ int mgfea_trace(unsigned long long *buf, int capacity) {
     return 0;
 }
 int mgfea_set_loader(int use_tma) { return g_use_tma.exchange(use_tma ? 1 : 0); }
+int mgfea_set_option(const char *name, int value) {
+    if (!name) return MGFEA_EINVAL;
+    Knobs &k = knobs_mut();
+    int *slot = nullptr;
+    if (!strcmp(name, "hstream_min_n")) slot = &k.hstream_min_n;
+    else if (!strcmp(name, "hstream_r")) slot = &k.hstream_r;
+    else if (!strcmp(name, "stream_min_n")) slot = &k.stream_min_n;
+    else if (!strcmp(name, "stream_keys")) slot = &k.stream_keys;
+    else if (!strcmp(name, "mid_max_n")) slot = &k.mid_max_n;
+    else if (!strcmp(name, "mid_max_n_up")) slot = &k.mid_max_n_up;
+    if (!slot) return MGFEA_EINVAL;
+    const int prev = *slot;
+    *slot = value;
+    return prev < 0 ? 0 : prev;
+}
 uint64_t mgfea_launch_count(void) { return g_launches.load(); }
 
 int mgfea_pattern_keys(uint8_t *keys, int N, int key_pitch, int shape, void *stream) {

@@ -19,7 +19,8 @@
 // per-node lookup variant (as in mg_stream2_kernel<.., KEYS>).
 //
 // Arithmetic: operation order of oracle/mgfea_oracle.c (orc_hjacobi, orc_residual, orc_restrict, orc_prolong_table):
-// row-major FMA chains, explicit roundings.
+// row-major FMA chains, explicit roundings; FFMA2 computes two such chains side by side (half the issue slots: the
+// scalar formulation of the same chain measured 118 vs 86 us on the 4097^2 down leg, see DESIGN).
 #pragma once
 #include "mgfea_stream.cuh"
 
@@ -31,7 +32,7 @@ constexpr int HS_RD = 12;        // u (and coarse) prefetch ring rows: two halve
 constexpr int HS_FD = 18;        // f ring rows (three thirds of 6): the residual stage re-reads f nine rows behind
 constexpr int HS_JD = 6;         // J delay line (rows): J row a-1 meets the last layer's row six steps later
 constexpr int HS_PD = 6;         // prefetch distance (rows)
-constexpr int HS_KD = 24;        // key ring rows (look-back 10 + the block being fetched)
+constexpr int HS_KD = 32;        // key ring rows (look-back 10 + the block being fetched = 22, rounded to a power of two)
 constexpr int HS_NL = 3;         // HNet layers
 // float4 units per lane: u ring, f ring, J delay line, coarse float2 ring (up leg)
 __host__ __device__ constexpr int hs_ring_f4(int mode) { return HS_RD + HS_FD + HS_JD + (mode == 1 ? HS_RD / 2 : 0); }
@@ -102,38 +103,111 @@ __device__ __noinline__ float4 hs_prolong_table_keys(const float *P, int odd, fl
     return hs_prolong_table(P, odd != 0, top, bot, kt, kb);
 }
 
-// source-key indexed stencil of one row (blocks a material interface crosses): the row-major FMA chain of stencil_rows
-// with tab[key(source node)][tap]; inv4 = omega/d of the four centre nodes.  Out of line: the single-pattern path keeps
-// its registers.
-__device__ __noinline__ void hs_stencil_keys(const float *tab, const float *invt, unsigned int w0, unsigned int w1,
-                                             unsigned int w2, R6 t, R6 m, R6 b, float4 *ku, float4 *inv4) {
-    const K6 kt = key6(w0), km = key6(w1), kb = key6(w2);
+// Rows as STRIDE-2 column pairs: p[j] = (a[j], a[j+2]) for the 6 values a[0..5] = box columns 4l-1 .. 4l+4.  A stencil's
+// outputs pair up as A = (e0, e2), B = (e1, e3), which ARE the next stage's p[1] and p[2]: a new row costs two shuffles
+// and two register moves (p[0], p[3]).  With adjacent-column pairs (RP, mgfea_stream.cuh) two of the five pairs straddle
+// the output pairs and ptxas spent ~17 MOVs per row on them (85 of 233 instructions per step here).
+struct RS {
+    u64 p[4];
+};
+__device__ __forceinline__ void stencil_rowsS(const u64 (&w)[9], const RS &t, const RS &m, const RS &b, u64 &A, u64 &B) {
+    A = mul2(w[0], t.p[0]);
+    B = mul2(w[0], t.p[1]);
+    A = fma2(w[1], t.p[1], A);
+    B = fma2(w[1], t.p[2], B);
+    A = fma2(w[2], t.p[2], A);
+    B = fma2(w[2], t.p[3], B);
+    A = fma2(w[3], m.p[0], A);
+    B = fma2(w[3], m.p[1], B);
+    A = fma2(w[4], m.p[1], A);
+    B = fma2(w[4], m.p[2], B);
+    A = fma2(w[5], m.p[2], A);
+    B = fma2(w[5], m.p[3], B);
+    A = fma2(w[6], b.p[0], A);
+    B = fma2(w[6], b.p[1], B);
+    A = fma2(w[7], b.p[1], A);
+    B = fma2(w[7], b.p[2], B);
+    A = fma2(w[8], b.p[2], A);
+    B = fma2(w[8], b.p[3], B);
+}
+// A = (a1, a3), B = (a2, a4): the lane's four columns
+__device__ __forceinline__ RS widenS(u64 A, u64 B) {
+    float a1, a2, a3, a4;
+    unpack2(A, a1, a3);
+    unpack2(B, a2, a4);
+    const float a0 = __shfl_up_sync(0xffffffffu, a4, 1);
+    const float a5 = __shfl_down_sync(0xffffffffu, a1, 1);
+    RS o;
+    o.p[0] = pack2(a0, a2);
+    o.p[1] = A;
+    o.p[2] = B;
+    o.p[3] = pack2(a3, a5);
+    return o;
+}
+__device__ __forceinline__ void unpack_rowS(const RS &r, float (&a)[6]) {
+    unpack2(r.p[0], a[0], a[2]);
+    unpack2(r.p[1], a[1], a[3]);
+    float t;
+    unpack2(r.p[2], t, a[4]);
+    unpack2(r.p[3], t, a[5]);
+}
+// mask bits of the lane's columns 0..3 applied to A = (e0, e2), B = (e1, e3)
+__device__ __forceinline__ void hs_maskS(u64 &A, u64 &B, unsigned int m) {
+    float e0, e1, e2, e3;
+    unpack2(A, e0, e2);
+    unpack2(B, e1, e3);
+    e0 = (m & 1u) ? e0 : 0.0f;
+    e1 = (m & 2u) ? e1 : 0.0f;
+    e2 = (m & 4u) ? e2 : 0.0f;
+    e3 = (m & 8u) ? e3 : 0.0f;
+    A = pack2(e0, e2);
+    B = pack2(e1, e3);
+}
+
+// Source-key indexed stencil of one row, inline: the rows a material interface crosses.  tab4 = [pattern][stencil row]
+// float4 (taps dj = 0, 1, 2 of that row): ONE 16-byte shared-memory load per source node and stencil row instead of one
+// 4-byte load per tap.  Same row-major FMA chain per output as stencil_rowsS.  out = {K A, K B, inv A, inv B}.
+__device__ __forceinline__ void hs_stencil_keys(const float *tab4, const float *invt, unsigned int w0, unsigned int w1,
+                                                unsigned int w2, const RS &t, const RS &m, const RS &b, u64 *out) {
+    const float4 *T4 = reinterpret_cast<const float4 *>(tab4);
     float acc[4];
+    float cen[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        float s = __fmul_rn(tab[9 * kt.k[e] + 0], t.a[e]);
-        s = __fmaf_rn(tab[9 * kt.k[e + 1] + 1], t.a[e + 1], s);
-        s = __fmaf_rn(tab[9 * kt.k[e + 2] + 2], t.a[e + 2], s);
-        s = __fmaf_rn(tab[9 * km.k[e] + 3], m.a[e], s);
-        s = __fmaf_rn(tab[9 * km.k[e + 1] + 4], m.a[e + 1], s);
-        s = __fmaf_rn(tab[9 * km.k[e + 2] + 5], m.a[e + 2], s);
-        s = __fmaf_rn(tab[9 * kb.k[e] + 6], b.a[e], s);
-        s = __fmaf_rn(tab[9 * kb.k[e + 1] + 7], b.a[e + 1], s);
-        s = __fmaf_rn(tab[9 * kb.k[e + 2] + 8], b.a[e + 2], s);
-        acc[e] = s;
+    for (int r = 0; r < 3; ++r) {
+        const K6 kk = key6(r == 0 ? w0 : (r == 1 ? w1 : w2));
+        float a[6];
+        unpack_rowS(r == 0 ? t : (r == 1 ? m : b), a);
+        float4 w[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) w[j] = T4[3 * kk.k[j] + r];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            acc[e] = (r == 0) ? __fmul_rn(w[e].x, a[e]) : __fmaf_rn(w[e].x, a[e], acc[e]);
+            acc[e] = __fmaf_rn(w[e + 1].y, a[e + 1], acc[e]);
+            acc[e] = __fmaf_rn(w[e + 2].z, a[e + 2], acc[e]);
+        }
+        if (r == 1) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) cen[e] = invt[kk.k[e + 1]];
+        }
     }
-    *ku = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    *inv4 = make_float4(invt[km.k[1]], invt[km.k[2]], invt[km.k[3]], invt[km.k[4]]);
+    out[0] = pack2(acc[0], acc[2]);
+    out[1] = pack2(acc[1], acc[3]);
+    out[2] = pack2(cen[0], cen[2]);
+    out[3] = pack2(cen[1], cen[3]);
 }
 
 // MODE 0: down leg (HNet sweep, store u, residual, table restriction -> fc); p.u_in == NULL: zero initial guess
 // MODE 1: up leg   (bilinear / table prolongation + correction, HNet sweep, store u, optional interior residual norm)
-template <int MODE, bool KEYS>
+// PTAB (up leg): table prolongation (ConvTranspose taps) instead of bilinear -- compile-time: both variants inline in every
+// unrolled block overflowed the instruction caches (ncu: no_instruction was the top stall of the up leg)
+template <int MODE, bool KEYS, bool PTAB = false>
 __global__ void __launch_bounds__(HS_WARPS * 32, 1) mg_hstream_kernel(const StreamParams p) {
     extern __shared__ __align__(16) unsigned char st_smem[];
     __shared__ double red[HS_WARPS];
     __shared__ int lastflag;
     __shared__ float s_tab[KEYS ? MAXPAT * 9 : 1];                 // stiffness tables of all patterns
+    __shared__ __align__(16) float s_tab4[KEYS ? MAXPAT * 12 : 4];  // the same, one float4 per stencil row (per-node path)
     __shared__ float s_inv[KEYS ? MAXPAT : 1];                     // omega / d per pattern
     __shared__ float s_rp[MAXPAT * 9];                             // restriction (MODE 0) / prolongation (MODE 1) tables
     pdl_launch_dependents();
@@ -141,30 +215,37 @@ __global__ void __launch_bounds__(HS_WARPS * 32, 1) mg_hstream_kernel(const Stre
     const int N = p.N;
     const int ntab = (MODE == 0) ? p.rtab_n : p.ptab_n;  // 1, or one table per pattern
     const float *gtab = (MODE == 0) ? p.rtab : p.ptab;
-    const bool ptable = (MODE == 1) && (p.prolong_mode == 3);
+    constexpr bool ptable = (MODE == 1) && PTAB;
     const bool pkeys = ptable && ntab > 1 && p.keys_c != nullptr;  // coarse-node keys select the prolongation table
     const bool rkeys = KEYS && (MODE == 0) && ntab > 1;
 
     // ---- weights in registers for the whole kernel (pattern 0; two-phase strips reload on a pattern change)
-    // (scalar FFMA, not the packed FFMA2 of mg_stream2_kernel: on B200 an FFMA2 occupies the FMA pipe exactly as long as
-    // two FFMAs (tools/ubench/fma_pipe.cu: 1.70 vs 0.85 cycles per warp instruction), and keeping rows as overlapping
-    // register PAIRS cost ~85 MOVs per row step here -- this chain is FMA-pipe bound, not issue bound)
-    float kw[9], hw[HS_NL][9];
+    u64 kw2[9], h2[HS_NL][9];
     float tw[9];  // restriction (down leg) / prolongation (up leg, table mode) taps of the current pattern
 #pragma unroll
     for (int q = 0; q < 9; ++q) {
-        kw[q] = p.ktab[q];
+        const float w = p.ktab[q];
+        kw2[q] = pack2(w, w);
         tw[q] = (gtab != nullptr) ? gtab[q] : 0.0f;
 #pragma unroll
-        for (int l = 0; l < HS_NL; ++l) hw[l][q] = p.hw[9 * l + q];
+        for (int l = 0; l < HS_NL; ++l) {
+            const float h = p.hw[9 * l + q];
+            h2[l][q] = pack2(h, h);
+        }
     }
-    float inv = p.invd[0];
+    const float inv0 = p.invd[0];
+    u64 inv2 = pack2(inv0, inv0);
+    const u64 one2 = pack2(p.one, p.one);  // opaque 1.0f: see the Jacobi update
     const float tscale = (MODE == 0) ? (p.r_has_scale ? (p.r_scale_dev ? *p.r_scale_dev : p.r_scale) : 1.0f)
                                      : (p.p_has_scale ? (p.p_scale_dev ? *p.p_scale_dev : p.p_scale) : 1.0f);
     const bool has_scale = (MODE == 0) ? (p.r_has_scale != 0) : (p.p_has_scale != 0);
     if (KEYS) {
         for (int i = threadIdx.x; i < MAXPAT * 9; i += HS_WARPS * 32) s_tab[i] = (i < p.npat * 9) ? p.ktab[i] : 0.0f;
         if (threadIdx.x < MAXPAT) s_inv[threadIdx.x] = (threadIdx.x < p.npat) ? p.invd[threadIdx.x] : 0.0f;
+        for (int i = threadIdx.x; i < MAXPAT * 12; i += HS_WARPS * 32) {
+            const int pat = i / 12, r = (i % 12) >> 2, c = i & 3;
+            s_tab4[i] = (pat < p.npat && c < 3) ? p.ktab[9 * pat + 3 * r + c] : 0.0f;
+        }
     }
     for (int i = threadIdx.x; i < MAXPAT * 9; i += HS_WARPS * 32) s_rp[i] = (gtab != nullptr && i < ntab * 9) ? gtab[i] : 0.0f;
     __syncthreads();
@@ -283,12 +364,12 @@ __global__ void __launch_bounds__(HS_WARPS * 32, 1) mg_hstream_kernel(const Stre
         if (solve_done) break;
 
         // rotating 3-row windows; slot (ph+2)%3 is the one the producer overwrites in this step
-        R6 A[3], X0[3], X1[3], X2[3], Bw[3];
-        float4 rawv = make_float4(0.f, 0.f, 0.f, 0.f);  // un-reset input row a-1 (edge strips)
+        RS A[3], X0[3], X1[3], X2[3], Bw[3];
+        u64 rawlo = 0, rawhi = 0;  // un-reset input row a-1 (edge strips)
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
 #pragma unroll
-            for (int j = 0; j < 6; ++j) A[i].a[j] = X0[i].a[j] = X1[i].a[j] = X2[i].a[j] = Bw[i].a[j] = 0.0f;
+            for (int j = 0; j < 4; ++j) A[i].p[j] = X0[i].p[j] = X1[i].p[j] = X2[i].p[j] = Bw[i].p[j] = 0;
         }
         float racc0 = 0.f, racc1 = 0.f;
         float *st_u = uo + (long long)(a0 - 7) * p.pitch;  // u' row a-7 at step 0
@@ -343,21 +424,23 @@ __global__ void __launch_bounds__(HS_WARPS * 32, 1) mg_hstream_kernel(const Stre
                 // ================= stage 5: residual row a-9 from the u' rows of earlier steps
                 if ((MODE == 0 || p.want_norm) && (!GUARD || k >= 10)) {
                     const int yr = a - 9;
-                    const R6 &t = Bw[(ph + 2) % 3], &m = Bw[ph % 3], &bq = Bw[(ph + 1) % 3];  // rows a-10, a-9, a-8
-                    float4 ku;
+                    const RS &t = Bw[(ph + 2) % 3], &m = Bw[ph % 3], &bq = Bw[(ph + 1) % 3];  // rows a-10, a-9, a-8
+                    u64 rlo, rhi;
                     if (KEYED) {
-                        float4 iv;
-                        hs_stencil_keys(s_tab, s_inv, ring_k[krow(k - 10)], ring_k[krow(k - 9)], ring_k[krow(k - 8)], t, m, bq,
-                                        &ku, &iv);
+                        u64 out[4];
+                        hs_stencil_keys(s_tab4, s_inv, ring_k[krow(k - 10)], ring_k[krow(k - 9)], ring_k[krow(k - 8)], t, m, bq,
+                                        out);
+                        rlo = out[0];
+                        rhi = out[1];
                     } else {
-                        ku = stencil_rows(kw, t, m, bq);
+                        stencil_rowsS(kw2, t, m, bq, rlo, rhi);
                     }
                     const float4 f2 = ring_f[frow(ph - 9) * 32 + lane];
+                    rlo = sub2(pack2(f2.x, f2.z), rlo);  // (r0, r2)
+                    rhi = sub2(pack2(f2.y, f2.w), rhi);  // (r1, r3)
                     float4 r;
-                    r.x = __fsub_rn(f2.x, ku.x);
-                    r.y = __fsub_rn(f2.y, ku.y);
-                    r.z = __fsub_rn(f2.z, ku.z);
-                    r.w = __fsub_rn(f2.w, ku.w);
+                    unpack2(rlo, r.x, r.z);
+                    unpack2(rhi, r.y, r.w);
                     if (MODE == 1) {
                         if (lane_int && (!GUARD || (yr >= y0 && yr < y1)) && (!EDGE || (yr >= 1 && yr <= N - 2))) {
                             const float4 q = EDGE ? mask4(r, cin) : r;
@@ -427,26 +510,31 @@ __global__ void __launch_bounds__(HS_WARPS * 32, 1) mg_hstream_kernel(const Stre
                 // ================= stage 4: HNet layer 3 row a-7, u' = J + h, store; new u' row into Bw
                 if (!GUARD || k >= 8) {
                     const int y = a - 7;
-                    float4 h = stencil_rows(hw[2], X2[(ph + 2) % 3], X2[ph % 3], X2[(ph + 1) % 3]);  // rows a-8, a-7, a-6
-                    if (EDGE) h = mask4(h, (y >= 1 && y <= N - 2) ? cin : 0u);
-                    const float4 jv = ring_j[ph * 32 + lane];  // J row a-7
-                    const float4 o = make_float4(__fadd_rn(jv.x, h.x), __fadd_rn(jv.y, h.y), __fadd_rn(jv.z, h.z),
-                                                 __fadd_rn(jv.w, h.w));
+                    u64 lo, hi;
+                    stencil_rowsS(h2[2], X2[(ph + 2) % 3], X2[ph % 3], X2[(ph + 1) % 3], lo, hi);  // rows a-8, a-7, a-6
+                    if (EDGE) hs_maskS(lo, hi, (y >= 1 && y <= N - 2) ? cin : 0u);
+                    const ulonglong2 jv = *reinterpret_cast<const ulonglong2 *>(&ring_j[ph * 32 + lane]);  // J row a-7: (A, B)
+                    const u64 ul = add2(jv.x, lo), uh = add2(jv.y, hi);
+                    float o0, o1, o2, o3;
+                    unpack2(ul, o0, o2);
+                    unpack2(uh, o1, o3);
                     const bool st_ok = lane_int && (!GUARD || (y >= y0 && y < y1)) && (!EDGE || (cdom & 1u));
-                    st_global_v4_pred(st_u, o.x, o.y, o.z, o.w, st_ok);
-                    Bw[(ph + 2) % 3] = widen(o);
+                    st_global_v4_pred(st_u, o0, o1, o2, o3, st_ok);
+                    Bw[(ph + 2) % 3] = widenS(ul, uh);
                 }
                 // ================= stage 3: layer 2 row a-5
                 if (!GUARD || k >= 6) {
-                    float4 h = stencil_rows(hw[1], X1[(ph + 2) % 3], X1[ph % 3], X1[(ph + 1) % 3]);  // rows a-6, a-5, a-4
-                    if (EDGE) h = mask4(h, (a - 5 >= 1 && a - 5 <= N - 2) ? cin : 0u);
-                    X2[(ph + 2) % 3] = widen(h);
+                    u64 lo, hi;
+                    stencil_rowsS(h2[1], X1[(ph + 2) % 3], X1[ph % 3], X1[(ph + 1) % 3], lo, hi);  // rows a-6, a-5, a-4
+                    if (EDGE) hs_maskS(lo, hi, (a - 5 >= 1 && a - 5 <= N - 2) ? cin : 0u);
+                    X2[(ph + 2) % 3] = widenS(lo, hi);
                 }
                 // ================= stage 2: layer 1 row a-3
                 if (!GUARD || k >= 4) {
-                    float4 h = stencil_rows(hw[0], X0[(ph + 2) % 3], X0[ph % 3], X0[(ph + 1) % 3]);  // rows a-4, a-3, a-2
-                    if (EDGE) h = mask4(h, (a - 3 >= 1 && a - 3 <= N - 2) ? cin : 0u);
-                    X1[(ph + 2) % 3] = widen(h);
+                    u64 lo, hi;
+                    stencil_rowsS(h2[0], X0[(ph + 2) % 3], X0[ph % 3], X0[(ph + 1) % 3], lo, hi);  // rows a-4, a-3, a-2
+                    if (EDGE) hs_maskS(lo, hi, (a - 3 >= 1 && a - 3 <= N - 2) ? cin : 0u);
+                    X1[(ph + 2) % 3] = widenS(lo, hi);
                 }
                 // ================= stage 0: input row a (+ prolongation / correction on the up leg)
                 float4 uv = zero ? make_float4(0.f, 0.f, 0.f, 0.f) : ring_u[urow(ph) * 32 + lane];
@@ -521,34 +609,38 @@ __global__ void __launch_bounds__(HS_WARPS * 32, 1) mg_hstream_kernel(const Stre
                     }
                 }
                 // x = J - (un-reset u): keep the raw row of edge strips; reset_boundary of the sweep's input
-                const float4 rawp = rawv;  // raw row a-1
+                const u64 rawp_lo = rawlo, rawp_hi = rawhi;  // raw row a-1
                 if (EDGE) {
-                    rawv = uv;
+                    rawlo = pack2(uv.x, uv.z);
+                    rawhi = pack2(uv.y, uv.w);
                     uv = mask4(uv, arow_in ? cin : 0u);
                 }
-                A[(ph + 2) % 3] = widen(uv);
+                A[(ph + 2) % 3] = widenS(pack2(uv.x, uv.z), pack2(uv.y, uv.w));
                 // ================= stage 1: Jacobi row a-1, x = J - u; J into the delay line (read above by stage 4)
                 if (!GUARD || k >= 2) {
                     const int y = a - 1;
-                    const R6 &t = A[(ph + 0) % 3], &m = A[(ph + 1) % 3], &bq = A[(ph + 2) % 3];
-                    float4 ku, iv = make_float4(inv, inv, inv, inv);
-                    if (KEYED) hs_stencil_keys(s_tab, s_inv, ring_k[krow(k - 2)], ring_k[krow(k - 1)], ring_k[krow(k)], t, m, bq, &ku, &iv);
-                    else ku = stencil_rows(kw, t, m, bq);
-                    const float4 ff = ring_f[frow(ph - 1) * 32 + lane];
-                    // u + inv * (f - K u): separate mul and add (two roundings, as the reference)
-                    float4 j;
-                    j.x = __fadd_rn(__fmul_rn(iv.x, __fsub_rn(ff.x, ku.x)), m.a[1]);
-                    j.y = __fadd_rn(__fmul_rn(iv.y, __fsub_rn(ff.y, ku.y)), m.a[2]);
-                    j.z = __fadd_rn(__fmul_rn(iv.z, __fsub_rn(ff.z, ku.z)), m.a[3]);
-                    j.w = __fadd_rn(__fmul_rn(iv.w, __fsub_rn(ff.w, ku.w)), m.a[4]);
-                    if (EDGE) j = mask4(j, (y >= 1 && y <= N - 2) ? cin : 0u);
-                    ring_j[ph * 32 + lane] = j;
-                    float4 x;
-                    x.x = __fsub_rn(j.x, EDGE ? rawp.x : m.a[1]);
-                    x.y = __fsub_rn(j.y, EDGE ? rawp.y : m.a[2]);
-                    x.z = __fsub_rn(j.z, EDGE ? rawp.z : m.a[3]);
-                    x.w = __fsub_rn(j.w, EDGE ? rawp.w : m.a[4]);
-                    X0[(ph + 2) % 3] = widen(x);
+                    const RS &t = A[(ph + 0) % 3], &m = A[(ph + 1) % 3], &bq = A[(ph + 2) % 3];
+                    u64 klo_, khi_, ivlo = inv2, ivhi = inv2;
+                    if (KEYED) {
+                        u64 out[4];
+                        hs_stencil_keys(s_tab4, s_inv, ring_k[krow(k - 2)], ring_k[krow(k - 1)], ring_k[krow(k)], t, m, bq, out);
+                        klo_ = out[0];
+                        khi_ = out[1];
+                        ivlo = out[2];
+                        ivhi = out[3];
+                    } else {
+                        stencil_rowsS(kw2, t, m, bq, klo_, khi_);
+                    }
+                    const float4 fv = ring_f[frow(ph - 1) * 32 + lane];
+                    const ulonglong2 ff = make_ulonglong2(pack2(fv.x, fv.z), pack2(fv.y, fv.w));
+                    // u + inv * (f - K u) with TWO roundings: fma(p, 1, u) = fl(p + u), 1 is a launch parameter (ptxas would
+                    // contract mul + add into one FFMA2 otherwise; see mg_stream2_kernel)
+                    const u64 plo = mul2(ivlo, sub2(ff.x, klo_)), phi = mul2(ivhi, sub2(ff.y, khi_));
+                    u64 jl = fma2(plo, one2, m.p[1]), jh = fma2(phi, one2, m.p[2]);
+                    if (EDGE) hs_maskS(jl, jh, (y >= 1 && y <= N - 2) ? cin : 0u);
+                    *reinterpret_cast<ulonglong2 *>(&ring_j[ph * 32 + lane]) = make_ulonglong2(jl, jh);
+                    const u64 xl = sub2(jl, EDGE ? rawp_lo : m.p[1]), xh = sub2(jh, EDGE ? rawp_hi : m.p[2]);
+                    X0[(ph + 2) % 3] = widenS(xl, xh);
                 }
                 st_u += p.pitch;
                 if (MODE == 0 && (ph & 1) == 0) st_c += p.pitch_c;
@@ -556,9 +648,6 @@ __global__ void __launch_bounds__(HS_WARPS * 32, 1) mg_hstream_kernel(const Stre
             if (MODE == 1 && pkeys) {
 #pragma unroll
                 for (int j = 0; j < 3; ++j) ckw[j] = ckn[j];
-            }
-            if (KEYS && !EDGE) {  // a per-node block (always an EDGE variant) may follow: hand it the raw row (== the reset one)
-                rawv = make_float4(A[1].a[1], A[1].a[2], A[1].a[3], A[1].a[4]);
             }
         };
         using T_ = std::true_type;
@@ -585,10 +674,12 @@ __global__ void __launch_bounds__(HS_WARPS * 32, 1) mg_hstream_kernel(const Stre
                 if (fast && bkey != kcur) {
 #pragma unroll
                     for (int q = 0; q < 9; ++q) {
-                        kw[q] = s_tab[9 * bkey + q];
+                        const float w = s_tab[9 * bkey + q];
+                        kw2[q] = pack2(w, w);
                         if (MODE == 0 && ntab > 1) tw[q] = s_rp[9 * bkey + q];
                     }
-                    inv = s_inv[bkey];
+                    const float iv = s_inv[bkey];
+                    inv2 = pack2(iv, iv);
                     kcur = bkey;
                 }
             }
@@ -605,10 +696,16 @@ __global__ void __launch_bounds__(HS_WARPS * 32, 1) mg_hstream_kernel(const Stre
                 }
                 fast = fast && cfast;
             }
-            if (!fast) block6(T_{}, T_{}, T_{}, T_{}, k0);
-            else if (edge) block6(T_{}, T_{}, T_{}, F_{}, k0);
-            else if (k0 >= 18 && k0 + 5 <= ksteady && k0 + 5 + PD < khi) block6(F_{}, F_{}, F_{}, F_{}, k0);
-            else block6(T_{}, F_{}, T_{}, F_{}, k0);
+            const bool steady = (k0 >= 18 && k0 + 5 <= ksteady && k0 + 5 + PD < khi);
+            if (fast) {
+                if (edge) block6(T_{}, T_{}, T_{}, F_{}, k0);
+                else if (steady) block6(F_{}, F_{}, F_{}, F_{}, k0);
+                else block6(T_{}, F_{}, T_{}, F_{}, k0);
+            } else {
+                if (edge) block6(T_{}, T_{}, T_{}, T_{}, k0);
+                else if (steady) block6(F_{}, F_{}, F_{}, T_{}, k0);
+                else block6(T_{}, F_{}, T_{}, T_{}, k0);
+            }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (MODE == 1 && p.want_norm) {

@@ -1168,45 +1168,51 @@ def test_hstream_legs_bit_exact(O, case):
     from FEANet.drivers import _InterfaceSingleGrid
     from FEANet.solver import LINEAR_4, VCycleEngine
 
+    import mgfea
+
     n, L = 512, 7
     N = n + 1
     B = 2 if case.endswith("b2") else 1
     keys = case.startswith("keys")
-    rng = np.random.default_rng(7)
-    jit = lambda base: (base.reshape(1, 9) * (1.0 + 0.2 * rng.random((16, 9)))).astype(np.float32)
-    R16, P16 = jit(LINEAR_4 / np.float32(4.0)), jit(LINEAR_4)
-    if case == "iso_table1":
-        R16, P16 = R16[:1], P16[:1]
-    hw = (OPS["hnet_w"] * (1.0 + 0.1 * rng.random(OPS["hnet_w"].shape))).astype(np.float32)
-    from FEANet.drivers import HNet
+    prev = mgfea.set_option("hstream_min_n", 129)
+    try:
+        rng = np.random.default_rng(7)
+        jit = lambda base: (base.reshape(1, 9) * (1.0 + 0.2 * rng.random((16, 9)))).astype(np.float32)
+        R16, P16 = jit(LINEAR_4 / np.float32(4.0)), jit(LINEAR_4)
+        if case == "iso_table1":
+            R16, P16 = R16[:1], P16[:1]
+        hw = (OPS["hnet_w"] * (1.0 + 0.1 * rng.random(OPS["hnet_w"].shape))).astype(np.float32)
+        from FEANet.drivers import HNet
 
-    hnet = HNet(3)
-    hnet.load_state_dict({f"convLayers.{i}.weight": torch.from_numpy(hw[i]).reshape(1, 1, 3, 3) for i in range(3)})
-    prop = (1.0, 20.0)
-    if keys:
-        grids = [_InterfaceSingleGrid(2, n // 2 ** l, prop=prop, shape=0) for l in range(L)]
-        jacs = [g.jac for g in grids]
-        levels = O.make_levels(n, L, prop=prop, shape=0)
-    else:
-        jacs = iso_jacs(n, L)
-        levels = O.make_levels(n, L)
-    bil = case == "keys_bilinear"
-    kw = dict(prolong="bilinear") if bil else dict(prolong="table", ptab=P16, p_scale=1.0)
-    eng = VCycleEngine(jacs, B=B, smoother="hjac", hnet=hnet, rtab=R16, r_scale=4.0, **kw)
-    okw = dict(prolong="bilinear") if bil else dict(prolong="table", ptab=P16, p_scale=1.0)
-    cfg = O.CycleCfg(smoother="hjac", hw=hw, rtab=R16, r_scale=4.0, **okw)
-    g = torch.Generator().manual_seed(11)
-    u0 = torch.randn(B, 1, N, N, generator=g)
-    f = torch.randn(B, 1, N, N, generator=g) * 1e-2
-    eng.set_u(u0)
-    eng.set_f(f)
-    uo = u0.numpy()[:, 0].copy()
-    fo = f.numpy()[:, 0].copy()
-    for c in range(2):
-        eng.cycle()
-        uo = O.vcycle(levels, cfg, uo, fo)
-        exact(host(eng.solution)[:, 0], uo, f"hstream {case} u after cycle {c + 1}")
-        r = O.residual(uo, fo, levels[0].keys, levels[0].ktab)[:, 1:-1, 1:-1].astype(np.float64)
-        got = host(eng.sumsq)
-        for b in range(B):
-            assert abs(got[b] - (r[b] ** 2).sum()) <= 1e-6 * (r[b] ** 2).sum(), (case, c, b)
+        hnet = HNet(3)
+        hnet.load_state_dict({f"convLayers.{i}.weight": torch.from_numpy(hw[i]).reshape(1, 1, 3, 3) for i in range(3)})
+        prop = (1.0, 20.0)
+        if keys:
+            grids = [_InterfaceSingleGrid(2, n // 2 ** l, prop=prop, shape=0) for l in range(L)]
+            jacs = [g.jac for g in grids]
+            levels = O.make_levels(n, L, prop=prop, shape=0)
+        else:
+            jacs = iso_jacs(n, L)
+            levels = O.make_levels(n, L)
+        bil = case == "keys_bilinear"
+        kw = dict(prolong="bilinear") if bil else dict(prolong="table", ptab=P16, p_scale=1.0)
+        eng = VCycleEngine(jacs, B=B, smoother="hjac", hnet=hnet, rtab=R16, r_scale=4.0, **kw)
+        okw = dict(prolong="bilinear") if bil else dict(prolong="table", ptab=P16, p_scale=1.0)
+        cfg = O.CycleCfg(smoother="hjac", hw=hw, rtab=R16, r_scale=4.0, **okw)
+        g = torch.Generator().manual_seed(11)
+        u0 = torch.randn(B, 1, N, N, generator=g)
+        f = torch.randn(B, 1, N, N, generator=g) * 1e-2
+        eng.set_u(u0)
+        eng.set_f(f)
+        uo = u0.numpy()[:, 0].copy()
+        fo = f.numpy()[:, 0].copy()
+        for c in range(2):
+            eng.cycle()
+            uo = O.vcycle(levels, cfg, uo, fo)
+            exact(host(eng.solution)[:, 0], uo, f"hstream {case} u after cycle {c + 1}")
+            r = O.residual(uo, fo, levels[0].keys, levels[0].ktab)[:, 1:-1, 1:-1].astype(np.float64)
+            got = host(eng.sumsq)
+            for b in range(B):
+                assert abs(got[b] - (r[b] ** 2).sum()) <= 1e-6 * (r[b] ** 2).sum(), (case, c, b)
+    finally:
+        mgfea.set_option("hstream_min_n", prev)
