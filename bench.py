@@ -324,6 +324,35 @@ def secondary_configs(which):
                                     steps=10, reset=lambda: eng.u[0].zero_())
             del eng, grids
             torch.cuda.empty_cache()
+    if "cfg3_single_pattern" in which:
+        # config 3's operators (learned HNet smoother, 16-channel linear R/P, w = [4, 1]) on a SINGLE-material mesh, the
+        # setting M-FEANet-mg_test.ipynb trains its HNet in: the finest level runs on the register-chained streaming
+        # kernels (csrc/mgfea_hstream.cuh); on the two-phase mesh above they are opt-in (slower than the tile programs)
+        n, L, B = 4096, 12, 1
+        grids = [SingleGrid(2, n // 2 ** l) for l in range(L)]
+        hnet = HNet(3)
+        hnet.load_state_dict({f"convLayers.{i}.weight": torch.from_numpy(hw[i]).reshape(1, 1, 3, 3) for i in range(3)})
+        R16 = np.repeat((LINEAR_4 / np.float32(4.0)).reshape(1, 9), 16, 0)
+        P4 = np.repeat(LINEAR_4.reshape(1, 9), 16, 0)
+        eng = VCycleEngine([g.jac for g in grids], B=B, smoother="hjac", hnet=hnet, prolong="table", rtab=R16,
+                           r_scale=4.0, ptab=P4, p_scale=1.0)
+        eng.set_u(torch.zeros(1, 1, n + 1, n + 1, device="cuda"))
+        eng.set_f(grids[0].fnet(torch.ones(1, 1, n + 1, n + 1, device="cuda")))
+        r0 = float(torch.sqrt(eng.residual_sumsq().sum()).item())
+        hist = [x / r0 for x in eng.run(n_iter=8)]
+        out["cfg3_single_pattern"] = config_entry(
+            "config 3's cycle on one material: iso Poisson 4097^2, 12 levels, V(1,1), learned HNet smoother, 16-ch linear "
+            "R/P, w=[4,1], F=ones", eng, n, L, B, 0, hist, steps=10, reset=lambda: eng.u[0].zero_())
+        prev = mgfea.set_option("hstream_min_n", 0)  # the same cycle on the tile programs only
+        eng2 = VCycleEngine([g.jac for g in grids], B=B, smoother="hjac", hnet=hnet, prolong="table", rtab=R16,
+                            r_scale=4.0, ptab=P4, p_scale=1.0)
+        eng2.set_u(torch.zeros(1, 1, n + 1, n + 1, device="cuda"))
+        eng2.set_f(grids[0].fnet(torch.ones(1, 1, n + 1, n + 1, device="cuda")))
+        ms2, _ = time_engine(eng2, 10, reset=lambda: eng2.u[0].zero_())
+        mgfea.set_option("hstream_min_n", prev)
+        out["cfg3_single_pattern"]["ms_per_cycle_tile_programs_only"] = ms2
+        del eng, eng2, grids
+        torch.cuda.empty_cache()
     for tag, n in (("cfg4_1gpu", 8192), ("cfg5_1gpu", 16384)):
         if tag in which:  # configs 4 / 5 on ONE GPU (the row-slab legs come from bench.py --gpus N): f = 0 model problem
             out[tag] = one_gpu_iso(n)
@@ -637,7 +666,7 @@ def run_ours(args):
         del eng
         prob._engines.clear()
         torch.cuda.empty_cache()
-        configs = secondary_configs(["cfg2", "cfg3", "cfg3_jacobi", "cfg4_1gpu", "cfg5_1gpu", "cfg5_two_phase_1gpu", "cfg5_element_1gpu"]
+        configs = secondary_configs(["cfg2", "cfg3", "cfg3_jacobi", "cfg3_single_pattern", "cfg4_1gpu", "cfg5_1gpu", "cfg5_two_phase_1gpu", "cfg5_element_1gpu"]
                                     if not args.configs else args.configs.split(","))
     cpu = cpu_baseline_sample(n, L) if (world == 1 and not args.no_cpu_baseline) else None
     line = {"metric": METRIC, "value": cycles_per_s * dof / 1e9, "unit": "GDOF/s", "n_gpus": world, "steps": steps,
@@ -968,7 +997,7 @@ def main():
     ap.add_argument("--no-mixed", action="store_true", help="skip the fp64 defect-correction time-to-tolerance run")
     ap.add_argument("--n-multi", type=int, default=0, help="grid intervals for the row-slab run at N > 1 (default by N)")
     ap.add_argument("--no-configs", action="store_true", help="skip the secondary BASELINE configs block")
-    ap.add_argument("--configs", default="", help="comma list out of cfg2,cfg3,cfg3_jacobi,cfg4_1gpu,cfg5_1gpu,"
+    ap.add_argument("--configs", default="", help="comma list out of cfg2,cfg3,cfg3_jacobi,cfg3_single_pattern,cfg4_1gpu,cfg5_1gpu,"
                                                   "cfg5_two_phase_1gpu,cfg5_element_1gpu (default: all at N=1)")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the slab-vs-single-GPU bit-identity self-check")
     args = ap.parse_args()

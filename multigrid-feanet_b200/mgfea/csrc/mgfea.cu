@@ -735,8 +735,15 @@ struct Knobs {
     int stream_rmin = 2;      // auto: never shorter than this (short strips pay 5 halo rows + pipeline fill each)
     int stream_packed = 1;    // 1: FFMA2 (fma.rn.f32x2) streaming kernels, 0: scalar FFMA
     int stream_keys = 0;      // 1: two-phase levels also stream (see stream_eligible)
-    int hstream_min_n = 0;    // learned-smoother levels with N >= this use mg_hstream_kernel (0 = off: see DESIGN)
+    int hstream_min_n = 4097; // learned-smoother levels with N >= this use mg_hstream_kernel (0 = off).  Measured on
+                              // 4097^2 / 2049^2 single-pattern legs: 87 + 135 us vs 143 + 196 us (tile programs) at
+                              // 4097^2, 55 + 80 vs 58 + 58 us at 2049^2 (profiles/r02_hstream_legs.log)
+    int hstream_keys = 0;     // 1: two-phase levels too.  Bit-exact, but slower than the tile programs there (247 + 312
+                              // vs 164 + 208 us at 4097^2): the per-node variants of the unrolled blocks overflow the
+                              // instruction caches (ncu no_instruction 2.8 per issue, profiles/r02_ncu_hstream_*.json)
     int hstream_r = 0;        // rows per strip of mg_hstream_kernel (0 = auto)
+    int hstream_over = 1;     // auto: strips per resident warp (dynamic strip queue); > 1 costs more halo rows than
+                              // the better balance returns (87 -> 97 us at 2)
     int tile_minb2 = 1;       // 1: tile programs limited to <= 2 CTAs per SM by shared memory use the 128-register build
     int mid_min_n = 66;       // coarse levels with mid_min_n <= N <= mid_max_n use the latency-oriented mid kernels
     int mid_max_n = 513;      // (mid_max_n = 0 disables them; at 1025 the streaming DOWN kernel wins: profiles/)
@@ -757,6 +764,8 @@ struct Knobs {
         if (const char *e = getenv("MGFEA_STREAM_KEYS")) stream_keys = atoi(e);
         if (const char *e = getenv("MGFEA_HSTREAM_MIN_N")) hstream_min_n = atoi(e);
         if (const char *e = getenv("MGFEA_HSTREAM_R")) hstream_r = atoi(e);
+        if (const char *e = getenv("MGFEA_HSTREAM_OVER")) hstream_over = atoi(e);
+        if (const char *e = getenv("MGFEA_HSTREAM_KEYS")) hstream_keys = atoi(e);
         if (const char *e = getenv("MGFEA_TILE_MINB2")) tile_minb2 = atoi(e);
         if (const char *e = getenv("MGFEA_THREADS")) threads = atoi(e);
         threads = 256;
@@ -995,6 +1004,7 @@ static bool hstream_eligible(const Program &pr, bool keys, bool gbc) {
     const int minn = knobs().hstream_min_n;
     if (minn <= 0 || pr.g->N < minn || !(pr.g->N & 1)) return false;
     if (gbc || pr.reset_only || pr.ktab_override || pr.slab || pr.push) return false;
+    if (keys && !knobs().hstream_keys) return false;
     if (pr.smoother != MGFEA_SMOOTH_HJACOBI || pr.nsweeps != 1 || pr.nlayers != HS_NL || !pr.hw) return false;
     if (!pr.u_out || !pr.f) return false;
     if (pr.out_mode == OUT_RESTRICT && pr.prolong_mode == 0)
@@ -1022,21 +1032,22 @@ static int run_hstream(const Program &pr, cudaStream_t st) {
     DeviceScratch *scr = nullptr;
     int rc;
     if ((rc = get_scratch(1, &scr))) return rc;
-    // rows per strip: about one resident wave of warps (1 CTA x 8 warps per SM); a strip recomputes 10 halo rows, so
-    // never shorter than 32 rows
+    // rows per strip: about `hstream_over` strips per resident warp (1 CTA x HS_WARPS per SM; the kernel hands strips
+    // out dynamically), but at least 32 rows each (a strip recomputes 15 halo rows); strips of equal height, the last
+    // one of a column shorter
     int R = knobs().hstream_r;
     if (R <= 0) {
-        const double slots = (double)scr->num_sms * HS_WARPS;
-        const double rt = (double)(g->N - 1) * p.ntx * pr.B / slots;
-        R = 32;
-        for (int c = 32; c <= 512; c *= 2)
-            if (fabs((double)c - rt) < fabs((double)R - rt)) R = c;
+        const int slots = scr->num_sms * HS_WARPS * (knobs().hstream_over > 0 ? knobs().hstream_over : 1);
+        int nry = slots / (p.ntx * pr.B);
+        const int maxry = (g->N - 1) / 32 > 0 ? (g->N - 1) / 32 : 1;
+        if (nry > maxry) nry = maxry;
+        if (nry < 1) nry = 1;
+        R = 2 * ((g->N - 1 + 2 * nry - 1) / (2 * nry));
     }
     R &= ~1;
-    if (R < 2) R = 2;
-    while (R > g->N - 1) R /= 2;
+    if (R < 16) R = 16;
     p.R = R;
-    p.nry = (g->N - 1) / R;
+    p.nry = (g->N - 1 + R - 1) / R;
     if (p.nry < 1) p.nry = 1;
     p.nstrips = p.ntx * p.nry;
     const long long total = (long long)p.nstrips * pr.B;
@@ -1636,6 +1647,8 @@ int mgfea_set_option(const char *name, int value) {
     int *slot = nullptr;
     if (!strcmp(name, "hstream_min_n")) slot = &k.hstream_min_n;
     else if (!strcmp(name, "hstream_r")) slot = &k.hstream_r;
+    else if (!strcmp(name, "hstream_over")) slot = &k.hstream_over;
+    else if (!strcmp(name, "hstream_keys")) slot = &k.hstream_keys;
     else if (!strcmp(name, "stream_min_n")) slot = &k.stream_min_n;
     else if (!strcmp(name, "stream_keys")) slot = &k.stream_keys;
     else if (!strcmp(name, "mid_max_n")) slot = &k.mid_max_n;

@@ -1175,6 +1175,7 @@ def test_hstream_legs_bit_exact(O, case):
     B = 2 if case.endswith("b2") else 1
     keys = case.startswith("keys")
     prev = mgfea.set_option("hstream_min_n", 129)
+    prevk = mgfea.set_option("hstream_keys", 1)
     try:
         rng = np.random.default_rng(7)
         jit = lambda base: (base.reshape(1, 9) * (1.0 + 0.2 * rng.random((16, 9)))).astype(np.float32)
@@ -1216,3 +1217,45 @@ def test_hstream_legs_bit_exact(O, case):
                 assert abs(got[b] - (r[b] ** 2).sum()) <= 1e-6 * (r[b] ** 2).sum(), (case, c, b)
     finally:
         mgfea.set_option("hstream_min_n", prev)
+        mgfea.set_option("hstream_keys", prevk)
+
+
+def test_hstream_matches_tile_programs_at_4097():
+    """Default routing at full size: the finest level of a single-pattern 4097^2 HNet cycle runs on the streaming kernels
+    (hstream_min_n = 4097); switching them off (tile programs everywhere) must give the same solution bits after each
+    of two cycles, and the same interior residual sum of squares up to the order of the fp64 accumulation (per strip vs
+    per tile partial sums)"""
+    import mgfea
+    from FEANet.drivers import HNet
+    from FEANet.solver import LINEAR_4, VCycleEngine
+
+    n, L = 4096, 12
+    N = n + 1
+    hw = OPS["hnet_w"]
+    g = torch.Generator().manual_seed(5)
+    u0 = torch.randn(1, 1, N, N, generator=g)
+    f = torch.randn(1, 1, N, N, generator=g) * 1e-3
+    R16 = np.repeat((LINEAR_4 / np.float32(4.0)).reshape(1, 9), 16, 0)
+    P4 = np.repeat(LINEAR_4.reshape(1, 9), 16, 0)
+    out = {}
+    for thr in (4097, 0):
+        prev = mgfea.set_option("hstream_min_n", thr)
+        try:
+            hnet = HNet(3)
+            hnet.load_state_dict({f"convLayers.{i}.weight": torch.from_numpy(hw[i]).reshape(1, 1, 3, 3) for i in range(3)})
+            eng = VCycleEngine(iso_jacs(n, L), B=1, smoother="hjac", hnet=hnet, prolong="table", rtab=R16, r_scale=4.0,
+                               ptab=P4, p_scale=1.0)
+            eng.set_u(u0)
+            eng.set_f(f)
+            res = []
+            for _ in range(2):
+                eng.cycle()
+                res.append((host(eng.solution).copy(), float(host(eng.sumsq)[0])))
+            out[thr] = res
+            del eng
+            torch.cuda.empty_cache()
+        finally:
+            mgfea.set_option("hstream_min_n", prev)
+    for c in range(2):
+        assert np.array_equal(out[4097][c][0], out[0][c][0]), f"cycle {c + 1}: streaming vs tile solution differs"
+        assert abs(out[4097][c][1] - out[0][c][1]) <= 1e-9 * out[0][c][1], f"cycle {c + 1}: residual sum of squares differs"

@@ -21,6 +21,7 @@ hw = np.load(os.path.join(ROOT, "tests", "golden", "ops.npz"))["hnet_w"]
 out = {"kind": kind, "n": n}
 for thr in [int(a) for a in (sys.argv[3].split(",") if len(sys.argv) > 3 else ["0", "4097", "2049", "129"])]:
     mgfea.set_option("hstream_min_n", thr)
+    mgfea.set_option("hstream_keys", 1)
     if kind == "iso":
         grids = [SingleGrid(2, n // 2 ** l) for l in range(L)]
     else:
