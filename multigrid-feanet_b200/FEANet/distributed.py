@@ -701,6 +701,7 @@ class SlabMultigrid:
                 self._mixed_iter()
             res = float(torch.sqrt(peer.total.sum()).item())
             hist.append(res)
+            peer.check()
         peer.check()
         self.residuals = hist
         return hist
@@ -790,6 +791,7 @@ class SlabMultigrid:
                 self.cycle()
             c = self.ctl.cpu()
             done = bool(c[1].item())
+            self.peer.check()  # a timed-out wait ends the solve here: nothing runs on with stale ghost rows
         ncyc = int(c[0].item())
         hist = [float(math.sqrt(v)) for v in self.hist[:ncyc].cpu().numpy()]
         self._ctl_set(0, -1.0, 2 ** 31 - 1)  # back to free-running for cycle() users

@@ -735,7 +735,7 @@ struct Knobs {
     int stream_rmin = 2;      // auto: never shorter than this (short strips pay 5 halo rows + pipeline fill each)
     int stream_packed = 1;    // 1: FFMA2 (fma.rn.f32x2) streaming kernels, 0: scalar FFMA
     int stream_keys = 0;      // 1: two-phase levels also stream (see stream_eligible)
-    int hstream_min_n = 4097; // learned-smoother levels with N >= this use mg_hstream_kernel (0 = off).  Measured on
+    int hstream_min_n = 2049; // learned-smoother levels with N >= this use mg_hstream_kernel (0 = off).  Measured on
                               // 4097^2 / 2049^2 single-pattern legs: 87 + 135 us vs 143 + 196 us (tile programs) at
                               // 4097^2, 55 + 80 vs 58 + 58 us at 2049^2 (profiles/r02_hstream_legs.log)
     int hstream_keys = 0;     // 1: two-phase levels too.  Bit-exact, but slower than the tile programs there (247 + 312
@@ -2050,7 +2050,7 @@ int mgfea_p2p_exchange(const mgfea_xchg *x, void *stream) {
         clocks_per_s = khz > 0 ? (long long)khz * 1000 : 2000000000LL;
     }
     const char *te = getenv("MGFEA_P2P_TIMEOUT_S");
-    p.timeout_clocks = clocks_per_s * (te ? atoll(te) : 5);
+    p.timeout_clocks = clocks_per_s * (te ? atoll(te) : 20);  // generous: first-launch lazy init / graph capture skew
     const int grid = (x->mode & MGFEA_XCHG_PUSH) ? x->grid : 1;
     (void)total;
     trace_stamp((cudaStream_t)stream);

@@ -325,7 +325,6 @@ __global__ void __launch_bounds__(HS_WARPS * 32, 1) mg_hstream_kernel(const Stre
         // a-9, else the store of u' row y1-1 = a-7
         const int alast = (MODE == 0) ? (y1 == N ? N + 9 : y1 + 8) : (p.want_norm ? y1 + 8 : y1 + 6);
         const int K = alast - a0 + 1;
-        const bool edge = (a0 <= 0) || (alast >= N - 1) || (tx == 0) || ((tx + 1) * HS_TWI + 8 >= N - 1);
         const int klo = 0 - a0;               // first k whose row is inside the domain
         const int khi = min(N - a0, K);       // one past the last such k
         const float *pf_u = zero ? nullptr : ub + (long long)a0 * p.pitch;
@@ -404,9 +403,12 @@ __global__ void __launch_bounds__(HS_WARPS * 32, 1) mg_hstream_kernel(const Stre
             for (int j = 0; j < 3; ++j) ckw[j] = coarse_keys(I0 + j);
         }
 
-        auto block6 = [&](auto guard_tag, auto edge_tag, auto pf_tag, auto keyed_tag, int k0) {
-            constexpr bool GUARD = decltype(guard_tag)::value;
-            constexpr bool EDGE = decltype(edge_tag)::value;
+        // ONE block body for every strip position: pipeline-fill / store-range guards, domain masks and checked prefetches
+        // are always on.  Separate steady-state / guarded / edge instantiations (as in mg_stream2_kernel) execute ~15 % fewer
+        // instructions per row but were 18-21 % SLOWER here: at 233+ instructions per row step every additional variant in
+        // flight evicts the others from the instruction caches (profiles/r02_hstream_legs.log)
+        auto block6 = [&](auto keyed_tag, int k0) {
+            constexpr bool GUARD = true, EDGE = true;
             constexpr bool KEYED = decltype(keyed_tag)::value;
             const int blk = k0 / 6;
             // u / coarse ring: two halves; streamed row k0 + d, d in [0, 11]
@@ -428,7 +430,7 @@ __global__ void __launch_bounds__(HS_WARPS * 32, 1) mg_hstream_kernel(const Stre
                 if (GUARD && k >= K) break;
                 const int a = a0 + k;
                 if (KEYS && ph == 0) fetch_keys(k0 + 6);
-                prefetch(pf_tag, urow(ph + PD), frow(ph + PD));
+                prefetch(std::true_type{}, urow(ph + PD), frow(ph + PD));
                 asm volatile("cp.async.wait_group %0;" ::"n"(PD) : "memory");
                 // window slots before this step's producers write: oldest (ph+2)%3, middle ph%3, newest (ph+1)%3
                 // ================= stage 5: residual row a-9 from the u' rows of earlier steps
@@ -662,9 +664,6 @@ __global__ void __launch_bounds__(HS_WARPS * 32, 1) mg_hstream_kernel(const Stre
         };
         using T_ = std::true_type;
         using F_ = std::false_type;
-        // steady state: pipeline full (the coarse row (a-10)/2 of the block's first step is >= y0/2: k0 >= 18 covers both
-        // legs) and every store row inside [y0, y1) (u' row a-7 <= y1-1 at the block's last step)
-        const int ksteady = y1 + 6 - a0;
         int prev_key = -2, prev2_key = -2, prev_ckey = -2;  // uniform key of the previous blocks (-1 mixed, -2 none)
         for (int k0 = 0; k0 < K; k0 += 6) {
             bool fast = true;
@@ -706,16 +705,8 @@ __global__ void __launch_bounds__(HS_WARPS * 32, 1) mg_hstream_kernel(const Stre
                 }
                 fast = fast && cfast;
             }
-            const bool steady = (k0 >= 18 && k0 + 5 <= ksteady && k0 + 5 + PD < khi);
-            if (fast) {
-                if (edge) block6(T_{}, T_{}, T_{}, F_{}, k0);
-                else if (steady) block6(F_{}, F_{}, F_{}, F_{}, k0);
-                else block6(T_{}, F_{}, T_{}, F_{}, k0);
-            } else {
-                if (edge) block6(T_{}, T_{}, T_{}, T_{}, k0);
-                else if (steady) block6(F_{}, F_{}, F_{}, T_{}, k0);
-                else block6(T_{}, F_{}, T_{}, T_{}, k0);
-            }
+            if (fast) block6(F_{}, k0);
+            else block6(T_{}, k0);
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (MODE == 1 && p.want_norm) {
