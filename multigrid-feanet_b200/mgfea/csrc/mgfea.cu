@@ -735,6 +735,8 @@ struct Knobs {
     int stream_rmin = 2;      // auto: never shorter than this (short strips pay 5 halo rows + pipeline fill each)
     int stream_packed = 1;    // 1: FFMA2 (fma.rn.f32x2) streaming kernels, 0: scalar FFMA
     int stream_keys = 0;      // 1: two-phase levels also stream (see stream_eligible)
+    int stream_one_variant = 3;  // streaming legs that run ONE block variant: bit 0 = down legs, bit 1 = up legs, of levels
+    int stream_one_variant_max_n = 1 << 30;  // ... with N <= this
     int hstream_min_n = 2049; // learned-smoother levels with N >= this use mg_hstream_kernel (0 = off).  Measured on
                               // 4097^2 / 2049^2 single-pattern legs: 87 + 135 us vs 143 + 196 us (tile programs) at
                               // 4097^2, 55 + 80 vs 58 + 58 us at 2049^2 (profiles/r02_hstream_legs.log)
@@ -762,6 +764,8 @@ struct Knobs {
         if (const char *e = getenv("MGFEA_STREAM_RMIN")) stream_rmin = atoi(e);
         if (const char *e = getenv("MGFEA_STREAM_PACKED")) stream_packed = atoi(e);
         if (const char *e = getenv("MGFEA_STREAM_KEYS")) stream_keys = atoi(e);
+        if (const char *e = getenv("MGFEA_STREAM_ONE_VARIANT")) stream_one_variant = atoi(e);
+        if (const char *e = getenv("MGFEA_STREAM_ONE_VARIANT_MAX_N")) stream_one_variant_max_n = atoi(e);
         if (const char *e = getenv("MGFEA_HSTREAM_MIN_N")) hstream_min_n = atoi(e);
         if (const char *e = getenv("MGFEA_HSTREAM_R")) hstream_r = atoi(e);
         if (const char *e = getenv("MGFEA_HSTREAM_OVER")) hstream_over = atoi(e);
@@ -972,16 +976,29 @@ static int run_stream(const Program &pr, cudaStream_t st) {
         cudaFuncSetAttribute(mg_stream2_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         cudaFuncSetAttribute(mg_stream2_kernel<1, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         cudaFuncSetAttribute(mg_stream2_kernel<1, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(mg_stream2_kernel<0, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(mg_stream2_kernel<0, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(mg_stream2_kernel<1, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(mg_stream2_kernel<0, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(mg_stream2_kernel<0, true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(mg_stream2_kernel<1, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         configured = true;
     }
     if (keys && !pk) return MGFEA_EUNSUPPORTED;
+    // single-pattern legs: one block variant (see mg_stream2_kernel ONEV) unless switched off for this leg / level size
+    const bool onev = pk && !pr.push && (g->N <= knobs().stream_one_variant_max_n) &&
+                      ((knobs().stream_one_variant >> mode) & 1);
     if (mode == 0) {
         if (pr.u_in) {
-            if (keys) launch_pdl(mg_stream2_kernel<0, false, true>, grid, ST_WARPS * 32, smem, st, p);
+            if (keys && onev) launch_pdl(mg_stream2_kernel<0, false, true, false, true>, grid, ST_WARPS * 32, smem, st, p);
+            else if (keys) launch_pdl(mg_stream2_kernel<0, false, true>, grid, ST_WARPS * 32, smem, st, p);
+            else if (onev) launch_pdl(mg_stream2_kernel<0, false, false, false, true>, grid, ST_WARPS * 32, smem, st, p);
             else if (pk) launch_pdl(mg_stream2_kernel<0, false, false>, grid, ST_WARPS * 32, smem, st, p);
             else launch_pdl(mg_stream_kernel<0, false>, grid, ST_WARPS * 32, smem, st, p);
         } else {
-            if (keys) launch_pdl(mg_stream2_kernel<0, true, true>, grid, ST_WARPS * 32, smem, st, p);
+            if (keys && onev) launch_pdl(mg_stream2_kernel<0, true, true, false, true>, grid, ST_WARPS * 32, smem, st, p);
+            else if (keys) launch_pdl(mg_stream2_kernel<0, true, true>, grid, ST_WARPS * 32, smem, st, p);
+            else if (onev) launch_pdl(mg_stream2_kernel<0, true, false, false, true>, grid, ST_WARPS * 32, smem, st, p);
             else if (pk) launch_pdl(mg_stream2_kernel<0, true, false>, grid, ST_WARPS * 32, smem, st, p);
             else launch_pdl(mg_stream_kernel<0, true>, grid, ST_WARPS * 32, smem, st, p);
         }
@@ -990,7 +1007,9 @@ static int run_stream(const Program &pr, cudaStream_t st) {
         if (keys) launch_pdl(mg_stream2_kernel<1, false, true, true>, grid, ST_WARPS * 32, smem, st, p);
         else launch_pdl(mg_stream2_kernel<1, false, false, true>, grid, ST_WARPS * 32, smem, st, p);
     } else {
-        if (keys) launch_pdl(mg_stream2_kernel<1, false, true>, grid, ST_WARPS * 32, smem, st, p);
+        if (keys && onev) launch_pdl(mg_stream2_kernel<1, false, true, false, true>, grid, ST_WARPS * 32, smem, st, p);
+        else if (keys) launch_pdl(mg_stream2_kernel<1, false, true>, grid, ST_WARPS * 32, smem, st, p);
+        else if (onev) launch_pdl(mg_stream2_kernel<1, false, false, false, true>, grid, ST_WARPS * 32, smem, st, p);
         else if (pk) launch_pdl(mg_stream2_kernel<1, false, false>, grid, ST_WARPS * 32, smem, st, p);
         else launch_pdl(mg_stream_kernel<1, false>, grid, ST_WARPS * 32, smem, st, p);
     }
@@ -1651,6 +1670,8 @@ int mgfea_set_option(const char *name, int value) {
     else if (!strcmp(name, "hstream_keys")) slot = &k.hstream_keys;
     else if (!strcmp(name, "stream_min_n")) slot = &k.stream_min_n;
     else if (!strcmp(name, "stream_keys")) slot = &k.stream_keys;
+    else if (!strcmp(name, "stream_one_variant")) slot = &k.stream_one_variant;
+    else if (!strcmp(name, "stream_one_variant_max_n")) slot = &k.stream_one_variant_max_n;
     else if (!strcmp(name, "mid_max_n")) slot = &k.mid_max_n;
     else if (!strcmp(name, "mid_max_n_up")) slot = &k.mid_max_n_up;
     if (!slot) return MGFEA_EINVAL;

@@ -624,7 +624,12 @@ __device__ __noinline__ void stencil_rows_keys(const float *tab, const float *in
 // i.e. twice per strip that crosses the inclusion).  Blocks that touch the interface run a general variant whose
 // stencils look every weight up by the source node's key (out of line, so the fast path's code and registers are
 // those of the iso kernel).
-template <int MODE, bool ZERO_INIT, bool KEYS = false, bool PUSH = false>
+// ONEV: every strip runs the guarded / masked block variant.  ~15 % more instructions per row, but ONE loop body in the
+// instruction caches instead of up to four (first block, steady state, checked prefetch, drain), and a smaller kernel
+// image: the 4097^2 cycle went 0.1837 -> 0.1759 ms, nearly all of it on the short coarse launches, which start with
+// cold instruction caches (ncu no_instruction 0.5 - 1.05 stalled warps per issue at 2049^2 / 1025^2, 0.15 - 0.34 at 4097^2).
+// Found on mg_hstream_kernel, where three variants cost 18-21 %.
+template <int MODE, bool ZERO_INIT, bool KEYS = false, bool PUSH = false, bool ONEV = false>
 __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const StreamParams p) {
     extern __shared__ __align__(16) unsigned char st_smem[];
     __shared__ double red[ST_WARPS];
@@ -655,6 +660,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
         __syncthreads();
     }
     int kcur = 0;  // pattern whose weights sit in kw2 / inv2
+    constexpr bool zero = ZERO_INIT;  // (a run-time zero-guess case sharing level 0's kernel image measured slower: 0.180 vs 0.176 ms)
     pdl_wait();  // weights above are never written by a kernel; all field data is touched only after this point
     // the solve-control word is requested here but tested only after the first prefetches are in flight, so the two
     // memory round trips overlap (a finished solve returns before anything is stored)
@@ -707,7 +713,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
             if (gx + e >= 0 && gx + e <= N - 1) cdom |= 1u << e;
         }
         const bool col_ok = (gx >= 0) && (gx + 3 < p.pitch);  // the 16-byte chunk exists in memory
-        const float *ub = ZERO_INIT ? nullptr : p.u_in + (long long)b * p.plane + gx;
+        const float *ub = zero ? nullptr : p.u_in + (long long)b * p.plane + gx;
         const float *fb = p.f + (long long)b * p.plane + gx;
         float *uo = p.u_out + (long long)b * p.plane + gx;
         const int cxl = gx >> 1;  // coarse column of this lane's first fine column (gx is even)
@@ -716,7 +722,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
         float *fco = (MODE == 0) ? p.fc + (long long)b * p.plane_c + cxl : nullptr;
         const bool fc_ok = lane_int && cxl >= 0 && cxl <= p.Nc - 1;
         // a strip whose whole streamed box lies strictly inside the domain needs no masks at all
-        const bool edge = (y0 - 3 <= 0) || (y1 + 2 >= N - 1) || (tx == 0) || ((tx + 1) * ST_TWI + 4 >= N - 1);
+        const bool edge = ONEV || (y0 - 3 <= 0) || (y1 + 2 >= N - 1) || (tx == 0) || ((tx + 1) * ST_TWI + 4 >= N - 1);
 
         const int a0 = y0 - 3;  // first streamed row
         // last streamed row: y1+1 (u1 row y1 for the residual row y1-1); the last strip of the down leg goes one
@@ -726,7 +732,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
         // slot, and no validity test in steady-state blocks (CHECK = false)
         const int klo = max(0, p.row0) - a0;                    // first k whose row exists locally / in the domain
         const int khi = min(min(N, p.row0 + p.nrloc) - a0, K);  // one past the last such k
-        const float *pf_u = ZERO_INIT ? nullptr : ub + (long long)(a0 - p.row0) * p.pitch;
+        const float *pf_u = zero ? nullptr : ub + (long long)(a0 - p.row0) * p.pitch;
         const float *pf_f = fb + (long long)(a0 - p.row0) * p.pitch;
         int kpf = 0;
         // KEYS: keys of the 6 streamed rows keyrow0 .. keyrow0+5 join the current commit group
@@ -746,7 +752,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
             constexpr bool CHECK = decltype(check_tag)::value;
             const bool ok = !CHECK || (col_ok && kpf >= klo && kpf < khi);
             const int slot = slot_row * 32 + lane;
-            if (!ZERO_INIT) st_cp16(&ring_u[slot], ok ? (const void *)pf_u : (const void *)p.f, ok);
+            if (!zero) st_cp16(&ring_u[slot], ok ? (const void *)pf_u : (const void *)p.f, ok);
             st_cp16(&ring_f[slot], ok ? (const void *)pf_f : (const void *)p.f, ok);
             if (MODE == 1) {  // coarse row ceil(a/2): the row an even fine row copies / an odd row's lower partner
                 const int I = (a0 + kpf + 1) >> 1;
@@ -759,7 +765,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
                              : "memory");
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
-            if (!ZERO_INIT) pf_u += p.pitch;
+            if (!zero) pf_u += p.pitch;
             pf_f += p.pitch;
             ++kpf;
         };
@@ -813,7 +819,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
                 prefetch(pf_tag, ring_row(ph + PD));  // rows k-2..k stay in the ring (f is re-read)
                 asm volatile("cp.async.wait_group %0;" ::"n"(PD) : "memory");
                 const int slot = ring_row(ph) * 32 + lane;
-                float4 uv = ZERO_INIT ? make_float4(0.f, 0.f, 0.f, 0.f) : ring_u[slot];
+                float4 uv = zero ? make_float4(0.f, 0.f, 0.f, 0.f) : ring_u[slot];
                 const bool arow_in = !EDGE || (a >= 1 && a <= N - 2);
                 if (MODE == 1) {
                     // u += reset(bilinear P v_c) on row a.  fl(a/2 + b/2) is written fma(0.5, a, 0.5 b): halving is exact, so

@@ -14,6 +14,9 @@ from bench import model_u0, time_engine
 from FEANet.drivers import Multigrid
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+for kv in sys.argv[2:]:  # name=value kernel-selection options (mgfea_set_option)
+    k, v = kv.split("=")
+    mgfea.set_option(k, int(v))
 N = n + 1
 prob = Multigrid(n)
 eng = prob._engine(1, 1, 0, B=1)
@@ -48,5 +51,5 @@ def up_norm():
         mgfea.PROLONG_BILINEAR, None, 0, 0, 0.0, None, 1, 0, None, 0, eng.sumsq.data_ptr(), 1, mgfea.stream_ptr()))
 
 
-print(json.dumps({"lib": os.path.basename(mgfea.LIB_PATH), "n": n, "ms_per_cycle": ms, "runs": runs,
+print(json.dumps({"lib": os.path.basename(mgfea.LIB_PATH), "n": n, "options": sys.argv[2:], "ms_per_cycle": ms, "runs": runs,
                   "down_us": tk(down), "up_norm_us": tk(up_norm)}))
