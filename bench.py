@@ -94,12 +94,12 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-NCU_PROFILE = "r02_ncu_full_stream2.json"
+NCU_PROFILE = "r02_ncu_full_stream2_onev.json"
 
 
 def ncu_traffic(kernel_prefix, grid=None):
     """DRAM bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full` summary
-    (profiles/r01_ncu_full_stream2_final.json, captured with tools/cycle_profile.py on the same 4097^2 workload)"""
+    (profiles/NCU_PROFILE, captured with tools/ncu_cycle.py on the same 4097^2 workload)"""
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", NCU_PROFILE)))
         for name, d in prof.items():
@@ -567,7 +567,7 @@ def run_ours(args):
     alg_up = 4 * (2 * M0 + M1 + 3 * M0)         # prolong->correct (v_c,u -> u) + post-smooth (u,f -> u)
     alg_upn = alg_up + 4 * 2 * M0               # + convergence norm (u,f)
     # the dominant kernel = the longest launch of the cycle
-    kname, kms, kalg = "mg_stream2_kernel<1, 0, 0> level-0 up leg (prolong+correct+smooth+residual norm)", ms_upn, alg_upn
+    kname, kms, kalg = "mg_stream2_kernel<1, 0, 0, 0, 1> level-0 up leg (prolong+correct+smooth+residual norm)", ms_upn, alg_upn
     traffic = ncu_traffic("mg_stream2_kernel<1, 0", 280) if n == 4096 else None
     ach = kalg / (kms * 1e-3) / 1e9
     balg = algorithmic_bytes_per_cycle(n, L)
