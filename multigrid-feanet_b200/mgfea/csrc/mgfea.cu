@@ -736,7 +736,10 @@ struct Knobs {
     int stream_packed = 1;    // 1: FFMA2 (fma.rn.f32x2) streaming kernels, 0: scalar FFMA
     int stream_keys = 0;      // 1: two-phase levels also stream (see stream_eligible)
     int stream_one_variant = 3;  // streaming legs that run ONE block variant: bit 0 = down legs, bit 1 = up legs, of levels
-    int stream_one_variant_max_n = 1 << 30;  // ... with N <= this
+    int stream_one_variant_max_n = 1 << 30;     // ... with N <= this (down legs)
+    int stream_one_variant_up_max_n = 8193;     // ... and N <= this for the up legs: at 16385^2 the finest up leg is
+                                                // faster with its four variants (676 vs 721 us), the down leg is not
+                                                // (718 vs 685 us): profiles/r02_one_variant_sweep.log
     int hstream_min_n = 2049; // learned-smoother levels with N >= this use mg_hstream_kernel (0 = off).  Measured on
                               // 4097^2 / 2049^2 single-pattern legs: 87 + 135 us vs 143 + 196 us (tile programs) at
                               // 4097^2, 55 + 80 vs 58 + 58 us at 2049^2 (profiles/r02_hstream_legs.log)
@@ -766,6 +769,7 @@ struct Knobs {
         if (const char *e = getenv("MGFEA_STREAM_KEYS")) stream_keys = atoi(e);
         if (const char *e = getenv("MGFEA_STREAM_ONE_VARIANT")) stream_one_variant = atoi(e);
         if (const char *e = getenv("MGFEA_STREAM_ONE_VARIANT_MAX_N")) stream_one_variant_max_n = atoi(e);
+        if (const char *e = getenv("MGFEA_STREAM_ONE_VARIANT_UP_MAX_N")) stream_one_variant_up_max_n = atoi(e);
         if (const char *e = getenv("MGFEA_HSTREAM_MIN_N")) hstream_min_n = atoi(e);
         if (const char *e = getenv("MGFEA_HSTREAM_R")) hstream_r = atoi(e);
         if (const char *e = getenv("MGFEA_HSTREAM_OVER")) hstream_over = atoi(e);
@@ -986,8 +990,8 @@ static int run_stream(const Program &pr, cudaStream_t st) {
     }
     if (keys && !pk) return MGFEA_EUNSUPPORTED;
     // single-pattern legs: one block variant (see mg_stream2_kernel ONEV) unless switched off for this leg / level size
-    const bool onev = pk && !pr.push && (g->N <= knobs().stream_one_variant_max_n) &&
-                      ((knobs().stream_one_variant >> mode) & 1);
+    const bool onev = pk && !pr.push && ((knobs().stream_one_variant >> mode) & 1) &&
+                      g->N <= (mode == 0 ? knobs().stream_one_variant_max_n : knobs().stream_one_variant_up_max_n);
     if (mode == 0) {
         if (pr.u_in) {
             if (keys && onev) launch_pdl(mg_stream2_kernel<0, false, true, false, true>, grid, ST_WARPS * 32, smem, st, p);
@@ -1672,6 +1676,7 @@ int mgfea_set_option(const char *name, int value) {
     else if (!strcmp(name, "stream_keys")) slot = &k.stream_keys;
     else if (!strcmp(name, "stream_one_variant")) slot = &k.stream_one_variant;
     else if (!strcmp(name, "stream_one_variant_max_n")) slot = &k.stream_one_variant_max_n;
+    else if (!strcmp(name, "stream_one_variant_up_max_n")) slot = &k.stream_one_variant_up_max_n;
     else if (!strcmp(name, "mid_max_n")) slot = &k.mid_max_n;
     else if (!strcmp(name, "mid_max_n_up")) slot = &k.mid_max_n_up;
     if (!slot) return MGFEA_EINVAL;
