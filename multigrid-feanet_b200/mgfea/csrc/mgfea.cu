@@ -990,8 +990,11 @@ static int run_stream(const Program &pr, cudaStream_t st) {
     }
     if (keys && !pk) return MGFEA_EUNSUPPORTED;
     // single-pattern legs: one block variant (see mg_stream2_kernel ONEV) unless switched off for this leg / level size
+    // (the size limit is on the launch's work: a row slab of a 16385^2 level is a small launch)
+    const long long onev_lim = mode == 0 ? knobs().stream_one_variant_max_n : knobs().stream_one_variant_up_max_n;
+    const long long onev_rows = pr.slab ? (pr.own1 - pr.own0) : g->N;
     const bool onev = pk && !pr.push && ((knobs().stream_one_variant >> mode) & 1) &&
-                      g->N <= (mode == 0 ? knobs().stream_one_variant_max_n : knobs().stream_one_variant_up_max_n);
+                      onev_rows * (long long)g->N <= onev_lim * onev_lim;
     if (mode == 0) {
         if (pr.u_in) {
             if (keys && onev) launch_pdl(mg_stream2_kernel<0, false, true, false, true>, grid, ST_WARPS * 32, smem, st, p);
