@@ -752,13 +752,15 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
             constexpr bool CHECK = decltype(check_tag)::value;
             const bool ok = !CHECK || (col_ok && kpf >= klo && kpf < khi);
             const int slot = slot_row * 32 + lane;
-            if (!zero) st_cp16(&ring_u[slot], ok ? (const void *)pf_u : (const void *)p.f, ok);
-            st_cp16(&ring_f[slot], ok ? (const void *)pf_f : (const void *)p.f, ok);
+            // a copy of ZERO source bytes reads nothing (the destination is zero-filled), so the running pointers are
+            // passed as they are for rows / columns outside the arrays: no pointer select per row
+            if (!zero) st_cp16(&ring_u[slot], pf_u, ok);
+            st_cp16(&ring_f[slot], pf_f, ok);
             if (MODE == 1) {  // coarse row ceil(a/2): the row an even fine row copies / an odd row's lower partner
                 const int I = (a0 + kpf + 1) >> 1;
                 const int lI = I - p.crow0;
                 const bool okc = !CHECK || (ccol_ok && (I >= 0) && (I < p.Nc) && (lI >= 0) && (lI < p.nrc) && kpf < K);
-                const void *src = okc ? (const void *)(cbp + (long long)lI * p.pitch_c) : (const void *)p.f;
+                const void *src = (const void *)(cbp + (long long)lI * p.pitch_c);
                 const uint32_t sz = okc ? 8u : 0u;
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(&ring_c[slot])), "l"(src),
                              "r"(sz)
@@ -827,7 +829,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
                     // instruction less per value (the up leg is FMA-pipe bound)
                     const float2 cv = ring_c[slot];
                     const float c2 = __shfl_down_sync(0xffffffffu, cv.x, 1);
-                    if (!EDGE || (a >= 0 && a <= N - 1)) {
+                    {  // rows outside the domain too: their coarse rows are zero-filled and u + e is reset to zero below
                         float4 e;
                         if ((ph & 1) != 0) {  // k odd <=> a even (a0 is odd): copy / horizontal average of coarse row a/2
                             vt[0] = cv.x;
@@ -857,12 +859,13 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
                                 e.w = __fmaf_rn(0.5f, tb, __fmul_rn(0.5f, bb));
                             }
                         }
-                        if (EDGE) e = mask4(e, arow_in ? cin : 0u);  // fine level's reset_boundary of the correction
+                        // (the fine level's reset_boundary of the correction, and the zeroing of the columns beyond the
+                        // domain, are both subsumed by the sweep's own reset_boundary of u + e just below: interior nodes
+                        // see the unmasked e, every other node is set to zero there)
                         uv.x = __fadd_rn(uv.x, e.x);
                         uv.y = __fadd_rn(uv.y, e.y);
                         uv.z = __fadd_rn(uv.z, e.z);
                         uv.w = __fadd_rn(uv.w, e.w);
-                        if (EDGE) uv = mask4(uv, cdom);
                     }
                 }
                 // reset_boundary of the sweep's input (ring -> 0, outside stays 0)
@@ -936,16 +939,18 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
                         unpack2(rlo, r.x, r.y);
                         unpack2(rhi, r.z, r.w);
                         if (MODE == 1) {
-                            if (p.want_norm && lane_int && (!GUARD || (yr >= y0 && yr < y1)) &&
-                                (!EDGE || (yr >= 1 && yr <= N - 2))) {
+                            if (p.want_norm) {
                                 // squares of the lane's 4 columns summed in fp32 (fixed order), rows in fp64: one
-                                // F2F + DADD per row instead of eight FP64-pipe instructions
+                                // F2F + DADD per row instead of eight FP64-pipe instructions; the row / lane conditions
+                                // select the addend instead of branching around it
+                                const bool nok = lane_int && (!GUARD || (yr >= y0 && yr < y1)) &&
+                                                 (!EDGE || (yr >= 1 && yr <= N - 2));
                                 const float4 q = EDGE ? mask4(r, cin) : r;
                                 float s4 = __fmul_rn(q.x, q.x);
                                 s4 = __fmaf_rn(q.y, q.y, s4);
                                 s4 = __fmaf_rn(q.z, q.z, s4);
                                 s4 = __fmaf_rn(q.w, q.w, s4);
-                                part += (double)s4;
+                                part += nok ? (double)s4 : 0.0;
                             }
                         } else {
                             // restriction, fed row by row in the chain's own order (row-major taps): no window of residual
