@@ -737,9 +737,10 @@ struct Knobs {
     int stream_keys = 0;      // 1: two-phase levels also stream (see stream_eligible)
     int stream_one_variant = 3;  // streaming legs that run ONE block variant: bit 0 = down legs, bit 1 = up legs, of levels
     int stream_one_variant_max_n = 1 << 30;     // ... with N <= this (down legs)
-    int stream_one_variant_up_max_n = 8193;     // ... and N <= this for the up legs: at 16385^2 the finest up leg is
-                                                // faster with its four variants (676 vs 721 us), the down leg is not
-                                                // (718 vs 685 us): profiles/r02_one_variant_sweep.log
+    int stream_one_variant_up_max_n = 1 << 30;  // ... and N <= this for the up legs (with the masked body everywhere the
+                                                // 16385^2 up leg was slower than its four variants, 721 vs 676 us; with
+                                                // the unmasked body for interior strips it is not: 658 us,
+                                                // profiles/r02_one_variant_sweep.log)
     int hstream_min_n = 2049; // learned-smoother levels with N >= this use mg_hstream_kernel (0 = off).  Measured on
                               // 4097^2 / 2049^2 single-pattern legs: 87 + 135 us vs 143 + 196 us (tile programs) at
                               // 4097^2, 55 + 80 vs 58 + 58 us at 2049^2 (profiles/r02_hstream_legs.log)

@@ -624,11 +624,14 @@ __device__ __noinline__ void stencil_rows_keys(const float *tab, const float *in
 // i.e. twice per strip that crosses the inclusion).  Blocks that touch the interface run a general variant whose
 // stencils look every weight up by the source node's key (out of line, so the fast path's code and registers are
 // those of the iso kernel).
-// ONEV: every strip runs the guarded / masked block variant.  ~15 % more instructions per row, but ONE loop body in the
-// instruction caches instead of up to four (first block, steady state, checked prefetch, drain), and a smaller kernel
-// image: the 4097^2 cycle went 0.1837 -> 0.1759 ms, nearly all of it on the short coarse launches, which start with
-// cold instruction caches (ncu no_instruction 0.5 - 1.05 stalled warps per issue at 2049^2 / 1025^2, 0.15 - 0.34 at 4097^2).
-// Found on mg_hstream_kernel, where three variants cost 18-21 %.
+// ONEV: a strip runs ONE block body from its first row to its last -- the guarded one (pipeline-fill guards, store-range
+// predicates, checked prefetches), with the domain masks for the strips on the domain edge and without them for the
+// others -- instead of switching between up to four per-phase instantiations (first block, steady state, checked
+// prefetch, drain).  More instructions per row, but one loop body per warp in the instruction caches and a kernel image
+// of 30-50 KB instead of 107-143 KB: the 4097^2 cycle went 0.1837 -> 0.1759 ms with the masked body everywhere, -> 0.1677
+// with the redundant masks removed and the unmasked body for interior strips; most of it on the short coarse launches,
+// which start with cold instruction caches (ncu no_instruction 0.5 - 1.05 stalled warps per issue at 2049^2 / 1025^2,
+// 0.15 - 0.34 at 4097^2).  Found on mg_hstream_kernel, where three variants cost 18-21 %.
 template <int MODE, bool ZERO_INIT, bool KEYS = false, bool PUSH = false, bool ONEV = false>
 __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const StreamParams p) {
     extern __shared__ __align__(16) unsigned char st_smem[];
@@ -722,7 +725,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
         float *fco = (MODE == 0) ? p.fc + (long long)b * p.plane_c + cxl : nullptr;
         const bool fc_ok = lane_int && cxl >= 0 && cxl <= p.Nc - 1;
         // a strip whose whole streamed box lies strictly inside the domain needs no masks at all
-        const bool edge = ONEV || (y0 - 3 <= 0) || (y1 + 2 >= N - 1) || (tx == 0) || ((tx + 1) * ST_TWI + 4 >= N - 1);
+        const bool edge = (y0 - 3 <= 0) || (y1 + 2 >= N - 1) || (tx == 0) || ((tx + 1) * ST_TWI + 4 >= N - 1);
 
         const int a0 = y0 - 3;  // first streamed row
         // last streamed row: y1+1 (u1 row y1 for the residual row y1-1); the last strip of the down leg goes one
@@ -1005,6 +1008,8 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
         if (!KEYS) {
             if (edge) {
                 for (; k0 < K; k0 += 6) block6(T_{}, T_{}, T_{}, F_{}, k0);
+            } else if (ONEV) {  // one body for the whole strip: guards and checked prefetches on, no masks
+                for (; k0 < K; k0 += 6) block6(T_{}, F_{}, T_{}, F_{}, k0);
             } else {
                 block6(T_{}, F_{}, T_{}, F_{}, 0);
                 // steady state: no pipeline / store-range guards; prefetches unchecked while every prefetched row exists
