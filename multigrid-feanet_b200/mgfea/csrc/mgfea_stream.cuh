@@ -1045,7 +1045,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 2) mg_stream2_kernel(const Stre
                     kcur = bkey;
                 }
                 if (edge) block6(T_{}, T_{}, T_{}, F_{}, k0);
-                else if (k0 == 0) block6(T_{}, F_{}, T_{}, F_{}, k0);
+                else if (ONEV || k0 == 0) block6(T_{}, F_{}, T_{}, F_{}, k0);
                 else if (k0 + 5 <= K - 4 && k0 + 5 + PD < khi) block6(F_{}, F_{}, F_{}, F_{}, k0);
                 else if (k0 + 5 <= K - 4) block6(F_{}, F_{}, T_{}, F_{}, k0);
                 else block6(T_{}, F_{}, T_{}, F_{}, k0);
