@@ -94,7 +94,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-NCU_PROFILE = "r02_ncu_full_stream2_onev.json"
+NCU_PROFILE = "r02_ncu_full_stream2_final.json"
 
 
 def ncu_traffic(kernel_prefix, grid=None):
