@@ -170,22 +170,31 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // The per-tile program (see mgfea_tile.cuh).  EDGE tiles carry the default-BC / domain masks, interior tiles do not.
-template <bool KEYS, bool GBC, bool EDGE>
+// PROG: the program is a compile-time constant (the image then holds only the stages it runs; the generic image is
+// ~275 KB and the small launches of a cycle spend most of their time fetching it: ncu no_instruction 5-6 stalled warps
+// per issue on the levels <= 1025^2 of BASELINE config 3).  0 = generic (everything from TileParams);
+// 1 / 3 = one HNet / Jacobi sweep, residual, restriction (the down legs of the learned / two-phase cycle);
+// 2 / 4 = table prolongation + correction, one HNet / Jacobi sweep, optional residual norm (the up legs).
+template <bool KEYS, bool GBC, bool EDGE, int PROG = 0>
 __device__ __forceinline__ void run_tile(TileCtx &c, Tables &T, const RegW &W, const TileParams &p, int t) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float *W1 = c.W1, *W2 = c.W2, *W3 = c.W3;
     int d = 0;
     float *cur = c.U;
-    if (p.prolong_mode) {
-        stage_prolong<GBC, EDGE>(c, T, p, c.U);
+    constexpr int PM = (PROG == 1 || PROG == 3) ? 0 : ((PROG == 2 || PROG == 4) ? 3 : -1);
+    const int prolong_mode = (PM >= 0) ? PM : p.prolong_mode;
+    const int nsweeps = PROG ? 1 : p.nsweeps;
+    const int smoother = (PROG == 1 || PROG == 2) ? 1 : ((PROG == 3 || PROG == 4) ? 0 : p.smoother);
+    if (prolong_mode) {
+        stage_prolong<GBC, EDGE, PM>(c, T, p, c.U);
         __syncthreads();
     }
-    if (p.nsweeps == 0 && p.smoother == 2) {  // reset_boundary only
+    if (PROG == 0 && nsweeps == 0 && smoother == 2) {  // reset_boundary only
         stage_reset<GBC>(c, cur, cur, 0, p.BH);
         __syncthreads();
     }
-    for (int sw = 0; sw < p.nsweeps; ++sw) {
-        if (p.smoother == 0) {
+    for (int sw = 0; sw < nsweeps; ++sw) {
+        if (smoother == 0) {
             if (GBC || (EDGE && sw == 0)) {
                 stage_reset<GBC>(c, cur, cur, d, p.BH - d);
                 __syncthreads();
@@ -221,15 +230,16 @@ __device__ __forceinline__ void run_tile(TileCtx &c, Tables &T, const RegW &W, c
         }
     }
     if (p.store_u) stage_store_u(c, p, cur);
-    if (p.out_mode == OUT_RESIDUAL) {
+    const int out_mode = (PROG == 1 || PROG == 3) ? (int)OUT_RESTRICT : p.out_mode;  // PROG 2 / 4: NONE or NORM
+    if (PROG == 0 && out_mode == OUT_RESIDUAL) {
         stage_out<KEYS, OUT_RESIDUAL, EDGE>(c, T, W, p, cur, nullptr, d + 1, p.BH - d - 1);
-    } else if (p.out_mode == OUT_KU) {
+    } else if (PROG == 0 && out_mode == OUT_KU) {
         stage_out<KEYS, OUT_KU, EDGE>(c, T, W, p, cur, nullptr, d + 1, p.BH - d - 1);
-    } else if (p.out_mode == OUT_RESTRICT) {
+    } else if ((PROG == 0 || PROG == 1 || PROG == 3) && out_mode == OUT_RESTRICT) {
         stage_out<KEYS, OUT_RESTRICT, EDGE>(c, T, W, p, cur, c.F, d + 1, p.BH - d - 1);
         __syncthreads();
         stage_restrict<KEYS, EDGE>(c, T, W, p, c.F);
-    } else if (p.out_mode == OUT_NORM) {
+    } else if ((PROG == 0 || PROG == 2 || PROG == 4) && out_mode == OUT_NORM) {
         double part = stage_out<KEYS, OUT_NORM, EDGE>(c, T, W, p, cur, nullptr, d + 1, p.BH - d - 1);
         part = warp_sum(part);
         if (lane == 0) T.red[warp] = part;
@@ -245,7 +255,7 @@ __device__ __forceinline__ void run_tile(TileCtx &c, Tables &T, const RegW &W, c
 
 // MINB: resident CTAs per SM the register budget is cut for.  Programs whose shared-memory carve-up admits only two
 // CTAs (HNet temporaries) get the 128-register build (no spills) instead of the 85-register one.
-template <bool KEYS, bool GBC, int MINB = MGFEA_MINBLOCKS>
+template <bool KEYS, bool GBC, int MINB = MGFEA_MINBLOCKS, int PROG = 0>
 __global__ void __launch_bounds__(NTHREADS, MINB) mg_tile_kernel(const __grid_constant__ TileMaps maps,
                                                            const TileParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -360,9 +370,9 @@ __global__ void __launch_bounds__(NTHREADS, MINB) mg_tile_kernel(const __grid_co
         }
         // ---- program
         if (c.touches_edge)
-            run_tile<KEYS, GBC, true>(c, T, W, p, t);
+            run_tile<KEYS, GBC, true, PROG>(c, T, W, p, t);
         else
-            run_tile<KEYS, GBC, false>(c, T, W, p, t);
+            run_tile<KEYS, GBC, false, PROG>(c, T, W, p, t);
         // generic-proxy accesses to this stage's buffers are done; order them before the next TMA write into it
         fence_proxy_async_smem();
         __syncthreads();
@@ -751,6 +761,7 @@ struct Knobs {
     int hstream_over = 1;     // auto: strips per resident warp (dynamic strip queue); > 1 costs more halo rows than
                               // the better balance returns (87 -> 97 us at 2)
     int tile_minb2 = 1;       // 1: tile programs limited to <= 2 CTAs per SM by shared memory use the 128-register build
+    int tile_prog = 1;        // 1: specialised tile-kernel images for the legs of the two-phase table-transfer cycles
     int mid_min_n = 66;       // coarse levels with mid_min_n <= N <= mid_max_n use the latency-oriented mid kernels
     int mid_max_n = 513;      // (mid_max_n = 0 disables them; at 1025 the streaming DOWN kernel wins: profiles/)
     int mid_max_n_up = 1025;  // the up leg stays ahead one level longer
@@ -776,6 +787,7 @@ struct Knobs {
         if (const char *e = getenv("MGFEA_HSTREAM_OVER")) hstream_over = atoi(e);
         if (const char *e = getenv("MGFEA_HSTREAM_KEYS")) hstream_keys = atoi(e);
         if (const char *e = getenv("MGFEA_TILE_MINB2")) tile_minb2 = atoi(e);
+        if (const char *e = getenv("MGFEA_TILE_PROG")) tile_prog = atoi(e);
         if (const char *e = getenv("MGFEA_THREADS")) threads = atoi(e);
         threads = 256;
         if (th < 8 || th > 64 || (th & 1)) th = 32;
@@ -788,16 +800,16 @@ static Knobs &knobs_mut() {
 }
 static const Knobs &knobs() { return knobs_mut(); }
 
-template <bool KEYS, bool GBC, int MINB>
+template <bool KEYS, bool GBC, int MINB, int PROG = 0>
 static cudaError_t launch_tile_(const TileMaps &maps, const TileParams &p, int grid, size_t smem, cudaStream_t st) {
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(mg_tile_kernel<KEYS, GBC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             232448);
+        cudaError_t e = cudaFuncSetAttribute(mg_tile_kernel<KEYS, GBC, MINB, PROG>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) return e;
         configured = 232448;
     }
-    cudaError_t le = launch_pdl(mg_tile_kernel<KEYS, GBC, MINB>, grid, NTHREADS, smem, st, maps, p);
+    cudaError_t le = launch_pdl(mg_tile_kernel<KEYS, GBC, MINB, PROG>, grid, NTHREADS, smem, st, maps, p);
     if (le != cudaSuccess) return le;
     g_launches.fetch_add(1);
     return cudaGetLastError();
@@ -808,6 +820,24 @@ static cudaError_t launch_tile(const TileMaps &maps, const TileParams &p, int gr
     (void)threads;
     // at most two CTAs fit anyway: take the registers (MGFEA_TILE_MINB2=2 forces the 128-register build everywhere)
     const bool two = ((232448 / smem) <= 2 && knobs().tile_minb2) || knobs().tile_minb2 == 2;
+    // specialised images for the legs of the two-phase cycles with table transfer operators (see run_tile)
+    if (KEYS && !GBC && knobs().tile_prog && p.nsweeps == 1 && p.store_u) {
+        int prog = 0;
+        if (p.prolong_mode == 0 && p.out_mode == OUT_RESTRICT) prog = (p.smoother == 1) ? 1 : (p.smoother == 0 ? 3 : 0);
+        else if (p.prolong_mode == 3 && (p.out_mode == OUT_NONE || p.out_mode == OUT_NORM))
+            prog = (p.smoother == 1) ? 2 : (p.smoother == 0 ? 4 : 0);
+        if (two) {
+            if (prog == 1) return launch_tile_<true, false, 2, 1>(maps, p, grid, smem, st);
+            if (prog == 2) return launch_tile_<true, false, 2, 2>(maps, p, grid, smem, st);
+            if (prog == 3) return launch_tile_<true, false, 2, 3>(maps, p, grid, smem, st);
+            if (prog == 4) return launch_tile_<true, false, 2, 4>(maps, p, grid, smem, st);
+        } else {
+            if (prog == 1) return launch_tile_<true, false, MGFEA_MINBLOCKS, 1>(maps, p, grid, smem, st);
+            if (prog == 2) return launch_tile_<true, false, MGFEA_MINBLOCKS, 2>(maps, p, grid, smem, st);
+            if (prog == 3) return launch_tile_<true, false, MGFEA_MINBLOCKS, 3>(maps, p, grid, smem, st);
+            if (prog == 4) return launch_tile_<true, false, MGFEA_MINBLOCKS, 4>(maps, p, grid, smem, st);
+        }
+    }
     return two ? launch_tile_<KEYS, GBC, 2>(maps, p, grid, smem, st)
                : launch_tile_<KEYS, GBC, MGFEA_MINBLOCKS>(maps, p, grid, smem, st);
 }
@@ -1678,6 +1708,7 @@ int mgfea_set_option(const char *name, int value) {
     else if (!strcmp(name, "hstream_keys")) slot = &k.hstream_keys;
     else if (!strcmp(name, "stream_min_n")) slot = &k.stream_min_n;
     else if (!strcmp(name, "stream_keys")) slot = &k.stream_keys;
+    else if (!strcmp(name, "tile_prog")) slot = &k.tile_prog;
     else if (!strcmp(name, "stream_one_variant")) slot = &k.stream_one_variant;
     else if (!strcmp(name, "stream_one_variant_max_n")) slot = &k.stream_one_variant_max_n;
     else if (!strcmp(name, "stream_one_variant_up_max_n")) slot = &k.stream_one_variant_up_max_n;

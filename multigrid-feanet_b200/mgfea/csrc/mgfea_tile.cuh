@@ -595,10 +595,11 @@ __device__ __forceinline__ void stage_restrict(const TileCtx &c, const Tables &T
 
 // ---------------------------------------------------------------------------------------------------------
 // Prolongation + correction on all box rows: U += scale * P(vc)   (coarse box VC, coarse keys KC)
-template <bool GBC, bool EDGE>
+template <bool GBC, bool EDGE, int PM = -1>
 __device__ __forceinline__ void stage_prolong(const TileCtx &c, const Tables &T, const TileParams &p, float *U) {
+    const int prolong_mode = (PM >= 0) ? PM : p.prolong_mode;  // PM: the specialised programs of mg_tile_kernel
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (!EDGE && !GBC && p.prolong_mode == 1) {
+    if (!EDGE && !GBC && prolong_mode == 1) {
         // interior tile, bilinear: every node of the box is an interior node of the domain, no masks needed
         const float *vbase = c.VC + c.vcofs + 2 * lane;  // 8-byte aligned (vcofs is even)
         const bool seq = p.prolong_seq != 0;
@@ -646,7 +647,7 @@ __device__ __forceinline__ void stage_prolong(const TileCtx &c, const Tables &T,
     const unsigned int cin = col_interior_bits(c, lane);
     const unsigned int cdom = col_domain_bits(c, lane);
     const int cc = 2 * lane;  // coarse box column of fine box column 4*lane (gx0 even, cx0 = gx0/2)
-    const bool table = (p.prolong_mode == 3);
+    const bool table = (prolong_mode == 3);
     const bool pkeys = table && (p.ptab_n > 1) && (c.KC != nullptr);
     for (int r = warp; r < c.BH; r += NWARPS) {
         const int gy = c.gy0 + r;
