@@ -766,11 +766,13 @@ struct Knobs {
     int mid_max_n = 513;      // (mid_max_n = 0 disables them; at 1025 the streaming DOWN kernel wins: profiles/)
     int mid_max_n_up = 1025;  // the up leg stays ahead one level longer
     int mid_max_tiles = 1200; // ... and only while tiles x samples stay within about two waves
+    int mid_keys = 1;         // 1: two-phase / table-transfer levels use mg_midk_kernel in the same size range
     Knobs() {
         if (const char *e = getenv("MGFEA_MID_MIN_N")) mid_min_n = atoi(e);
         if (const char *e = getenv("MGFEA_MID_MAX_N")) mid_max_n = mid_max_n_up = atoi(e);
         if (const char *e = getenv("MGFEA_MID_MAX_N_UP")) mid_max_n_up = atoi(e);
         if (const char *e = getenv("MGFEA_MID_MAX_TILES")) mid_max_tiles = atoi(e);
+        if (const char *e = getenv("MGFEA_MID_KEYS")) mid_keys = atoi(e);
         if (const char *e = getenv("MGFEA_TH")) th = atoi(e);
         if (const char *e = getenv("MGFEA_STAGES")) stages = atoi(e);
         if (const char *e = getenv("MGFEA_CTAS")) ctas = atoi(e);
@@ -1199,8 +1201,24 @@ static int mid_mode(const Program &pr, bool keys, bool gbc) {
     const Knobs &k = knobs();
     const int mmax = k.mid_max_n > k.mid_max_n_up ? k.mid_max_n : k.mid_max_n_up;
     if (mmax <= 0 || pr.g->N < k.mid_min_n || pr.g->N > mmax) return -1;
-    if (keys || gbc || pr.reset_only || pr.ktab_override || pr.slab) return -1;
+    if (gbc || pr.reset_only || pr.ktab_override || pr.slab) return -1;
     if (pr.smoother != MGFEA_SMOOTH_JACOBI || pr.nsweeps != 1 || !pr.u_out || !pr.f) return -1;
+    // two-phase meshes and / or table transfer operators: mg_midk_kernel (same tiles, per-node table lookups)
+    const bool tabR = pr.out_mode == OUT_RESTRICT && pr.rtab_n > 1;
+    const bool tabP = pr.prolong_mode == MGFEA_PROLONG_TABLE;
+    if (keys || tabR || tabP) {
+        if (!k.mid_keys) return -1;
+        const long long ntk = (pr.g->N + MID_T - 1) / MID_T;
+        if (ntk * ntk * pr.B > k.mid_max_tiles) return -1;
+        if (pr.out_mode == OUT_RESTRICT && pr.prolong_mode == 0 && pr.u_in == nullptr && pr.rtab &&
+            (pr.rtab_n == 1 || (keys && pr.rtab_n == pr.g->npat)))
+            return pr.g->N <= k.mid_max_n_up ? 2 : -1;
+        if (pr.out_mode == OUT_NONE && pr.u_in != nullptr && pr.vc && pr.gc &&
+            (pr.prolong_mode == MGFEA_PROLONG_BILINEAR ||
+             (tabP && pr.ptab && (pr.ptab_n == 1 || (pr.gc->keys && pr.ptab_n == pr.gc->npat)))))
+            return pr.g->N <= k.mid_max_n_up ? 3 : -1;
+        return -1;
+    }
     // latency-oriented kernels: only while the whole launch is a wave or two of tiles (a batch of 64 samples turns
     // the same level into a throughput problem, where the streaming kernels execute fewer instructions per node)
     const long long nt = (pr.g->N + MID_T - 1) / MID_T;
@@ -1232,6 +1250,28 @@ static int run_mid(const Program &pr, int mode, cudaStream_t st) {
     p.invd = g->invd;
     p.Nc = (g->N - 1) / 2 + 1;
     p.ctl = pr.ctl;
+    const bool keyed = mode >= 2;  // mg_midk_kernel
+    if (keyed) {
+        mode -= 2;
+        p.npat = g->npat;
+        if (g->keys && !pr.ignore_keys) {
+            if (g->key_pitch & 15) return MGFEA_EALIGN;
+            p.keys = g->keys;
+            p.key_pitch = g->key_pitch;
+        }
+        p.rtab_n = pr.rtab_n;
+        p.prolong_mode = pr.prolong_mode;
+        p.ptab = pr.ptab;
+        p.ptab_n = pr.ptab_n;
+        p.p_has_scale = pr.p_has_scale;
+        p.p_scale = pr.p_scale;
+        p.p_scale_dev = pr.p_scale_dev;
+        if (mode == 1 && pr.prolong_mode == MGFEA_PROLONG_TABLE && pr.ptab_n > 1 && pr.gc && pr.gc->keys) {
+            if (pr.gc->key_pitch & 15) return MGFEA_EALIGN;
+            p.keys_c = pr.gc->keys;
+            p.key_pitch_c = pr.gc->key_pitch;
+        }
+    }
     if (mode == 0) {
         if (!pr.fc || !pr.rtab) return MGFEA_EINVAL;
         p.fc = pr.fc;
@@ -1241,7 +1281,8 @@ static int run_mid(const Program &pr, int mode, cudaStream_t st) {
         p.r_has_scale = pr.r_has_scale;
         p.r_scale = pr.r_scale;
         p.r_scale_dev = pr.r_scale_dev;
-        launch_pdl(mg_mid_kernel<0>, (int)total, MID_THREADS, 0, st, p);
+        if (keyed) launch_pdl(mg_midk_kernel<0>, (int)total, MID_THREADS, 0, st, p);
+        else launch_pdl(mg_mid_kernel<0>, (int)total, MID_THREADS, 0, st, p);
     } else {
         if (!pr.vc || !pr.gc || pr.gc->N != p.Nc) return MGFEA_EINVAL;
         int rc = check_field(pr.vc, pr.gc->pitch, pr.gc->plane);
@@ -1250,7 +1291,8 @@ static int run_mid(const Program &pr, int mode, cudaStream_t st) {
         p.pitch_c = pr.gc->pitch;
         p.plane_c = pr.gc->plane;
         p.prolong_seq = (g->N <= 33);
-        launch_pdl(mg_mid_kernel<1>, (int)total, MID_THREADS, 0, st, p);
+        if (keyed) launch_pdl(mg_midk_kernel<1>, (int)total, MID_THREADS, 0, st, p);
+        else launch_pdl(mg_mid_kernel<1>, (int)total, MID_THREADS, 0, st, p);
     }
     g_launches.fetch_add(1);
     return (int)cudaGetLastError();
@@ -1709,6 +1751,7 @@ int mgfea_set_option(const char *name, int value) {
     else if (!strcmp(name, "stream_min_n")) slot = &k.stream_min_n;
     else if (!strcmp(name, "stream_keys")) slot = &k.stream_keys;
     else if (!strcmp(name, "tile_prog")) slot = &k.tile_prog;
+    else if (!strcmp(name, "mid_keys")) slot = &k.mid_keys;
     else if (!strcmp(name, "stream_one_variant")) slot = &k.stream_one_variant;
     else if (!strcmp(name, "stream_one_variant_max_n")) slot = &k.stream_one_variant_max_n;
     else if (!strcmp(name, "stream_one_variant_up_max_n")) slot = &k.stream_one_variant_up_max_n;
