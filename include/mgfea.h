@@ -83,7 +83,8 @@ const char *mgfea_error_string(int code);
 int mgfea_set_loader(int use_tma);
 /* kernel-selection thresholds (the MGFEA_* environment knobs of csrc/mgfea.cu at run time; changing one invalidates
  * captured CUDA graphs): "hstream_min_n", "hstream_keys", "hstream_r", "hstream_over", "stream_min_n", "stream_keys",
- * "stream_one_variant", "stream_one_variant_max_n", "stream_one_variant_up_max_n", "mid_max_n", "mid_max_n_up".
+ * "stream_one_variant", "stream_one_variant_max_n", "stream_one_variant_up_max_n", "tile_prog", "mid_keys",
+ * "mid_max_n", "mid_max_n_up".
  * Returns the previous value (>= 0), MGFEA_EINVAL for an unknown name. */
 int mgfea_set_option(const char *name, int value);
 /* profiling aid: while buf != NULL a one-thread kernel stores %globaltimer (ns) into buf[i++] before and after every
