@@ -754,7 +754,8 @@ struct Knobs {
     int hstream_min_n = 2049; // learned-smoother levels with N >= this use mg_hstream_kernel (0 = off).  Measured on
                               // 4097^2 / 2049^2 single-pattern legs: 87 + 135 us vs 143 + 196 us (tile programs) at
                               // 4097^2, 55 + 80 vs 58 + 58 us at 2049^2 (profiles/r02_hstream_legs.log)
-    int hstream_keys = 0;     // 1: two-phase levels too.  Bit-exact, but slower than the tile programs there (247 + 312
+    int hstream_keys = 0;     // 1: two-phase levels too; 2: also the layer-free (Jacobi) variant with key-indexed table
+                              // transfer (config 3 / Jacobi: 0.45 - 0.48 vs 0.32 ms/cycle, so off).  Bit-exact, but slower than the tile programs there (247 + 312
                               // vs 164 + 208 us at 4097^2): the per-node variants of the unrolled blocks overflow the
                               // instruction caches (ncu no_instruction 2.8 per issue, profiles/r02_ncu_hstream_*.json)
     int hstream_r = 0;        // rows per strip of mg_hstream_kernel (0 = auto)
@@ -1064,7 +1065,19 @@ static bool hstream_eligible(const Program &pr, bool keys, bool gbc) {
     if (minn <= 0 || pr.g->N < minn || !(pr.g->N & 1)) return false;
     if (gbc || pr.reset_only || pr.ktab_override || pr.slab || pr.push) return false;
     if (keys && !knobs().hstream_keys) return false;
-    if (pr.smoother != MGFEA_SMOOTH_HJACOBI || pr.nsweeps != 1 || pr.nlayers != HS_NL || !pr.hw) return false;
+    if (pr.nsweeps != 1) return false;
+    if (pr.smoother == MGFEA_SMOOTH_JACOBI) {
+        // the Jacobi sweep through the same pipeline (NOL): only what no other streaming kernel does -- two-phase levels
+        // with key-indexed restriction tables / table prolongation
+        if (!keys || knobs().hstream_keys < 2) return false;
+        if (pr.out_mode == OUT_RESTRICT && pr.prolong_mode == 0) {
+            if (pr.rtab_n <= 1) return false;
+        } else if (pr.prolong_mode != MGFEA_PROLONG_TABLE) {
+            return false;
+        }
+    } else if (pr.smoother != MGFEA_SMOOTH_HJACOBI || pr.nlayers != HS_NL || !pr.hw) {
+        return false;
+    }
     if (!pr.u_out || !pr.f) return false;
     if (pr.out_mode == OUT_RESTRICT && pr.prolong_mode == 0)
         return pr.fc && pr.rtab && (pr.rtab_n == 1 || (keys && pr.rtab_n == pr.g->npat));
@@ -1184,7 +1197,16 @@ static int run_hstream(const Program &pr, cudaStream_t st) {
     }
     const bool ptab = (mode == 1) && (pr.prolong_mode == MGFEA_PROLONG_TABLE);
     cudaError_t le;
-    if (mode == 0) le = keys ? launch_pdl(mg_hstream_kernel<0, true>, grid, HS_WARPS * 32, smem, st, p)
+    if (pr.smoother == MGFEA_SMOOTH_JACOBI) {  // NOL instantiations (keys, table transfer: see hstream_eligible)
+        static bool cfg2 = false;
+        if (!cfg2) {
+            cudaFuncSetAttribute(mg_hstream_kernel<0, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs_smem_bytes(0, true));
+            cudaFuncSetAttribute(mg_hstream_kernel<1, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs_smem_bytes(1, true));
+            cfg2 = true;
+        }
+        le = (mode == 0) ? launch_pdl(mg_hstream_kernel<0, true, false, true>, grid, HS_WARPS * 32, smem, st, p)
+                         : launch_pdl(mg_hstream_kernel<1, true, true, true>, grid, HS_WARPS * 32, smem, st, p);
+    } else if (mode == 0) le = keys ? launch_pdl(mg_hstream_kernel<0, true>, grid, HS_WARPS * 32, smem, st, p)
                              : launch_pdl(mg_hstream_kernel<0, false>, grid, HS_WARPS * 32, smem, st, p);
     else if (ptab) le = keys ? launch_pdl(mg_hstream_kernel<1, true, true>, grid, HS_WARPS * 32, smem, st, p)
                              : launch_pdl(mg_hstream_kernel<1, false, true>, grid, HS_WARPS * 32, smem, st, p);

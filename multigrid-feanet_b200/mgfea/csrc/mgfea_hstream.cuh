@@ -201,7 +201,9 @@ __device__ __forceinline__ void hs_stencil_keys(const float *tab4, const float *
 // MODE 1: up leg   (bilinear / table prolongation + correction, HNet sweep, store u, optional interior residual norm)
 // PTAB (up leg): table prolongation (ConvTranspose taps) instead of bilinear -- compile-time: both variants inline in every
 // unrolled block overflowed the instruction caches (ncu: no_instruction was the top stall of the up leg)
-template <int MODE, bool KEYS, bool PTAB = false>
+// NOL: no HNet layers -- the plain weighted-Jacobi sweep (u' = J) through the same pipeline: the two-phase Jacobi cycle
+// with key-indexed table restriction / prolongation, which mg_stream2_kernel<.., KEYS> (single table, bilinear) cannot do
+template <int MODE, bool KEYS, bool PTAB = false, bool NOL = false>
 __global__ void __launch_bounds__(HS_WARPS * 32, 1) mg_hstream_kernel(const StreamParams p) {
     extern __shared__ __align__(16) unsigned char st_smem[];
     __shared__ double red[HS_WARPS];
@@ -229,7 +231,7 @@ __global__ void __launch_bounds__(HS_WARPS * 32, 1) mg_hstream_kernel(const Stre
         tw[q] = (gtab != nullptr) ? gtab[q] : 0.0f;
 #pragma unroll
         for (int l = 0; l < HS_NL; ++l) {
-            const float h = p.hw[9 * l + q];
+            const float h = NOL ? 0.0f : p.hw[9 * l + q];
             h2[l][q] = pack2(h, h);
         }
     }
@@ -522,11 +524,15 @@ __global__ void __launch_bounds__(HS_WARPS * 32, 1) mg_hstream_kernel(const Stre
                 // ================= stage 4: HNet layer 3 row a-7, u' = J + h, store; new u' row into Bw
                 if (!GUARD || k >= 8) {
                     const int y = a - 7;
-                    u64 lo, hi;
-                    stencil_rowsS(h2[2], X2[(ph + 2) % 3], X2[ph % 3], X2[(ph + 1) % 3], lo, hi);  // rows a-8, a-7, a-6
-                    if (EDGE) hs_maskS(lo, hi, (y >= 1 && y <= N - 2) ? cin : 0u);
                     const ulonglong2 jv = *reinterpret_cast<const ulonglong2 *>(&ring_j[ph * 32 + lane]);  // J row a-7: (A, B)
-                    const u64 ul = add2(jv.x, lo), uh = add2(jv.y, hi);
+                    u64 ul = jv.x, uh = jv.y;
+                    if (!NOL) {
+                        u64 lo, hi;
+                        stencil_rowsS(h2[2], X2[(ph + 2) % 3], X2[ph % 3], X2[(ph + 1) % 3], lo, hi);  // rows a-8, a-7, a-6
+                        if (EDGE) hs_maskS(lo, hi, (y >= 1 && y <= N - 2) ? cin : 0u);
+                        ul = add2(jv.x, lo);
+                        uh = add2(jv.y, hi);
+                    }
                     float o0, o1, o2, o3;
                     unpack2(ul, o0, o2);
                     unpack2(uh, o1, o3);
@@ -535,14 +541,14 @@ __global__ void __launch_bounds__(HS_WARPS * 32, 1) mg_hstream_kernel(const Stre
                     Bw[(ph + 2) % 3] = widenS(ul, uh);
                 }
                 // ================= stage 3: layer 2 row a-5
-                if (!GUARD || k >= 6) {
+                if (!NOL && (!GUARD || k >= 6)) {
                     u64 lo, hi;
                     stencil_rowsS(h2[1], X1[(ph + 2) % 3], X1[ph % 3], X1[(ph + 1) % 3], lo, hi);  // rows a-6, a-5, a-4
                     if (EDGE) hs_maskS(lo, hi, (a - 5 >= 1 && a - 5 <= N - 2) ? cin : 0u);
                     X2[(ph + 2) % 3] = widenS(lo, hi);
                 }
                 // ================= stage 2: layer 1 row a-3
-                if (!GUARD || k >= 4) {
+                if (!NOL && (!GUARD || k >= 4)) {
                     u64 lo, hi;
                     stencil_rowsS(h2[0], X0[(ph + 2) % 3], X0[ph % 3], X0[(ph + 1) % 3], lo, hi);  // rows a-4, a-3, a-2
                     if (EDGE) hs_maskS(lo, hi, (a - 3 >= 1 && a - 3 <= N - 2) ? cin : 0u);
@@ -651,8 +657,10 @@ __global__ void __launch_bounds__(HS_WARPS * 32, 1) mg_hstream_kernel(const Stre
                     u64 jl = fma2(plo, one2, m.p[1]), jh = fma2(phi, one2, m.p[2]);
                     if (EDGE) hs_maskS(jl, jh, (y >= 1 && y <= N - 2) ? cin : 0u);
                     *reinterpret_cast<ulonglong2 *>(&ring_j[ph * 32 + lane]) = make_ulonglong2(jl, jh);
-                    const u64 xl = sub2(jl, EDGE ? rawp_lo : m.p[1]), xh = sub2(jh, EDGE ? rawp_hi : m.p[2]);
-                    X0[(ph + 2) % 3] = widenS(xl, xh);
+                    if (!NOL) {
+                        const u64 xl = sub2(jl, EDGE ? rawp_lo : m.p[1]), xh = sub2(jh, EDGE ? rawp_hi : m.p[2]);
+                        X0[(ph + 2) % 3] = widenS(xl, xh);
+                    }
                 }
                 st_u += p.pitch;
                 if (MODE == 0 && (ph & 1) == 0) st_c += p.pitch_c;

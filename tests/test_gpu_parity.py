@@ -1159,7 +1159,7 @@ def test_multigrid_training_step_matches_reference_autograd(n):
 
 
 # ------------------------------------------------------------------- learned-smoother streaming kernels (mg_hstream_kernel)
-@pytest.mark.parametrize("case", ["keys_table", "keys_bilinear", "iso_table1", "keys_table_b2"])
+@pytest.mark.parametrize("case", ["keys_table", "keys_bilinear", "iso_table1", "keys_table_b2", "keys_table_jac"])
 def test_hstream_legs_bit_exact(O, case):
     """The register-chained HNet legs (csrc/mgfea_hstream.cuh; levels with N >= 129) against the oracle, bit for bit,
     after every cycle: two-phase circle (per-node lookups where the interface crosses a block of rows), 16 DISTINCT
@@ -1174,8 +1174,10 @@ def test_hstream_legs_bit_exact(O, case):
     N = n + 1
     B = 2 if case.endswith("b2") else 1
     keys = case.startswith("keys")
+    jac = case.endswith("_jac")  # the layer-free variant of the kernel: Jacobi sweep, key-indexed table transfer
     prev = mgfea.set_option("hstream_min_n", 129)
-    prevk = mgfea.set_option("hstream_keys", 1)
+    prevk = mgfea.set_option("hstream_keys", 2 if jac else 1)
+    prevm = mgfea.set_option("mid_keys", 0 if jac else 1)  # (the keyed mid kernel would take these level sizes first)
     try:
         rng = np.random.default_rng(7)
         jit = lambda base: (base.reshape(1, 9) * (1.0 + 0.2 * rng.random((16, 9)))).astype(np.float32)
@@ -1197,9 +1199,9 @@ def test_hstream_legs_bit_exact(O, case):
             levels = O.make_levels(n, L)
         bil = case == "keys_bilinear"
         kw = dict(prolong="bilinear") if bil else dict(prolong="table", ptab=P16, p_scale=1.0)
-        eng = VCycleEngine(jacs, B=B, smoother="hjac", hnet=hnet, rtab=R16, r_scale=4.0, **kw)
+        eng = VCycleEngine(jacs, B=B, smoother="jac" if jac else "hjac", hnet=hnet, rtab=R16, r_scale=4.0, **kw)
         okw = dict(prolong="bilinear") if bil else dict(prolong="table", ptab=P16, p_scale=1.0)
-        cfg = O.CycleCfg(smoother="hjac", hw=hw, rtab=R16, r_scale=4.0, **okw)
+        cfg = O.CycleCfg(smoother="jac" if jac else "hjac", hw=hw, rtab=R16, r_scale=4.0, **okw)
         g = torch.Generator().manual_seed(11)
         u0 = torch.randn(B, 1, N, N, generator=g)
         f = torch.randn(B, 1, N, N, generator=g) * 1e-2
@@ -1218,6 +1220,7 @@ def test_hstream_legs_bit_exact(O, case):
     finally:
         mgfea.set_option("hstream_min_n", prev)
         mgfea.set_option("hstream_keys", prevk)
+        mgfea.set_option("mid_keys", prevm)
 
 
 def test_hstream_matches_tile_programs_at_4097():
