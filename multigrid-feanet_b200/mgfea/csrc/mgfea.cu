@@ -765,7 +765,9 @@ struct Knobs {
     int tile_prog = 1;        // 1: specialised tile-kernel images for the legs of the two-phase table-transfer cycles
     int mid_min_n = 66;       // coarse levels with mid_min_n <= N <= mid_max_n use the latency-oriented mid kernels
     int mid_max_n = 513;      // (mid_max_n = 0 disables them; at 1025 the streaming DOWN kernel wins: profiles/)
-    int mid_max_n_up = 1025;  // the up leg stays ahead one level longer
+    int mid_max_n_up = 513;   // (the up leg stayed ahead one level longer, to 1025, until the streaming kernels ran one
+                              // block body per strip: 4097^2 cycle 0.1672 -> 0.1655 ms with 513)
+    int mid_keys_max_n = 1025; // size range of the keyed mid kernel (its alternative is the generic tile kernel)
     int mid_max_tiles = 1200; // ... and only while tiles x samples stay within about two waves
     int mid_keys = 1;         // 1: two-phase / table-transfer levels use mg_midk_kernel in the same size range
     Knobs() {
@@ -1221,7 +1223,8 @@ static int run_hstream(const Program &pr, cudaStream_t st) {
 // mid-level kernels (mgfea_mid.cuh): eligibility + launch
 static int mid_mode(const Program &pr, bool keys, bool gbc) {
     const Knobs &k = knobs();
-    const int mmax = k.mid_max_n > k.mid_max_n_up ? k.mid_max_n : k.mid_max_n_up;
+    int mmax = k.mid_max_n > k.mid_max_n_up ? k.mid_max_n : k.mid_max_n_up;
+    if (k.mid_keys && k.mid_keys_max_n > mmax) mmax = k.mid_keys_max_n;
     if (mmax <= 0 || pr.g->N < k.mid_min_n || pr.g->N > mmax) return -1;
     if (gbc || pr.reset_only || pr.ktab_override || pr.slab) return -1;
     if (pr.smoother != MGFEA_SMOOTH_JACOBI || pr.nsweeps != 1 || !pr.u_out || !pr.f) return -1;
@@ -1234,11 +1237,11 @@ static int mid_mode(const Program &pr, bool keys, bool gbc) {
         if (ntk * ntk * pr.B > k.mid_max_tiles) return -1;
         if (pr.out_mode == OUT_RESTRICT && pr.prolong_mode == 0 && pr.u_in == nullptr && pr.rtab &&
             (pr.rtab_n == 1 || (keys && pr.rtab_n == pr.g->npat)))
-            return pr.g->N <= k.mid_max_n_up ? 2 : -1;
+            return pr.g->N <= k.mid_keys_max_n ? 2 : -1;
         if (pr.out_mode == OUT_NONE && pr.u_in != nullptr && pr.vc && pr.gc &&
             (pr.prolong_mode == MGFEA_PROLONG_BILINEAR ||
              (tabP && pr.ptab && (pr.ptab_n == 1 || (pr.gc->keys && pr.ptab_n == pr.gc->npat)))))
-            return pr.g->N <= k.mid_max_n_up ? 3 : -1;
+            return pr.g->N <= k.mid_keys_max_n ? 3 : -1;
         return -1;
     }
     // latency-oriented kernels: only while the whole launch is a wave or two of tiles (a batch of 64 samples turns
