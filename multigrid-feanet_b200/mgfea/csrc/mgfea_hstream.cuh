@@ -11,9 +11,11 @@
 //           -> r row a-9 (= f - K u') -> down leg: coarse f row (a-10)/2 (restriction) | up leg: sum r^2
 //
 // Every stage works on the rows its producer finished in EARLIER steps (a software pipeline: two rows of lag per stage), so
-// the five stencils of a step are independent instruction streams -- with one dependent chain through all stages a warp
-// needed ~1200 cycles per row (profiles/r02_cfg3iso_hstream_launches_v1.csv).  The data dependences are those of the
-// operators: column halo 8 (112 interior columns per strip), 6 rows above / 4 below a strip recomputed.
+// the five stencils of a step are independent instruction streams.  (Measured: not faster than one dependent chain per
+// step, 85.7 vs 85.8 us on the 4097^2 down leg -- ptxas interleaves consecutive steps of the unrolled block anyway -- but
+// it costs no registers either: profiles/r02_hstream_legs.log.)  The data dependences are those of the operators: column
+// halo 8 (112 interior columns per strip), 6 rows above / 4 below a strip; with the pipeline lags a strip of R rows
+// streams R + 15.
 // u, f (and the key map) are read from HBM once, u' is written once; the three HNet layers never leave the registers.
 // Weights of the current material pattern sit in registers; blocks of 6 rows that a material interface crosses take a
 // per-node lookup variant (as in mg_stream2_kernel<.., KEYS>).
