@@ -151,3 +151,23 @@ def test_training_entry_points_exist():
     if not torch.cuda.is_available():
         with pytest.raises(mgfea.MgfeaError):
             mg(torch.zeros(1, 1, 9, 9))
+
+
+def test_set_option_names_documented_in_header():
+    """every kernel-selection option named in include/mgfea.h (mgfea_set_option) is accepted by the library, returns the
+    previous value and can be restored; an unknown name is MGFEA_EINVAL.  Pure host code: no GPU needed."""
+    import re
+
+    import mgfea
+
+    hdr = open(os.path.join(ROOT, "include", "mgfea.h")).read()
+    block = hdr[hdr.index("kernel-selection thresholds"):hdr.index("int mgfea_set_option")]
+    names = re.findall(r'"([a-z_0-9]+)"', block)
+    assert len(names) >= 12 and "hstream_min_n" in names and "stream_one_variant" in names
+    L = mgfea.lib()
+    for n in names:
+        prev = L.mgfea_set_option(n.encode(), 7)
+        assert prev >= 0, n
+        assert L.mgfea_set_option(n.encode(), prev) == 7, n
+    assert L.mgfea_set_option(b"no_such_option", 1) == -1
+    assert L.mgfea_set_option(None, 1) == -1
