@@ -1184,6 +1184,7 @@ static int run_hstream(const Program &pr, cudaStream_t st) {
     p.sumsq = pr.sumsq;
     p.hist = pr.hist;
     p.ctl = pr.ctl;
+    p.dyn_queue = (total > (long long)scr->num_sms * HS_WARPS) ? 1 : 0;  // more strips than resident warps
     const size_t smem = hs_smem_bytes(mode, keys);
     const long long ctas = (total + HS_WARPS - 1) / HS_WARPS;
     const int grid = (int)(ctas < scr->num_sms ? ctas : scr->num_sms);

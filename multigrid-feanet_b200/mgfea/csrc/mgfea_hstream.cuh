@@ -266,18 +266,23 @@ __global__ void __launch_bounds__(HS_WARPS * 32, 1) mg_hstream_kernel(const Stre
     float2 *ring_c = reinterpret_cast<float2 *>(ring_j + HS_JD * 32);
     unsigned int *ring_k = reinterpret_cast<unsigned int *>(st_smem + HS_WARPS * RF4 * 32 * 16) + warp * (HS_KD * 32);
 
-    // Strips are handed out dynamically (one atomic per strip): the strips a material interface runs through cost up to
-    // three times a single-pattern strip, edge strips ~1.3x, so a static assignment left the SMs idle half of the time
-    // (ncu: sm__cycles_active 48% of elapsed on the 4097^2 two-phase down leg).  The host cuts about two strips per
-    // resident warp; the queue words live next to the norm ticket and are reset by the last CTA to leave.
+    // Strip hand-out.  Static (strip s -> warp s mod resident warps) when the host cuts one strip per resident warp (the
+    // default).  Dynamic (one atomic per strip) when it cuts more (hstream_over > 1, two-phase meshes): the strips a
+    // material interface runs through cost up to three times a single-pattern strip, and a static assignment left the SMs
+    // idle half of the time (ncu: sm__cycles_active 48 % of elapsed on the 4097^2 two-phase down leg).  The queue words
+    // live next to the norm ticket in the per-device scratch and are reset by the last CTA to leave -- like the norm
+    // ticket they assume that the library's launches on one device are stream-ordered.
+    const bool dynq = p.dyn_queue != 0;
     unsigned int *queue = p.counter + 4, *leave = p.counter + 5;
-    auto next_strip = [&]() {
+    const int sstep = gridDim.x * HS_WARPS;
+    auto next_strip = [&](int prev) {
+        if (!dynq) return prev < 0 ? (int)(blockIdx.x * HS_WARPS + warp) : prev + sstep;
         int v = 0;
         if (lane == 0) v = (int)atomicAdd(queue, 1u);
         return __shfl_sync(0xffffffffu, v, 0);
     };
     const int total = p.nstrips * p.B;
-    for (int s = next_strip(); s < total; s = next_strip()) {
+    for (int s = next_strip(-1); s < total; s = next_strip(s)) {
         int b = 0, rem = s;
         if (p.B > 1) {
             b = __float2int_rz(__int2float_rn(s) * p.inv_nstrips);
@@ -725,11 +730,13 @@ __global__ void __launch_bounds__(HS_WARPS * 32, 1) mg_hstream_kernel(const Stre
         }
     }
 
-    __syncthreads();  // every warp of this CTA has taken its last strip number
-    if (threadIdx.x == 0 && atomicAdd(leave, 1u) == gridDim.x - 1) {
-        *queue = 0u;
-        *leave = 0u;
-        __threadfence();
+    if (dynq) {
+        __syncthreads();  // every warp of this CTA has taken its last strip number
+        if (threadIdx.x == 0 && atomicAdd(leave, 1u) == gridDim.x - 1) {
+            *queue = 0u;
+            *leave = 0u;
+            __threadfence();
+        }
     }
     if (solve_done) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");

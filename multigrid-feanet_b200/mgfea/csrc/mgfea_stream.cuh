@@ -99,6 +99,7 @@ struct StreamParams {
     const float *p_scale_dev;
     const unsigned char *keys_c;  // coarse level's key map (ptab_n > 1)
     int key_pitch_c;
+    int dyn_queue;                // strips handed out by an atomic queue (more than one strip per resident warp)
 };
 
 __device__ __forceinline__ double warp_sum_d(double v) {

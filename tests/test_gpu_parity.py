@@ -1159,7 +1159,8 @@ def test_multigrid_training_step_matches_reference_autograd(n):
 
 
 # ------------------------------------------------------------------- learned-smoother streaming kernels (mg_hstream_kernel)
-@pytest.mark.parametrize("case", ["keys_table", "keys_bilinear", "iso_table1", "keys_table_b2", "keys_table_jac"])
+@pytest.mark.parametrize("case", ["keys_table", "keys_bilinear", "iso_table1", "keys_table_b2", "keys_table_jac",
+                                  "keys_table_b8_dyn"])
 def test_hstream_legs_bit_exact(O, case):
     """The register-chained HNet legs (csrc/mgfea_hstream.cuh; levels with N >= 129) against the oracle, bit for bit,
     after every cycle: two-phase circle (per-node lookups where the interface crosses a block of rows), 16 DISTINCT
@@ -1172,12 +1173,14 @@ def test_hstream_legs_bit_exact(O, case):
 
     n, L = 512, 7
     N = n + 1
-    B = 2 if case.endswith("b2") else 1
+    B = 2 if case.endswith("b2") else (8 if "b8" in case else 1)
+    dyn = case.endswith("_dyn")  # 16-row strips x 8 samples: more strips than resident warps -> the atomic strip queue
     keys = case.startswith("keys")
     jac = case.endswith("_jac")  # the layer-free variant of the kernel: Jacobi sweep, key-indexed table transfer
     prev = mgfea.set_option("hstream_min_n", 129)
     prevk = mgfea.set_option("hstream_keys", 2 if jac else 1)
     prevm = mgfea.set_option("mid_keys", 0 if jac else 1)  # (the keyed mid kernel would take these level sizes first)
+    prevr = mgfea.set_option("hstream_r", 16 if dyn else 0)
     try:
         rng = np.random.default_rng(7)
         jit = lambda base: (base.reshape(1, 9) * (1.0 + 0.2 * rng.random((16, 9)))).astype(np.float32)
@@ -1221,6 +1224,7 @@ def test_hstream_legs_bit_exact(O, case):
         mgfea.set_option("hstream_min_n", prev)
         mgfea.set_option("hstream_keys", prevk)
         mgfea.set_option("mid_keys", prevm)
+        mgfea.set_option("hstream_r", prevr)
 
 
 def test_hstream_matches_tile_programs_at_4097():
